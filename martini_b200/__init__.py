@@ -1,0 +1,13 @@
+"""martini_b200 -- B200-native particle->datacube projection behind MARTINI's Python API.
+
+Scope: the work of ``Martini.insert_source_in_cube`` (prune, per-particle spectra, SPH kernel
+pixel integrals, per-pixel accumulation) as hand-written sm_100a CUDA kernels behind a C ABI
+(``include/martini_b200.h``).  See DESIGN.md.  There is no CPU fallback.
+"""
+
+__version__ = "0.1.0"
+
+from . import sph_kernels, spectral_models  # noqa: F401
+from .engine import Engine, KernelTable  # noqa: F401
+
+__all__ = ["Engine", "KernelTable", "sph_kernels", "spectral_models"]

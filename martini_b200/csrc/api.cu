@@ -1,0 +1,543 @@
+// C ABI of libmartini_b200.so -- see include/martini_b200.h for the contract.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernel_integrals.cuh"
+#include "plan.cuh"
+#include "project.cuh"
+#include "scan.cuh"
+#include "sort.cuh"
+
+namespace mtn {
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+// optional per-stage timing of mtn_project (CUDA events on the caller's stream)
+constexpr int N_STAGES = 6;  // emit, sort, items, project, reduce, finalize
+thread_local int g_timing = 0;
+thread_local int g_count_exec = 0;
+thread_local cudaEvent_t g_ev[N_STAGES + 1];
+thread_local bool g_ev_init = false;
+thread_local bool g_ev_valid = false;
+thread_local unsigned long long g_exec_counts[3] = {0, 0, 0};
+
+static void mark(int i, cudaStream_t st) {
+  if (!g_timing) return;
+  if (!g_ev_init) {
+    for (int k = 0; k <= N_STAGES; ++k) cudaEventCreate(&g_ev[k]);
+    g_ev_init = true;
+  }
+  cudaEventRecord(g_ev[i], st);
+}
+
+static int to_dev_table(const MtnKernelTable* t, KernelTableDev* d) {
+  if (!t || t->n < 1 || t->n > MTN_MAX_KERNELS) return fail(MTN_ERR_INVALID, "kernel table: bad n%s", "");
+  memset(d, 0, sizeof(*d));
+  d->n = t->n;
+  d->adaptive = t->adaptive;
+  for (int i = 0; i < t->n; ++i) {
+    const MtnKernelEntry& e = t->k[i];
+    if (e.kind < 0 || e.kind > MTN_KERNEL_QUARTICSPLINE)
+      return fail(MTN_ERR_INVALID, "kernel table: unknown kind%s %lld", "", (long long)e.kind);
+    d->kind[i] = e.kind;
+    d->valid_is_max[i] = e.valid_is_max;
+    d->rescale[i] = e.rescale;
+    d->size_in_fwhm[i] = e.size_in_fwhm;
+    d->valid_size[i] = e.valid_size;
+    d->truncate[i] = e.truncate;
+    d->norm[i] = e.norm;
+  }
+  return MTN_OK;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int make_geo(const MtnCube* c, Geo* g, int edges_increasing) {
+  if (!c || c->nx <= 0 || c->ny <= 0 || c->n_channels <= 0)
+    return fail(MTN_ERR_INVALID, "cube: bad shape%s", "");
+  if (c->x_lo < 0 || c->x_hi > c->nx || c->x_lo >= c->x_hi)
+    return fail(MTN_ERR_INVALID, "cube: bad slab rows%s", "");
+  if (c->spectrum != MTN_SPECTRUM_GAUSSIAN && c->spectrum != MTN_SPECTRUM_DIRACDELTA)
+    return fail(MTN_ERR_INVALID, "cube: unknown spectrum kind%s", "");
+  g->nx = c->nx;
+  g->ny = c->ny;
+  g->C = c->n_channels;
+  g->x_lo = c->x_lo;
+  g->x_hi = c->x_hi;
+  g->ntx = (c->x_hi - c->x_lo + TILE_X - 1) / TILE_X;
+  g->nty = (c->ny + TILE_Y - 1) / TILE_Y;
+  g->ncb = (c->n_channels + CB - 1) / CB;
+  const int64_t nb = (int64_t)g->ntx * g->nty * g->ncb;
+  if (nb >= (1ll << 31)) return fail(MTN_ERR_LIMIT, "cube: too many bricks%s", "");
+  g->n_bricks = (int)nb;
+  g->spectrum = c->spectrum;
+  g->edges_increasing = edges_increasing;
+  return MTN_OK;
+}
+
+static PlanIn make_plan_in(const MtnParticles* p, const MtnCube* c) {
+  PlanIn in;
+  in.n = p->n;
+  in.px = p->px;
+  in.py = p->py;
+  in.h_eff = p->h_eff;
+  in.sm_range = p->sm_range;
+  in.kernel_id = p->kernel_id;
+  in.v = p->v;
+  in.sigma = p->sigma;
+  in.sigma_scalar = p->sigma_scalar;
+  in.mHI = p->mHI;
+  in.mHI_scalar = p->mHI_scalar;
+  in.D = p->D;
+  in.D_scalar = p->D_scalar;
+  in.accept = p->accept;
+  in.edges = c->edges;
+  return in;
+}
+
+// plan scratch: [blk_kept | blk_pairs | totals(4 x u64) | edge probe (2 doubles)]
+struct PlanScratch {
+  int64_t nblk;
+  int64_t* blk_kept;
+  int64_t* blk_pairs;
+  unsigned long long* totals;
+};
+static size_t plan_scratch_layout(int64_t n, void* base, PlanScratch* s) {
+  const int64_t nblk = std::max<int64_t>(1, (n + PLAN_THREADS - 1) / PLAN_THREADS);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? (char*)base + off : nullptr;
+    off += align_up(bytes);
+    return p;
+  };
+  char* a = take(nblk * sizeof(int64_t));
+  char* b = take(nblk * sizeof(int64_t));
+  char* t = take(8 * sizeof(unsigned long long));
+  if (s) {
+    s->nblk = nblk;
+    s->blk_kept = (int64_t*)a;
+    s->blk_pairs = (int64_t*)b;
+    s->totals = (unsigned long long*)t;
+  }
+  return off;
+}
+
+// project workspace
+struct Workspace {
+  Record* records;
+  uint64_t* pairs_a;
+  uint64_t* pairs_b;
+  uint32_t* hist;
+  void* scan_temp;
+  uint32_t* brick_count;
+  uint32_t* brick_start;
+  uint32_t* counts;
+  uint32_t* multi;
+  uint32_t* ismulti;
+  uint32_t* scalars;  // [n_items, n_slots, n_multi, counter]
+  Item* items;
+  MultiBrick* multis;
+  double* partials;
+  int64_t max_items, max_multi, max_slots;
+};
+static size_t workspace_layout(int64_t n_kept, int64_t n_pairs, int64_t n_bricks, int64_t chunk,
+                               void* base, Workspace* w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? (char*)base + off : nullptr;
+    off += align_up(bytes ? bytes : 1);
+    return p;
+  };
+  const int64_t max_multi = n_pairs / chunk + 1;
+  const int64_t max_slots = 2 * (n_pairs / chunk) + 2;
+  const int64_t max_items = std::min<int64_t>(n_bricks, n_pairs) + n_pairs / chunk + 1;
+  Workspace ws;
+  ws.records = (Record*)take((size_t)n_kept * sizeof(Record));
+  ws.pairs_a = (uint64_t*)take((size_t)n_pairs * 8);
+  ws.pairs_b = (uint64_t*)take((size_t)n_pairs * 8);
+  ws.hist = (uint32_t*)take(sort_hist_bytes(n_pairs));
+  const size_t st = std::max(scan_temp_bytes(sort_num_chunks(n_pairs) * RADIX, 4),
+                             scan_temp_bytes(n_bricks, 4));
+  ws.scan_temp = take(st);
+  ws.brick_count = (uint32_t*)take((size_t)n_bricks * 4);
+  ws.brick_start = (uint32_t*)take((size_t)n_bricks * 4);
+  ws.counts = (uint32_t*)take((size_t)n_bricks * 4);
+  ws.multi = (uint32_t*)take((size_t)n_bricks * 4);
+  ws.ismulti = (uint32_t*)take((size_t)n_bricks * 4);
+  ws.scalars = (uint32_t*)take(64);
+  ws.items = (Item*)take((size_t)max_items * sizeof(Item));
+  ws.multis = (MultiBrick*)take((size_t)max_multi * sizeof(MultiBrick));
+  ws.partials = (double*)take((size_t)max_slots * PROJ_THREADS * CB * sizeof(double));
+  ws.max_items = max_items;
+  ws.max_multi = max_multi;
+  ws.max_slots = max_slots;
+  if (w) *w = ws;
+  return off;
+}
+
+static int64_t choose_chunk(int64_t n_pairs) {
+  // enough work items for ~8 rounds over 2 CTAs per SM, never smaller than 8 batches
+  const int64_t target = (int64_t)sm_count() * 2 * 8;
+  int64_t chunk = std::max<int64_t>(8 * PBATCH, (n_pairs + target - 1) / target);
+  return (chunk + PBATCH - 1) / PBATCH * PBATCH;
+}
+
+// FP64 FMA microbenchmark: 8 independent chains per thread, all in registers.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456) out[0] = s;  // never true; keeps the chains alive
+}
+
+__global__ void __launch_bounds__(256) probe_kernel_integral_kernel(
+    int kind, double truncate, double norm, int64_t n, const double* __restrict__ dx,
+    const double* __restrict__ dy, const double* __restrict__ h, double* __restrict__ w) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double hh = h[i];
+  w[i] = kernel_weight(kind, dx[i], dy[i], hh, 1.0 / (hh * hh), truncate, norm);
+}
+
+__global__ void __launch_bounds__(256) probe_spectra_kernel(
+    int spectrum, int64_t n, const double* __restrict__ v, const double* __restrict__ sigma,
+    double sigma_scalar, const double* __restrict__ amp, int C, const double* __restrict__ edges,
+    double* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * C) return;
+  const int64_t i = idx / C;
+  const int c = (int)(idx - i * C);
+  const double e0 = edges[c], e1 = edges[c + 1];
+  const double lo = fmin(e0, e1), hi = fmax(e0, e1);
+  const double inv_dv = 1.0 / fabs(e1 - e0);
+  double f;
+  if (spectrum == MTN_SPECTRUM_GAUSSIAN) {
+    const double inv_s = 1.0 / (1.4142135623730951 * (sigma ? sigma[i] : sigma_scalar));
+    f = (edge_erf(hi, v[i], inv_s) - edge_erf(lo, v[i], inv_s)) * (0.5 * amp[i] * inv_dv);
+  } else {
+    f = dirac_channel(lo, hi, v[i]) * (amp[i] * inv_dv);
+  }
+  out[idx] = f;
+}
+
+}  // namespace mtn
+
+using namespace mtn;
+
+extern "C" {
+
+int mtn_version(void) { return MTN_VERSION; }
+const char* mtn_last_error(void) { return g_err; }
+int mtn_last_launch_count(void) { return g_launches; }
+
+int mtn_device_info(int* sms, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  MTN_CUDA(cudaGetDevice(&dev));
+  if (sms) MTN_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major) MTN_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_minor) MTN_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return MTN_OK;
+}
+
+int mtn_smoothing_setup(int64_t n, const double* sm_length, const MtnKernelTable* table,
+                        uint8_t* kernel_id_out, uint8_t* valid_out, double* sm_range_out,
+                        double* h_eff_out, void* stream) {
+  KernelTableDev t;
+  if (int rc = to_dev_table(table, &t)) return rc;
+  if (n < 0 || (n > 0 && !sm_length)) return fail(MTN_ERR_INVALID, "smoothing_setup: bad input%s", "");
+  if (n == 0) return MTN_OK;
+  smoothing_setup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      n, sm_length, t, kernel_id_out, valid_out, sm_range_out, h_eff_out);
+  MTN_LAUNCH_CHECK();
+  return MTN_OK;
+}
+
+int mtn_prune(int64_t n0, const double* px, const double* py, const double* pz,
+              const double* sm_range, const double* mHI, double mHI_scalar,
+              const double* half_width, double half_width_scalar, double max_abs_dv,
+              int32_t nx_tot, int32_t ny_tot, int32_t n_channels, int32_t flags,
+              uint8_t* accept_out, int64_t* n_accept_out, void* stream) {
+  if (n0 < 0 || !accept_out) return fail(MTN_ERR_INVALID, "prune: bad input%s", "");
+  if ((flags & MTN_PRUNE_SPATIAL) && (!px || !py || !sm_range))
+    return fail(MTN_ERR_INVALID, "prune: spatial pruning needs px, py, sm_range%s", "");
+  if ((flags & MTN_PRUNE_SPECTRAL) && !pz)
+    return fail(MTN_ERR_INVALID, "prune: spectral pruning needs pz%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_accept_out) MTN_CUDA(cudaMemsetAsync(n_accept_out, 0, sizeof(int64_t), st));
+  if (n0 == 0) return MTN_OK;
+  prune_kernel<<<(unsigned)((n0 + 255) / 256), 256, 0, st>>>(
+      n0, px, py, pz, sm_range, mHI, mHI_scalar, half_width, half_width_scalar, max_abs_dv,
+      (double)nx_tot, (double)ny_tot, (double)n_channels, flags, accept_out,
+      (unsigned long long*)n_accept_out);
+  MTN_LAUNCH_CHECK();
+  return MTN_OK;
+}
+
+size_t mtn_plan_scratch_bytes(int64_t n) { return plan_scratch_layout(n, nullptr, nullptr); }
+
+static int check_particles(const MtnParticles* p) {
+  if (!p || p->n < 0) return fail(MTN_ERR_INVALID, "particles: bad n%s", "");
+  if (p->n > 0 && (!p->px || !p->py || !p->h_eff || !p->sm_range || !p->v))
+    return fail(MTN_ERR_INVALID, "particles: px, py, h_eff, sm_range and v are required%s", "");
+  return MTN_OK;
+}
+
+static int edges_direction(const MtnCube* cube, cudaStream_t st, int* increasing) {
+  // the host mirror validates monotonicity (spectral_models.py:180-187); here only the
+  // direction is needed
+  double e[2];
+  MTN_CUDA(cudaMemcpyAsync(e, cube->edges, sizeof(e), cudaMemcpyDeviceToHost, st));
+  MTN_CUDA(cudaStreamSynchronize(st));
+  *increasing = e[1] > e[0] ? 1 : 0;
+  return MTN_OK;
+}
+
+int mtn_plan(const MtnParticles* p, const MtnCube* cube, void* scratch, size_t scratch_bytes,
+             MtnPlan* plan, void* stream) {
+  if (int rc = check_particles(p)) return rc;
+  if (!cube || !cube->edges || !plan) return fail(MTN_ERR_INVALID, "plan: bad arguments%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  PlanScratch ps;
+  if (plan_scratch_layout(p->n, scratch, &ps) > scratch_bytes || !scratch)
+    return fail(MTN_ERR_WORKSPACE, "plan: scratch too small%s", "");
+  int inc = 0;
+  if (int rc = edges_direction(cube, st, &inc)) return rc;
+  Geo g;
+  if (int rc = make_geo(cube, &g, inc)) return rc;
+  MTN_CUDA(cudaMemsetAsync(ps.totals, 0, 8 * sizeof(unsigned long long), st));
+  if (p->n > 0) {
+    plan_count_kernel<<<(unsigned)ps.nblk, PLAN_THREADS, 0, st>>>(make_plan_in(p, cube), g, ps.blk_kept,
+                                                                 ps.blk_pairs, ps.totals + 2);
+    MTN_LAUNCH_CHECK();
+    scan_sums_inplace<int64_t><<<1, 1024, 0, st>>>(ps.blk_kept, ps.nblk, (int64_t*)ps.totals);
+    MTN_LAUNCH_CHECK();
+    scan_sums_inplace<int64_t><<<1, 1024, 0, st>>>(ps.blk_pairs, ps.nblk, (int64_t*)ps.totals + 1);
+    MTN_LAUNCH_CHECK();
+  }
+  unsigned long long tot[3];
+  MTN_CUDA(cudaMemcpyAsync(tot, ps.totals, sizeof(tot), cudaMemcpyDeviceToHost, st));
+  MTN_CUDA(cudaStreamSynchronize(st));
+  plan->n_kept = (int64_t)tot[0];
+  plan->n_pairs = (int64_t)tot[1];
+  plan->updates_dense = (int64_t)tot[2];
+  plan->n_bricks = g.n_bricks;
+  if (plan->n_pairs >= (1ll << 32) - 1 || plan->n_kept >= (1ll << 32) - 1)
+    return fail(MTN_ERR_LIMIT, "plan: %s%lld pairs exceed the 32-bit sort index; split the slab", "",
+                (long long)plan->n_pairs);
+  plan->chunk = choose_chunk(plan->n_pairs);
+  plan->edges_increasing = inc;
+  plan->reserved = 0;
+  plan->workspace_bytes =
+      workspace_layout(plan->n_kept, plan->n_pairs, plan->n_bricks, plan->chunk, nullptr, nullptr);
+  return MTN_OK;
+}
+
+int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCube* cube,
+                const MtnPlan* plan, void* scratch, size_t scratch_bytes, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  if (int rc = check_particles(p)) return rc;
+  if (!cube || !cube->edges || !cube->slab || !plan)
+    return fail(MTN_ERR_INVALID, "project: bad arguments%s", "");
+  if (!(cube->px_size_arcsec > 0.0)) return fail(MTN_ERR_INVALID, "project: px_size must be > 0%s", "");
+  KernelTableDev t;
+  if (int rc = to_dev_table(table, &t)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  PlanScratch ps;
+  if (plan_scratch_layout(p->n, scratch, &ps) > scratch_bytes || !scratch)
+    return fail(MTN_ERR_WORKSPACE, "project: scratch too small%s", "");
+  Workspace ws;
+  if (workspace_layout(plan->n_kept, plan->n_pairs, plan->n_bricks, plan->chunk, workspace, &ws) >
+          workspace_bytes ||
+      !workspace)
+    return fail(MTN_ERR_WORKSPACE, "project: workspace too small%s", "");
+  Geo g;
+  if (int rc = make_geo(cube, &g, plan->edges_increasing)) return rc;
+  if (g.n_bricks != plan->n_bricks) return fail(MTN_ERR_INVALID, "project: plan/cube mismatch%s", "");
+  const double px_area = cube->px_size_arcsec * cube->px_size_arcsec;
+  const int zeroed = (cube->flags & MTN_CUBE_ZEROED) ? 1 : 0;
+
+  MTN_CUDA(cudaMemsetAsync(ws.brick_count, 0, (size_t)g.n_bricks * 4, st));
+  MTN_CUDA(cudaMemsetAsync(ws.scalars, 0, 64, st));
+  g_ev_valid = false;
+  mark(0, st);
+  for (int k = 1; k <= N_STAGES; ++k) mark(k, st);  // stages skipped below read as 0 ms
+
+  if (plan->n_pairs > 0) {
+    plan_emit_kernel<<<(unsigned)ps.nblk, PLAN_THREADS, 0, st>>>(
+        make_plan_in(p, cube), g, ps.blk_kept, ps.blk_pairs, ws.records, ws.pairs_a, ws.brick_count);
+    MTN_LAUNCH_CHECK();
+
+    mark(1, st);
+    int key_bits = 1;
+    while ((1ll << key_bits) < g.n_bricks) ++key_bits;
+    uint64_t* sorted = nullptr;
+    if (int rc = radix_sort_pairs(ws.pairs_a, ws.pairs_b, plan->n_pairs, key_bits, ws.hist,
+                                  ws.scan_temp, &sorted, st))
+      return rc;
+
+    mark(2, st);
+    if (int rc = exclusive_scan<uint32_t, uint32_t>(ws.brick_count, ws.brick_start, g.n_bricks,
+                                                    ws.scan_temp, nullptr, st))
+      return rc;
+    const unsigned bgrid = (unsigned)((g.n_bricks + 255) / 256);
+    item_count_kernel<<<bgrid, 256, 0, st>>>(ws.brick_count, g.n_bricks, (uint32_t)plan->chunk,
+                                             ws.counts, ws.multi, ws.ismulti);
+    MTN_LAUNCH_CHECK();
+    if (int rc = exclusive_scan<uint32_t, uint32_t>(ws.counts, ws.counts, g.n_bricks, ws.scan_temp,
+                                                    ws.scalars + 0, st))
+      return rc;
+    if (int rc = exclusive_scan<uint32_t, uint32_t>(ws.multi, ws.multi, g.n_bricks, ws.scan_temp,
+                                                    ws.scalars + 1, st))
+      return rc;
+    if (int rc = exclusive_scan<uint32_t, uint32_t>(ws.ismulti, ws.ismulti, g.n_bricks, ws.scan_temp,
+                                                    ws.scalars + 2, st))
+      return rc;
+    item_fill_kernel<<<bgrid, 256, 0, st>>>(ws.brick_count, ws.brick_start, g.n_bricks,
+                                            (uint32_t)plan->chunk, ws.counts, ws.multi, ws.ismulti,
+                                            ws.items, ws.multis);
+    MTN_LAUNCH_CHECK();
+
+    ProjArgs a;
+    a.geo = g;
+    a.table = t;
+    a.records = ws.records;
+    a.pairs = sorted;
+    a.items = ws.items;
+    a.n_items = ws.scalars + 0;
+    a.counter = ws.scalars + 3;
+    a.edges = cube->edges;
+    a.slab = cube->slab;
+    a.partials = ws.partials;
+    a.px_area = px_area;
+    a.zeroed = zeroed;
+    a.exec_counts = (unsigned long long*)(ws.scalars + 8);  // zeroed with the scalars
+    static bool attr_set = false;
+    if (!attr_set) {
+      MTN_CUDA(cudaFuncSetAttribute(project_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(ProjSmem)));
+      MTN_CUDA(cudaFuncSetAttribute(project_kernel<true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(ProjSmem)));
+      attr_set = true;
+    }
+    const unsigned pgrid = (unsigned)std::min<int64_t>(ws.max_items, (int64_t)sm_count() * 2);
+    mark(3, st);
+    if (g_count_exec)
+      project_kernel<true><<<pgrid, PROJ_THREADS, sizeof(ProjSmem), st>>>(a);
+    else
+      project_kernel<false><<<pgrid, PROJ_THREADS, sizeof(ProjSmem), st>>>(a);
+    MTN_LAUNCH_CHECK();
+    mark(4, st);
+    reduce_partials_kernel<<<(unsigned)ws.max_multi, PROJ_THREADS, 0, st>>>(
+        g, ws.multis, ws.scalars + 2, ws.partials, cube->slab, px_area, zeroed);
+    MTN_LAUNCH_CHECK();
+    if (g_count_exec) {
+      MTN_CUDA(cudaMemcpyAsync(g_exec_counts, a.exec_counts, sizeof(g_exec_counts),
+                               cudaMemcpyDeviceToHost, st));
+      MTN_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  mark(5, st);
+  if (!zeroed) {
+    empty_brick_kernel<<<(unsigned)g.n_bricks, PROJ_THREADS, 0, st>>>(g, ws.brick_count, cube->slab,
+                                                                     px_area);
+    MTN_LAUNCH_CHECK();
+  }
+  mark(6, st);
+  g_ev_valid = g_timing != 0;
+  return MTN_OK;
+}
+
+int mtn_set_timing(int enable) {
+  g_timing = enable ? 1 : 0;
+  return MTN_OK;
+}
+
+int mtn_set_count_exec(int enable) {
+  g_count_exec = enable ? 1 : 0;
+  return MTN_OK;
+}
+
+int mtn_last_exec_counts(int64_t* out3) {
+  if (!out3) return fail(MTN_ERR_INVALID, "exec_counts: null output%s", "");
+  for (int i = 0; i < 3; ++i) out3[i] = (int64_t)g_exec_counts[i];
+  return MTN_OK;
+}
+
+int mtn_last_timing(float* ms_out, int n) {
+  if (!ms_out || n < N_STAGES) return fail(MTN_ERR_INVALID, "timing: need room for 6 stages%s", "");
+  if (!g_ev_valid) return fail(MTN_ERR_INVALID, "timing: enable with mtn_set_timing first%s", "");
+  MTN_CUDA(cudaEventSynchronize(g_ev[N_STAGES]));
+  for (int k = 0; k < N_STAGES; ++k) MTN_CUDA(cudaEventElapsedTime(ms_out + k, g_ev[k], g_ev[k + 1]));
+  return MTN_OK;
+}
+
+int mtn_fp64_peak(double* tflops_out, double* ms_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  double* d = nullptr;
+  MTN_CUDA(cudaMalloc(&d, 8));
+  const int iters = 4096, blocks = sm_count() * 16;
+  cudaEvent_t e0, e1;
+  MTN_CUDA(cudaEventCreate(&e0));
+  MTN_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    MTN_CUDA(cudaEventRecord(e0, st));
+    fp64_peak_kernel<<<blocks, 256, 0, st>>>(d, iters, 0.999999, 1e-7);
+    MTN_CUDA(cudaEventRecord(e1, st));
+    MTN_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    MTN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  MTN_CUDA(cudaGetLastError());
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
+  if (tflops_out) *tflops_out = flops / (best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  return MTN_OK;
+}
+
+int mtn_probe_kernel_integral(const MtnKernelEntry* entry, int64_t n, const double* dx,
+                              const double* dy, const double* h, double* w_out, void* stream) {
+  if (!entry || n < 0) return fail(MTN_ERR_INVALID, "probe: bad arguments%s", "");
+  if (n == 0) return MTN_OK;
+  probe_kernel_integral_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      entry->kind, entry->truncate, entry->norm, n, dx, dy, h, w_out);
+  MTN_LAUNCH_CHECK();
+  return MTN_OK;
+}
+
+int mtn_probe_spectra(int32_t spectrum, int64_t n, const double* v, const double* sigma,
+                      double sigma_scalar, const double* amp, int32_t n_channels,
+                      const double* edges, double* s_out, void* stream) {
+  if (n < 0 || n_channels <= 0) return fail(MTN_ERR_INVALID, "probe: bad arguments%s", "");
+  if (n == 0) return MTN_OK;
+  const int64_t tot = n * n_channels;
+  probe_spectra_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      spectrum, n, v, sigma, sigma_scalar, amp, n_channels, edges, s_out);
+  MTN_LAUNCH_CHECK();
+  return MTN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Shared definitions for the martini_b200 CUDA library (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/martini_b200.h"
+
+namespace mtn {
+
+// ---------------------------------------------------------------------------------------
+// Brick geometry.  A brick is TILE_X x TILE_Y pixels x CB channels; it is the unit of
+// binning (sort key) and the unit of register accumulation in the projection kernel.
+// ---------------------------------------------------------------------------------------
+constexpr int TILE_X = 16;            // pixels along x (slowest cube axis)
+constexpr int TILE_Y = 16;            // pixels along y
+constexpr int CB = 32;                // channels per brick = accumulators per thread
+constexpr int PROJ_THREADS = TILE_X * TILE_Y;  // one thread per pixel of the tile
+constexpr int PROJ_WARPS = PROJ_THREADS / 32;
+constexpr int SUB_X = 4;              // a warp owns a SUB_X x SUB_Y pixel sub-block
+constexpr int SUB_Y = 8;
+constexpr int PBATCH = 64;            // particle records staged per batch
+constexpr int REC_DOUBLES = 8;        // 64-byte particle record
+constexpr int REC_BYTES = REC_DOUBLES * 8;
+
+// erf(x) == 1.0 exactly for x >= ~5.93 (1 - erf(x) < 2^-54); channels whose edges are
+// both beyond ERF_SAT on the same side of the line centre contribute exactly 0 in the
+// reference (scipy) and here, so skipping them is bit-safe.
+constexpr double ERF_SAT = 6.0;
+
+struct Geo {
+  int nx, ny, C;        // full cube
+  int x_lo, x_hi;       // slab rows
+  int ntx, nty, ncb;    // bricks along x (slab), y, channel
+  int n_bricks;
+  int spectrum;         // MTN_SPECTRUM_*
+  int edges_increasing; // 1 if edges[c+1] > edges[c]
+};
+
+// One staged particle: everything the projection kernel needs, 64 bytes, 16-B aligned so
+// a single cp.async.bulk moves it.
+struct __align__(16) Record {
+  double px, py;     // pixel coordinates
+  double h;          // h_eff = sm_length * rescale
+  double inv_h2;     // 1 / (h*h)
+  double v;          // line centre [km/s]
+  double inv_s;      // 1 / (sqrt(2) * sigma)   (Gaussian spectrum)
+  double amp;        // mHI * D^-2 / 2.36e5  [Jy km/s]
+  float r;           // sm_range (integer valued or +inf)
+  int32_t kid;       // kernel table index
+};
+static_assert(sizeof(Record) == REC_BYTES, "record must be 64 bytes");
+
+// A unit of work for the projection kernel: a contiguous run of one brick's sorted pairs.
+struct __align__(16) Item {
+  uint32_t begin, end;  // range in the sorted pair array
+  uint32_t brick;       // brick key
+  int32_t slot;         // >= 0: write partial sums to partials[slot]; -1: write the cube
+};
+
+struct KernelTableDev {
+  int n;
+  int adaptive;
+  int kind[MTN_MAX_KERNELS];
+  int valid_is_max[MTN_MAX_KERNELS];
+  double rescale[MTN_MAX_KERNELS];
+  double size_in_fwhm[MTN_MAX_KERNELS];
+  double valid_size[MTN_MAX_KERNELS];
+  double truncate[MTN_MAX_KERNELS];
+  double norm[MTN_MAX_KERNELS];
+};
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+extern thread_local char g_err[512];
+extern thread_local int g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+#define MTN_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      snprintf(mtn::g_err, sizeof(mtn::g_err), "%s:%d: %s: %s", __FILE__, __LINE__, #call, \
+               cudaGetErrorString(e_));                                                  \
+      return MTN_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define MTN_LAUNCH_CHECK()                \
+  do {                                    \
+    ++mtn::g_launches;                    \
+    MTN_CUDA(cudaGetLastError());         \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+}  // namespace mtn

@@ -1,0 +1,285 @@
+// K0 smoothing setup, K1 prune, and the footprint / binning front half of the projection.
+#pragma once
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace mtn {
+
+constexpr int PLAN_THREADS = 1024;
+
+// ---------------------------------------------------------------------------------------
+// K0: per-particle kernel choice, sm_range, h_eff.
+//   sph_kernels.py:257-262 (_init_sm_ranges), :1254-1272 (_AdaptiveKernel._init_sm_lengths),
+//   :116 (rescaled_h), :121-138 (_confirm_validation's `valid`).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) smoothing_setup_kernel(
+    int64_t n, const double* __restrict__ sm_length, KernelTableDev t,
+    uint8_t* __restrict__ kid_out, uint8_t* __restrict__ valid_out,
+    double* __restrict__ range_out, double* __restrict__ heff_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double s = sm_length[i];
+  int kid = 0, valid = 0;
+  if (t.adaptive) {
+    // first kernel whose _validate(sm_lengths * K._rescale) passes; none -> entry 0
+    for (int k = 0; k < t.n; ++k) {
+      const double x = __dmul_rn(s, t.rescale[k]);
+      const bool ok = t.valid_is_max[k] ? (x <= t.valid_size[k]) : (x >= t.valid_size[k]);
+      if (ok) {
+        kid = k;
+        valid = 1;
+        break;
+      }
+    }
+  } else {
+    // a simple kernel validates the raw smoothing length (:138)
+    valid = t.valid_is_max[0] ? (s <= t.valid_size[0]) : (s >= t.valid_size[0]);
+  }
+  if (kid_out) kid_out[i] = (uint8_t)kid;
+  if (valid_out) valid_out[i] = (uint8_t)valid;
+  if (range_out) range_out[i] = ceil(__dmul_rn(s, t.size_in_fwhm[kid]));
+  if (heff_out) heff_out[i] = __dmul_rn(s, t.rescale[kid]);
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: prune mask, martini.py:198-232 (bit-exact: same IEEE comparisons as numpy).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prune_kernel(
+    int64_t n, const double* __restrict__ px, const double* __restrict__ py,
+    const double* __restrict__ pz, const double* __restrict__ sm_range,
+    const double* __restrict__ mHI, double mHI_scalar, const double* __restrict__ half_width,
+    double hw_scalar, double max_abs_dv, double nx_tot, double ny_tot, double n_channels,
+    int flags, uint8_t* __restrict__ accept, unsigned long long* __restrict__ n_accept) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (i < n) {
+    bool reject = false;
+    if (flags & MTN_PRUNE_SPATIAL) {
+      const double x = px[i], y = py[i], r = sm_range[i];
+      reject |= __dadd_rn(x, r) < 0.0;
+      reject |= __dadd_rn(y, r) < 0.0;
+      reject |= __dsub_rn(x, r) > nx_tot;
+      reject |= __dsub_rn(y, r) > ny_tot;
+      reject |= isnan(x) || isnan(y);
+    }
+    if (flags & MTN_PRUNE_SPECTRAL) {
+      const double hw = half_width ? half_width[i] : hw_scalar;
+      const double w4 = __dmul_rn(4.0, __ddiv_rn(hw, max_abs_dv));
+      const double z = pz[i];
+      reject |= __dadd_rn(z, w4) < 0.0;
+      reject |= __dsub_rn(z, w4) > n_channels;
+    }
+    if (flags & MTN_PRUNE_MASS) {
+      const double m = mHI ? mHI[i] : mHI_scalar;
+      reject |= (m == 0.0);
+    }
+    keep = !reject;
+    accept[i] = keep ? 1 : 0;
+  }
+  if (n_accept) {
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_accept, (unsigned long long)__popc(b));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Footprint of one particle in the slab.
+// ---------------------------------------------------------------------------------------
+struct Foot {
+  int i0, i1, j0, j1;  // inclusive pixel bounds (full-cube coordinates), clipped to the slab
+  int c0, c1;          // inclusive live-channel window
+  bool box;            // candidate box reaches the slab (counts towards U_dense)
+  bool live;           // box && a live channel exists
+};
+
+// Smallest and largest integer i in [lim_lo, lim_hi] with |i - p| <= r, the candidate test
+// of martini.py:272-274 evaluated exactly as numpy does (fl(i - p), then compare).
+__device__ __forceinline__ bool pixel_bounds(double p, double r, int lim_lo, int lim_hi, int& lo,
+                                             int& hi) {
+  if (!(r >= 0.0) || isnan(p) || lim_lo > lim_hi) return false;
+  auto in = [&](int i) { return fabs(__dsub_rn((double)i, p)) <= r; };
+  double a0 = ceil(p - r), b0 = floor(p + r);
+  a0 = fmin(fmax(a0, (double)lim_lo - 1.0), (double)lim_hi + 1.0);
+  b0 = fmin(fmax(b0, (double)lim_lo - 1.0), (double)lim_hi + 1.0);
+  int a = (int)a0, b = (int)b0;
+  if (a - 1 >= lim_lo && in(a - 1)) --a;
+  if (a < lim_lo) a = lim_lo;
+  if (a <= lim_hi && !in(a)) ++a;
+  if (a <= lim_hi && !in(a)) ++a;
+  if (b + 1 <= lim_hi && in(b + 1)) ++b;
+  if (b > lim_hi) b = lim_hi;
+  if (b >= lim_lo && !in(b)) --b;
+  if (b >= lim_lo && !in(b)) --b;
+  if (a > b || a > lim_hi || b < lim_lo) return false;
+  if (!in(a) || !in(b)) return false;
+  lo = a;
+  hi = b;
+  return true;
+}
+
+// Live channel window.  g(e) = sgn * (edges[e] - v) * inv_s is non-decreasing in e;
+// channel c can be non-zero only if g(c+1) > -T and g(c) < T (T = ERF_SAT for the Gaussian
+// line, closed at 0 for the Dirac line).  Returns false if no channel is live.
+__device__ __forceinline__ bool channel_window(const double* __restrict__ edges, int C, int sgn,
+                                               int spectrum, double v, double inv_s, int& c0,
+                                               int& c1) {
+  const bool dirac = spectrum == MTN_SPECTRUM_DIRACDELTA;
+  const double scale = dirac ? (double)sgn : (double)sgn * inv_s;
+  auto g = [&](int e) { return (__ldg(edges + e) - v) * scale; };
+  // first edge e in [0, C] with g(e) > -T (>= 0 for dirac)
+  int lo = 0, hi = C + 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const double x = g(mid);
+    const bool t = dirac ? (x >= 0.0) : (x > -ERF_SAT);
+    if (t) hi = mid; else lo = mid + 1;
+  }
+  const int e_first = lo;  // C+1 if none
+  // last edge e in [0, C] with g(e) < T (<= 0 for dirac): first e failing, minus one
+  lo = 0;
+  hi = C + 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const double x = g(mid);
+    const bool t = dirac ? (x <= 0.0) : (x < ERF_SAT);
+    if (t) lo = mid + 1; else hi = mid;
+  }
+  const int e_last = lo - 1;  // -1 if none
+  if (e_first > C || e_last < 0) return false;
+  c0 = max(e_first - 1, 0);
+  c1 = min(e_last, C - 1);
+  return c0 <= c1;
+}
+
+struct PlanIn {
+  int64_t n;
+  const double* px;
+  const double* py;
+  const double* h_eff;
+  const double* sm_range;
+  const uint8_t* kernel_id;
+  const double* v;
+  const double* sigma;
+  double sigma_scalar;
+  const double* mHI;
+  double mHI_scalar;
+  const double* D;
+  double D_scalar;
+  const uint8_t* accept;
+  const double* edges;
+};
+
+__device__ __forceinline__ double inv_sqrt2_sigma(const PlanIn& in, int64_t i) {
+  const double sg = in.sigma ? in.sigma[i] : in.sigma_scalar;
+  return 1.0 / (1.4142135623730951 * sg);
+}
+
+__device__ __forceinline__ Foot footprint(const PlanIn& in, const Geo& g, int64_t i) {
+  Foot f;
+  f.box = f.live = false;
+  if (in.accept && !in.accept[i]) return f;
+  const double r = in.sm_range[i];
+  if (!pixel_bounds(in.px[i], r, g.x_lo, g.x_hi - 1, f.i0, f.i1)) return f;
+  if (!pixel_bounds(in.py[i], r, 0, g.ny - 1, f.j0, f.j1)) return f;
+  f.box = true;
+  const double inv_s = g.spectrum == MTN_SPECTRUM_GAUSSIAN ? inv_sqrt2_sigma(in, i) : 1.0;
+  f.live = channel_window(in.edges, g.C, g.edges_increasing ? 1 : -1, g.spectrum, in.v[i], inv_s,
+                          f.c0, f.c1);
+  return f;
+}
+
+__device__ __forceinline__ void brick_range(const Foot& f, const Geo& g, int& tx0, int& tx1,
+                                            int& ty0, int& ty1, int& cb0, int& cb1) {
+  tx0 = (f.i0 - g.x_lo) / TILE_X;
+  tx1 = (f.i1 - g.x_lo) / TILE_X;
+  ty0 = f.j0 / TILE_Y;
+  ty1 = f.j1 / TILE_Y;
+  cb0 = f.c0 / CB;
+  cb1 = f.c1 / CB;
+}
+
+// Pass 1: per-block totals of (kept particles, bricks overlapped) and the slab's U_dense.
+__global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(
+    PlanIn in, Geo g, int64_t* __restrict__ blk_kept, int64_t* __restrict__ blk_pairs,
+    unsigned long long* __restrict__ updates) {
+  __shared__ int64_t sm[33];
+  const int64_t i = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
+  int64_t kept = 0, pairs = 0, upd = 0;
+  if (i < in.n) {
+    const Foot f = footprint(in, g, i);
+    if (f.box) upd = (int64_t)(f.i1 - f.i0 + 1) * (f.j1 - f.j0 + 1) * g.C;
+    if (f.live) {
+      int tx0, tx1, ty0, ty1, cb0, cb1;
+      brick_range(f, g, tx0, tx1, ty0, ty1, cb0, cb1);
+      kept = 1;
+      pairs = (int64_t)(tx1 - tx0 + 1) * (ty1 - ty0 + 1) * (cb1 - cb0 + 1);
+    }
+  }
+  int64_t tk, tp, tu;
+  block_excl_scan(kept, sm, &tk);
+  block_excl_scan(pairs, sm, &tp);
+  block_excl_scan(upd, sm, &tu);
+  if (threadIdx.x == 0) {
+    blk_kept[blockIdx.x] = tk;
+    blk_pairs[blockIdx.x] = tp;
+    if (tu) atomicAdd(updates, (unsigned long long)tu);
+  }
+}
+
+// Pass 3 (after the block sums were scanned): write one 64-byte record per kept particle
+// and one (brick key << 32 | record index) pair per brick it overlaps, in particle order;
+// count pairs per brick.
+__global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
+    PlanIn in, Geo g, const int64_t* __restrict__ blk_kept, const int64_t* __restrict__ blk_pairs,
+    Record* __restrict__ records, uint64_t* __restrict__ pairs_out,
+    uint32_t* __restrict__ brick_count) {
+  __shared__ int64_t sm[33];
+  const int64_t i = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
+  int64_t kept = 0, npair = 0;
+  Foot f;
+  f.live = false;
+  int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1, cb0 = 0, cb1 = -1;
+  if (i < in.n) {
+    f = footprint(in, g, i);
+    if (f.live) {
+      brick_range(f, g, tx0, tx1, ty0, ty1, cb0, cb1);
+      kept = 1;
+      npair = (int64_t)(tx1 - tx0 + 1) * (ty1 - ty0 + 1) * (cb1 - cb0 + 1);
+    }
+  }
+  int64_t tk, tp;
+  const int64_t ridx = blk_kept[blockIdx.x] + block_excl_scan(kept, sm, &tk);
+  int64_t off = blk_pairs[blockIdx.x] + block_excl_scan(npair, sm, &tp);
+  if (!f.live) return;
+  Record rec;
+  rec.px = in.px[i];
+  rec.py = in.py[i];
+  rec.h = in.h_eff[i];
+  rec.inv_h2 = 1.0 / (rec.h * rec.h);
+  rec.v = in.v[i];
+  const double m = in.mHI ? in.mHI[i] : in.mHI_scalar;
+  const double d = in.D ? in.D[i] : in.D_scalar;
+  // A = mHI * D^-2 (spectral_models.py:94), / 2.36e5 (:139); the Gaussian line's 0.5 is
+  // folded in here (exact: a power of two)
+  const double amp = m * (1.0 / (d * d)) / 2.36e5;
+  if (g.spectrum == MTN_SPECTRUM_GAUSSIAN) {
+    rec.inv_s = inv_sqrt2_sigma(in, i);
+    rec.amp = 0.5 * amp;
+  } else {
+    rec.inv_s = 1.0;
+    rec.amp = amp;
+  }
+  rec.r = (float)in.sm_range[i];
+  rec.kid = in.kernel_id ? (int32_t)in.kernel_id[i] : 0;
+  records[ridx] = rec;
+  for (int tx = tx0; tx <= tx1; ++tx)
+    for (int ty = ty0; ty <= ty1; ++ty)
+      for (int cb = cb0; cb <= cb1; ++cb) {
+        const uint32_t key = (uint32_t)((tx * g.nty + ty) * g.ncb + cb);
+        pairs_out[off++] = ((uint64_t)key << 32) | (uint64_t)(uint32_t)ridx;
+        atomicAdd(brick_count + key, 1u);
+      }
+}
+
+}  // namespace mtn

@@ -1,0 +1,232 @@
+"""Array-level host API over the C ABI: device buffers are torch tensors, the work is CUDA.
+
+This is the layer the MARTINI-compatible classes (``martini_b200.martini.Martini``) and
+``bench.py`` call.  All arrays are float64 in pixel / km/s / Mpc / Msun units (see
+include/martini_b200.h).  Nothing here computes on the CPU: every method enqueues kernels of
+``libmartini_b200.so`` on torch's current CUDA stream.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+@dataclass
+class KernelTable:
+    """Host description of the SPH kernel(s) in use (-> ``MtnKernelTable``)."""
+
+    entries: list = field(default_factory=list)  # dicts: kind, valid_is_max, rescale, ...
+    adaptive: bool = False
+
+    def to_c(self) -> L.MtnKernelTable:
+        if not 1 <= len(self.entries) <= L.MTN_MAX_KERNELS:
+            raise ValueError("kernel table needs 1..8 entries")
+        t = L.MtnKernelTable()
+        t.n = len(self.entries)
+        t.adaptive = 1 if self.adaptive else 0
+        for i, e in enumerate(self.entries):
+            t.k[i].kind = int(e["kind"])
+            t.k[i].valid_is_max = int(e.get("valid_is_max", 0))
+            t.k[i].rescale = float(e.get("rescale", 1.0))
+            t.k[i].size_in_fwhm = float(e["size_in_fwhm"])
+            t.k[i].valid_size = float(e.get("valid_size", 0.0))
+            t.k[i].truncate = float(e.get("truncate", 0.0))
+            t.k[i].norm = float(e.get("norm", 1.0))
+        return t
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _scalar_or_tensor(x, device):
+    """Return (tensor_or_None, scalar) for an input that may be a scalar or an array."""
+    if x is None:
+        return None, 0.0
+    if isinstance(x, torch.Tensor):
+        if x.ndim == 0:
+            return None, float(x)
+        return x.to(device=device, dtype=torch.float64).contiguous(), 0.0
+    a = np.asarray(x, dtype=np.float64)
+    if a.ndim == 0:
+        return None, float(a)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device), 0.0
+
+
+class Engine:
+    """One CUDA device's projection engine (owns grow-only scratch tensors)."""
+
+    def __init__(self, device="cuda:0"):
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise L.MartiniB200Error("martini_b200 needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self._scratch = None
+        self._workspace = None
+        self.last_plan = None
+        self.last_launches = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def to_device(self, x, dtype=torch.float64):
+        if isinstance(x, torch.Tensor):
+            return x.to(device=self.device, dtype=dtype).contiguous()
+        a = np.ascontiguousarray(np.asarray(x))
+        t = torch.from_numpy(a)
+        if a.dtype != np.dtype("uint8") or dtype != torch.uint8:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True)
+
+    def _grow(self, name, nbytes):
+        buf = getattr(self, name)
+        if buf is None or buf.numel() < nbytes:
+            buf = None
+            setattr(self, name, None)
+            buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+            setattr(self, name, buf)
+        return buf
+
+    def device_info(self):
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        L.check(self.lib.mtn_device_info(C.byref(sm), C.byref(ma), C.byref(mi)), "mtn_device_info")
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value)}
+
+    # ------------------------------------------------------------------ K0 / K1
+    def smoothing_setup(self, sm_length: torch.Tensor, table: KernelTable):
+        """-> (kernel_id u8, valid u8, sm_range f64, h_eff f64); see mtn_smoothing_setup."""
+        n = sm_length.numel()
+        kid = torch.empty(n, dtype=torch.uint8, device=self.device)
+        valid = torch.empty(n, dtype=torch.uint8, device=self.device)
+        rng = torch.empty(n, dtype=torch.float64, device=self.device)
+        heff = torch.empty(n, dtype=torch.float64, device=self.device)
+        tc = table.to_c()
+        L.check(
+            self.lib.mtn_smoothing_setup(n, _ptr(sm_length), C.byref(tc), _ptr(kid), _ptr(valid),
+                                         _ptr(rng), _ptr(heff), self._stream()),
+            "mtn_smoothing_setup",
+        )
+        return kid, valid, rng, heff
+
+    def prune(self, px, py, pz, sm_range, mHI, half_width, max_abs_dv, nx_tot, ny_tot, n_channels,
+              spatial=True, spectral=True, mass=True):
+        """-> (accept u8 tensor, n_accept 0-d int64 tensor); see mtn_prune."""
+        n = px.numel()
+        mt, ms = _scalar_or_tensor(mHI, self.device)
+        ht, hs = _scalar_or_tensor(half_width, self.device)
+        accept = torch.empty(n, dtype=torch.uint8, device=self.device)
+        count = torch.zeros((), dtype=torch.int64, device=self.device)
+        flags = (L.PRUNE_SPATIAL if spatial else 0) | (L.PRUNE_SPECTRAL if spectral else 0) | (
+            L.PRUNE_MASS if mass else 0)
+        L.check(
+            self.lib.mtn_prune(n, _ptr(px), _ptr(py), _ptr(pz), _ptr(sm_range), _ptr(mt), ms,
+                               _ptr(ht), hs, float(max_abs_dv), int(nx_tot), int(ny_tot),
+                               int(n_channels), flags, _ptr(accept), _ptr(count), self._stream()),
+            "mtn_prune",
+        )
+        return accept, count
+
+    # ------------------------------------------------------------------ plan + project
+    def insert(self, *, px, py, h_eff, sm_range, v, kernel_id=None, sigma=None, mHI=None, D=None,
+               accept=None, table: KernelTable, spectrum: int, edges: torch.Tensor,
+               cube: torch.Tensor, px_size_arcsec: float, x_lo: int = 0, x_hi: int | None = None,
+               nx_full: int | None = None, zeroed: bool = False):
+        """Project particles into ``cube`` (a (x_hi-x_lo, ny, C) float64 device tensor holding
+        rows [x_lo, x_hi) of the full cube), in place:  cube = (cube + inserted) / px_size^2.
+
+        Returns the ``MtnPlan`` (n_kept, n_pairs, updates_dense, ...).
+        """
+        assert cube.is_contiguous() and cube.dtype == torch.float64 and cube.ndim == 3
+        n = px.numel()
+        st, ss = _scalar_or_tensor(sigma, self.device)
+        mt, ms = _scalar_or_tensor(mHI, self.device)
+        dt, ds = _scalar_or_tensor(D, self.device)
+        keep = (st, mt, dt)  # keep temporaries alive until the kernels are enqueued
+        p = L.MtnParticles()
+        p.n = n
+        p.px, p.py, p.h_eff, p.sm_range = _ptr(px), _ptr(py), _ptr(h_eff), _ptr(sm_range)
+        p.kernel_id = _ptr(kernel_id)
+        p.v = _ptr(v)
+        p.sigma, p.sigma_scalar = _ptr(st), ss
+        p.mHI, p.mHI_scalar = _ptr(mt), ms
+        p.D, p.D_scalar = _ptr(dt), ds
+        p.accept = _ptr(accept)
+        c = L.MtnCube()
+        if x_hi is None:
+            x_hi = x_lo + cube.shape[0]
+        c.nx = int(nx_full if nx_full is not None else x_hi)
+        c.ny, c.n_channels = int(cube.shape[1]), int(cube.shape[2])
+        c.x_lo, c.x_hi = int(x_lo), int(x_hi)
+        assert c.x_hi - c.x_lo == cube.shape[0] and edges.numel() == c.n_channels + 1
+        c.spectrum = int(spectrum)
+        c.flags = L.CUBE_ZEROED if zeroed else L.CUBE_ACCUMULATE
+        c.px_size_arcsec = float(px_size_arcsec)
+        c.edges, c.slab = _ptr(edges), _ptr(cube)
+        tc = table.to_c()
+        stream = self._stream()
+
+        sbytes = self.lib.mtn_plan_scratch_bytes(n)
+        scratch = self._grow("_scratch", sbytes)
+        plan = L.MtnPlan()
+        L.check(self.lib.mtn_plan(C.byref(p), C.byref(c), _ptr(scratch), scratch.numel(),
+                                  C.byref(plan), stream), "mtn_plan")
+        ws = self._grow("_workspace", plan.workspace_bytes)
+        L.check(self.lib.mtn_project(C.byref(p), C.byref(tc), C.byref(c), C.byref(plan),
+                                     _ptr(scratch), scratch.numel(), _ptr(ws), ws.numel(), stream),
+                "mtn_project")
+        self.last_plan = plan
+        self.last_launches = self.lib.mtn_last_launch_count() + 3  # + mtn_plan's three kernels
+        del keep
+        return plan
+
+    # ------------------------------------------------------------------ diagnostics
+    STAGES = ("emit", "sort", "items", "project", "reduce", "finalize")
+
+    def set_timing(self, enable: bool):
+        L.check(self.lib.mtn_set_timing(int(enable)), "mtn_set_timing")
+
+    def last_timing_ms(self):
+        """Stage durations [ms] of the last insert() (needs set_timing(True)); synchronises."""
+        arr = (C.c_float * 6)()
+        L.check(self.lib.mtn_last_timing(arr, 6), "mtn_last_timing")
+        return dict(zip(self.STAGES, (float(x) for x in arr)))
+
+    def set_count_exec(self, enable: bool):
+        L.check(self.lib.mtn_set_count_exec(int(enable)), "mtn_set_count_exec")
+
+    def last_exec_counts(self):
+        arr = (C.c_int64 * 3)()
+        L.check(self.lib.mtn_last_exec_counts(arr), "mtn_last_exec_counts")
+        return {"updates": int(arr[0]), "weights": int(arr[1]), "erfs": int(arr[2])}
+
+    def fp64_peak_tflops(self):
+        t, ms = C.c_double(), C.c_double()
+        L.check(self.lib.mtn_fp64_peak(C.byref(t), C.byref(ms), self._stream()), "mtn_fp64_peak")
+        return t.value
+
+    def probe_kernel_integral(self, entry: dict, dx, dy, h):
+        e = KernelTable([entry]).to_c().k[0]
+        dx, dy, h = (self.to_device(a) for a in (dx, dy, h))
+        out = torch.empty_like(dx)
+        L.check(self.lib.mtn_probe_kernel_integral(C.byref(e), dx.numel(), _ptr(dx), _ptr(dy),
+                                                   _ptr(h), _ptr(out), self._stream()),
+                "mtn_probe_kernel_integral")
+        return out
+
+    def probe_spectra(self, spectrum, v, sigma, amp, edges):
+        v, amp, edges = (self.to_device(a) for a in (v, amp, edges))
+        st, ss = _scalar_or_tensor(sigma, self.device)
+        nchan = edges.numel() - 1
+        out = torch.empty((v.numel(), nchan), dtype=torch.float64, device=self.device)
+        L.check(self.lib.mtn_probe_spectra(int(spectrum), v.numel(), _ptr(v), _ptr(st), ss,
+                                           _ptr(amp), nchan, _ptr(edges), _ptr(out), self._stream()),
+                "mtn_probe_spectra")
+        return out

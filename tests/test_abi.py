@@ -1,0 +1,104 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every
+symbol include/martini_b200.h declares (no compute calls: there is no GPU here)."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+import __graft_entry__ as entry
+from martini_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    entry.build()
+    return L.load()
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "martini_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mtn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree(lib):
+    names = header_functions()
+    assert len(names) >= 14
+    assert sorted(L.SYMBOLS) == names
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_version_and_error_string(lib):
+    assert lib.mtn_version() == 100
+    assert isinstance(lib.mtn_last_error(), bytes)
+
+
+def test_struct_layouts_match_header():
+    # sizes the C compiler gives the same declarations (x86-64 SysV)
+    assert ctypes.sizeof(L.MtnKernelEntry) == 48
+    assert ctypes.sizeof(L.MtnKernelTable) == 8 + 8 * 48
+    assert ctypes.sizeof(L.MtnParticles) == 14 * 8
+    assert ctypes.sizeof(L.MtnCube) == 7 * 4 + 4 + 8 + 8 + 8
+    assert ctypes.sizeof(L.MtnPlan) == 5 * 8 + 8 + 8
+
+
+def test_invalid_arguments_are_reported_not_crashed(lib):
+    # argument validation happens before any CUDA call, so this is safe without a GPU
+    t = L.MtnKernelTable()
+    t.n = 0
+    rc = lib.mtn_smoothing_setup(0, None, ctypes.byref(t), None, None, None, None, None)
+    assert rc == -1 and b"kernel table" in lib.mtn_last_error()
+    with pytest.raises(L.MartiniB200Error, match="kernel table"):
+        L.check(rc, "mtn_smoothing_setup")
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+
+    from martini_b200.engine import Engine
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(L.MartiniB200Error, match="no CPU fallback"):
+        Engine()
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(L.MartiniB200Error, match="has not been built"):
+        L.load()
+
+
+def test_product_never_imports_oracle():
+    """The product package must not reference oracle/ (a CPU fallback would void parity)."""
+    pkg = os.path.join(ROOT, "martini_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_unsupported_plugins_raise():
+    from martini_b200 import spectral_models as S
+    from martini_b200 import sph_kernels as K
+
+    class MyKernel(K._WendlandC2Kernel):
+        pass
+
+    class MySpectrum(S.GaussianSpectrum):
+        pass
+
+    with pytest.raises(NotImplementedError, match="MyKernel"):
+        K.kernel_table(MyKernel())
+    with pytest.raises(NotImplementedError, match="MyKernel"):
+        K.kernel_table(K._AdaptiveKernel((MyKernel(), K.DiracDeltaKernel())))
+    with pytest.raises(NotImplementedError, match="MySpectrum"):
+        S.spectrum_kind(MySpectrum())
+    assert K.kernel_table(K.GaussianKernel(truncate=4.0)).adaptive
