@@ -61,6 +61,34 @@ static int sm_count() {
   return n;
 }
 
+// Taylor coefficients of erf about the interval centres, computed in x87 extended precision:
+// erf^(k)(x) = (2/sqrt(pi)) (-1)^(k-1) H_(k-1)(x) exp(-x^2), H = physicists' Hermite.
+static int ensure_erf_table() {
+  static bool done[64] = {false};
+  int dev = 0;
+  MTN_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && done[dev]) return MTN_OK;
+  static double tab[ERF_NINT * ERF_NCOEF];
+  const long double two_over_sqrt_pi = 1.1283791670955125738961589031215452L;
+  for (int i = 0; i < ERF_NINT; ++i) {
+    const long double c = ((long double)i + 0.5L) / ERF_INV_W;
+    const long double ex = expl(-c * c);
+    long double h_prev = 0.0L, h = 1.0L, fact = 1.0L;  // H_(-1) := 0, H_0 = 1
+    tab[i * ERF_NCOEF + 0] = (double)erfl(c);
+    for (int k = 1; k <= ERF_DEG; ++k) {
+      fact *= k;
+      const long double sign = ((k - 1) & 1) ? -1.0L : 1.0L;
+      tab[i * ERF_NCOEF + k] = (double)(two_over_sqrt_pi * sign * h * ex / fact);
+      const long double h_next = 2.0L * c * h - 2.0L * (k - 1) * h_prev;  // H_k from H_(k-1), H_(k-2)
+      h_prev = h;
+      h = h_next;
+    }
+  }
+  MTN_CUDA(cudaMemcpyToSymbol(g_erf_table, tab, sizeof(tab)));
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return MTN_OK;
+}
+
 static int make_geo(const MtnCube* c, Geo* g, int edges_increasing) {
   if (!c || c->nx <= 0 || c->ny <= 0 || c->n_channels <= 0)
     return fail(MTN_ERR_INVALID, "cube: bad shape%s", "");
@@ -176,7 +204,7 @@ static size_t workspace_layout(int64_t n_kept, int64_t n_pairs, int64_t n_bricks
   ws.scalars = (uint32_t*)take(64);
   ws.items = (Item*)take((size_t)max_items * sizeof(Item));
   ws.multis = (MultiBrick*)take((size_t)max_multi * sizeof(MultiBrick));
-  ws.partials = (double*)take((size_t)max_slots * PROJ_THREADS * CB * sizeof(double));
+  ws.partials = (double*)take((size_t)max_slots * TILE_PIX * CB * sizeof(double));
   ws.max_items = max_items;
   ws.max_multi = max_multi;
   ws.max_slots = max_slots;
@@ -185,8 +213,8 @@ static size_t workspace_layout(int64_t n_kept, int64_t n_pairs, int64_t n_bricks
 }
 
 static int64_t choose_chunk(int64_t n_pairs) {
-  // enough work items for ~8 rounds over 2 CTAs per SM, never smaller than 8 batches
-  const int64_t target = (int64_t)sm_count() * 2 * 8;
+  // enough work items for ~8 rounds over the resident CTAs, never smaller than 8 batches
+  const int64_t target = (int64_t)sm_count() * PROJ_CTAS_PER_SM * 8;
   int64_t chunk = std::max<int64_t>(8 * PBATCH, (n_pairs + target - 1) / target);
   return (chunk + PBATCH - 1) / PBATCH * PBATCH;
 }
@@ -273,14 +301,14 @@ int mtn_prune(int64_t n0, const double* px, const double* py, const double* pz,
               const double* half_width, double half_width_scalar, double max_abs_dv,
               int32_t nx_tot, int32_t ny_tot, int32_t n_channels, int32_t flags,
               uint8_t* accept_out, int64_t* n_accept_out, void* stream) {
-  if (n0 < 0 || !accept_out) return fail(MTN_ERR_INVALID, "prune: bad input%s", "");
+  if (n0 < 0 || (n0 > 0 && !accept_out)) return fail(MTN_ERR_INVALID, "prune: bad input%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_accept_out) MTN_CUDA(cudaMemsetAsync(n_accept_out, 0, sizeof(int64_t), st));
+  if (n0 == 0) return MTN_OK;
   if ((flags & MTN_PRUNE_SPATIAL) && (!px || !py || !sm_range))
     return fail(MTN_ERR_INVALID, "prune: spatial pruning needs px, py, sm_range%s", "");
   if ((flags & MTN_PRUNE_SPECTRAL) && !pz)
     return fail(MTN_ERR_INVALID, "prune: spectral pruning needs pz%s", "");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (n_accept_out) MTN_CUDA(cudaMemsetAsync(n_accept_out, 0, sizeof(int64_t), st));
-  if (n0 == 0) return MTN_OK;
   prune_kernel<<<(unsigned)((n0 + 255) / 256), 256, 0, st>>>(
       n0, px, py, pz, sm_range, mHI, mHI_scalar, half_width, half_width_scalar, max_abs_dv,
       (double)nx_tot, (double)ny_tot, (double)n_channels, flags, accept_out,
@@ -352,6 +380,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
                 const MtnPlan* plan, void* scratch, size_t scratch_bytes, void* workspace,
                 size_t workspace_bytes, void* stream) {
   g_launches = 0;
+  if (int rc = ensure_erf_table()) return rc;
   if (int rc = check_particles(p)) return rc;
   if (!cube || !cube->edges || !cube->slab || !plan)
     return fail(MTN_ERR_INVALID, "project: bad arguments%s", "");
@@ -381,7 +410,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
 
   if (plan->n_pairs > 0) {
     plan_emit_kernel<<<(unsigned)ps.nblk, PLAN_THREADS, 0, st>>>(
-        make_plan_in(p, cube), g, ps.blk_kept, ps.blk_pairs, ws.records, ws.pairs_a, ws.brick_count);
+        make_plan_in(p, cube), g, ps.blk_kept, ps.blk_pairs, ws.records, ws.pairs_a);
     MTN_LAUNCH_CHECK();
 
     mark(1, st);
@@ -393,12 +422,12 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
       return rc;
 
     mark(2, st);
-    if (int rc = exclusive_scan<uint32_t, uint32_t>(ws.brick_count, ws.brick_start, g.n_bricks,
-                                                    ws.scan_temp, nullptr, st))
-      return rc;
+    brick_bounds_kernel<<<(unsigned)((plan->n_pairs + 255) / 256), 256, 0, st>>>(
+        sorted, plan->n_pairs, ws.brick_start, ws.brick_count);
+    MTN_LAUNCH_CHECK();
     const unsigned bgrid = (unsigned)((g.n_bricks + 255) / 256);
-    item_count_kernel<<<bgrid, 256, 0, st>>>(ws.brick_count, g.n_bricks, (uint32_t)plan->chunk,
-                                             ws.counts, ws.multi, ws.ismulti);
+    item_count_kernel<<<bgrid, 256, 0, st>>>(ws.brick_count, ws.brick_start, g.n_bricks,
+                                             (uint32_t)plan->chunk, ws.counts, ws.multi, ws.ismulti);
     MTN_LAUNCH_CHECK();
     if (int rc = exclusive_scan<uint32_t, uint32_t>(ws.counts, ws.counts, g.n_bricks, ws.scan_temp,
                                                     ws.scalars + 0, st))
@@ -438,7 +467,8 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
                                     (int)sizeof(ProjSmem)));
       attr_set = true;
     }
-    const unsigned pgrid = (unsigned)std::min<int64_t>(ws.max_items, (int64_t)sm_count() * 2);
+    const unsigned pgrid =
+        (unsigned)std::min<int64_t>(ws.max_items, (int64_t)sm_count() * PROJ_CTAS_PER_SM);
     mark(3, st);
     if (g_count_exec)
       project_kernel<true><<<pgrid, PROJ_THREADS, sizeof(ProjSmem), st>>>(a);
@@ -533,6 +563,7 @@ int mtn_probe_spectra(int32_t spectrum, int64_t n, const double* v, const double
                       const double* edges, double* s_out, void* stream) {
   if (n < 0 || n_channels <= 0) return fail(MTN_ERR_INVALID, "probe: bad arguments%s", "");
   if (n == 0) return MTN_OK;
+  if (int rc = ensure_erf_table()) return rc;
   const int64_t tot = n * n_channels;
   probe_spectra_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       spectrum, n, v, sigma, sigma_scalar, amp, n_channels, edges, s_out);

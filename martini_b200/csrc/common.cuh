@@ -16,14 +16,28 @@ namespace mtn {
 // Brick geometry.  A brick is TILE_X x TILE_Y pixels x CB channels; it is the unit of
 // binning (sort key) and the unit of register accumulation in the projection kernel.
 // ---------------------------------------------------------------------------------------
-constexpr int TILE_X = 16;            // pixels along x (slowest cube axis)
-constexpr int TILE_Y = 16;            // pixels along y
-constexpr int CB = 32;                // channels per brick = accumulators per thread
-constexpr int PROJ_THREADS = TILE_X * TILE_Y;  // one thread per pixel of the tile
-constexpr int PROJ_WARPS = PROJ_THREADS / 32;
-constexpr int SUB_X = 4;              // a warp owns a SUB_X x SUB_Y pixel sub-block
-constexpr int SUB_Y = 8;
-constexpr int PBATCH = 64;            // particle records staged per batch
+#ifndef MTN_TILE
+#define MTN_TILE 8
+#endif
+constexpr int TILE_X = MTN_TILE;      // pixels along x (slowest cube axis)
+constexpr int TILE_Y = MTN_TILE;      // pixels along y
+constexpr int TILE_PIX = TILE_X * TILE_Y;
+constexpr int CB = 64;                // channels per brick: each lane owns 2 adjacent channels
+constexpr int SUB = 4;                // a warp owns a SUB x SUB pixel sub-block of the tile
+constexpr int SUB_PIX = SUB * SUB;    // = accumulator pairs per thread
+constexpr int SUBS_Y = TILE_Y / SUB;  // sub-blocks per tile row
+constexpr int PROJ_WARPS = TILE_PIX / SUB_PIX;  // 4 (8x8 tile) or 16 (16x16 tile)
+constexpr int PROJ_THREADS = PROJ_WARPS * 32;
+constexpr int PROJ_CTAS_PER_SM = 512 / PROJ_THREADS;  // register-limited: 16 warps per SM
+constexpr int PBATCH = 32;            // particle records staged per batch (= one per lane)
+static_assert(PBATCH == 32, "the batch is indexed by lane in several places");
+
+// erf table: Taylor coefficients of erf at the centres of ERF_NINT intervals of width
+// 1/ERF_INV_W covering [0, ERF_SAT]; degree ERF_DEG.  Truncation error < 5e-18.
+constexpr int ERF_INV_W = 16;
+constexpr int ERF_DEG = 9;
+constexpr int ERF_NCOEF = ERF_DEG + 1;  // 10 doubles = 80 B per interval (16-B aligned rows)
+constexpr int ERF_NINT = 6 * ERF_INV_W + 1;
 constexpr int REC_DOUBLES = 8;        // 64-byte particle record
 constexpr int REC_BYTES = REC_DOUBLES * 8;
 

@@ -196,12 +196,37 @@ __device__ __forceinline__ double kernel_weight(int kind, double dx, double dy, 
 // then * mHI * D^-2 / |hi - lo| / 2.36e5 (spectral_models.py:119-145).
 // ---------------------------------------------------------------------------------------
 
-// erf of a channel edge seen from a particle; saturates exactly like erf itself.
+// Table of Taylor coefficients of erf (filled once by the host in extended precision, see
+// api.cu: init_erf_table).  Row i holds erf^(k)(c_i)/k!, k = 0..ERF_DEG, at the centre
+// c_i = (i + 1/2)/ERF_INV_W of the interval [i, i+1)/ERF_INV_W.
+__device__ double g_erf_table[ERF_NINT * ERF_NCOEF];
+
+// erf(t) to ~1 ulp: exactly +-1 for |t| >= ERF_SAT (where erf rounds to 1 in float64 anyway),
+// otherwise a degree-9 Taylor polynomial about the centre of the 1/16-wide interval holding
+// |t| (|u| <= 1/32: truncation < 5e-18).  ~10 FMAs instead of libm's ~100 instructions.
+__device__ __forceinline__ double erf_tab(double t) {
+  const double a = fabs(t);
+  if (a >= ERF_SAT) return copysign(1.0, t);
+  const int i = (int)(a * ERF_INV_W);
+  const double u = a - ((double)i + 0.5) * (1.0 / ERF_INV_W);
+  const double2* row = reinterpret_cast<const double2*>(g_erf_table + i * ERF_NCOEF);
+  const double2 c89 = __ldg(row + 4), c67 = __ldg(row + 3), c45 = __ldg(row + 2),
+                c23 = __ldg(row + 1), c01 = __ldg(row);
+  double r = fma(c89.y, u, c89.x);
+  r = fma(r, u, c67.y);
+  r = fma(r, u, c67.x);
+  r = fma(r, u, c45.y);
+  r = fma(r, u, c45.x);
+  r = fma(r, u, c23.y);
+  r = fma(r, u, c23.x);
+  r = fma(r, u, c01.y);
+  r = fmin(fma(r, u, c01.x), 1.0);
+  return copysign(r, t);
+}
+
+// erf of a channel edge seen from a particle.
 __device__ __forceinline__ double edge_erf(double edge, double v, double inv_s) {
-  const double t = (edge - v) * inv_s;
-  if (t >= ERF_SAT) return 1.0;
-  if (t <= -ERF_SAT) return -1.0;
-  return erf(t);
+  return erf_tab((edge - v) * inv_s);
 }
 
 __device__ __forceinline__ double dirac_channel(double lo, double hi, double v) {

@@ -228,12 +228,10 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(
 }
 
 // Pass 3 (after the block sums were scanned): write one 64-byte record per kept particle
-// and one (brick key << 32 | record index) pair per brick it overlaps, in particle order;
-// count pairs per brick.
+// and one (brick key << 32 | record index) pair per brick it overlaps, in particle order.
 __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
     PlanIn in, Geo g, const int64_t* __restrict__ blk_kept, const int64_t* __restrict__ blk_pairs,
-    Record* __restrict__ records, uint64_t* __restrict__ pairs_out,
-    uint32_t* __restrict__ brick_count) {
+    Record* __restrict__ records, uint64_t* __restrict__ pairs_out) {
   __shared__ int64_t sm[33];
   const int64_t i = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
   int64_t kept = 0, npair = 0;
@@ -278,7 +276,6 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
       for (int cb = cb0; cb <= cb1; ++cb) {
         const uint32_t key = (uint32_t)((tx * g.nty + ty) * g.ncb + cb);
         pairs_out[off++] = ((uint64_t)key << 32) | (uint64_t)(uint32_t)ridx;
-        atomicAdd(brick_count + key, 1u);
       }
 }
 

@@ -1,18 +1,32 @@
 // The tile projection kernel and its small companions (work items, partial reduce).
 //
-// One CTA works on one brick (16 x 16 pixels x 32 channels) at a time.  Thread = pixel;
-// each thread keeps its pixel's 32 channel sums in registers.  Particle records of the
-// brick are gathered into shared memory with cp.async.bulk (one 64-byte bulk copy per
-// record, completion on an mbarrier, double buffered).  Per batch the CTA evaluates each
-// particle's channel spectrum once (edge erfs shared by adjacent channels) into shared
-// memory; then every warp walks the batch: a warp-uniform box test skips particles that
-// miss the warp's 4 x 8 pixel sub-block, each lane evaluates the kernel integral of its own
-// pixel in registers, and the rank-1 update acc[c] += W * S[c] runs over the live channel
-// groups only.  No atomics on the data path; every voxel is stored once.
+// One CTA works on one brick -- TILE x TILE pixels x 64 channels -- at a time and keeps the
+// brick's sums in registers: warp w owns a 4 x 4 pixel sub-block, lane l owns channels
+// (2l, 2l+1) of the brick, i.e. 16 pixels x 2 channels = 32 float64 accumulators per thread.
+// With the default 8 x 8 tile a CTA is 4 warps and four CTAs share an SM, so one CTA's
+// barrier waits are covered by the others.  The particle records of the brick are gathered
+// into shared memory with cp.async.bulk (one 64-byte bulk copy per record, completion on an
+// mbarrier, double buffered).  Per batch of 32 staged particles:
+//
+//   setup  warp 0, one lane per particle: the particle's candidate box inside the tile
+//          (martini.py:272-274, exact predicate) and its window of unsaturated channel
+//          edges; prefix sums of box areas and window lengths;
+//   A      every (particle, box pixel) pair and every (particle, unsaturated edge) pair is
+//          handed to one thread through those prefix sums -- all lanes hold real work --
+//          which evaluates the SPH-kernel pixel integral, or the edge erf, ONCE into shared
+//          memory;
+//   B      edge erfs -> per-channel line spectra S[p][c], in place; each warp builds, with one
+//          ballot, the list of particles that touch its sub-block and their pixel masks;
+//   C      each warp walks its own list: the lane loads its two S values once and does
+//          acc[pixel] += W * S for the masked pixels (W is a shared-memory broadcast).
+//
+// No atomics on the data path; every voxel is stored exactly once, as a 16-byte vector store
+// (a warp writes 512 contiguous bytes per pixel).
 #pragma once
 
 #include "common.cuh"
 #include "kernel_integrals.cuh"
+#include "plan.cuh"
 
 namespace mtn {
 
@@ -44,6 +58,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // bounded spin: a lost transaction traps instead of hanging the GPU
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 26); ++it)
     if (mbar_try_wait(bar, parity)) return;
   __trap();
@@ -58,16 +73,40 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t x, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  return x;
+}
+
 // ------------------------------------------------------------------------------ work items
-// counts[b] = chunks of brick b; multi[b] = same if > 1 else 0; ismulti[b] = 0/1
-__global__ void __launch_bounds__(256) item_count_kernel(const uint32_t* __restrict__ brick_count,
+// Bricks are found in the sorted pair array by their key boundaries: start[] gets the first
+// index, end_or_count[] the one-past-last index (rewritten to a count by item_count_kernel).
+__global__ void __launch_bounds__(256) brick_bounds_kernel(const uint64_t* __restrict__ pairs,
+                                                           int64_t n, uint32_t* __restrict__ start,
+                                                           uint32_t* __restrict__ end_or_count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = (uint32_t)(pairs[i] >> 32);
+  if (i == 0 || (uint32_t)(pairs[i - 1] >> 32) != k) start[k] = (uint32_t)i;
+  if (i == n - 1 || (uint32_t)(pairs[i + 1] >> 32) != k) end_or_count[k] = (uint32_t)i + 1u;
+}
+
+// counts[b] = chunks of brick b; multi[b] = same if > 1 else 0; ismulti[b] = 0/1.
+__global__ void __launch_bounds__(256) item_count_kernel(uint32_t* __restrict__ brick_count,
+                                                         const uint32_t* __restrict__ brick_start,
                                                          int n_bricks, uint32_t chunk,
                                                          uint32_t* __restrict__ counts,
                                                          uint32_t* __restrict__ multi,
                                                          uint32_t* __restrict__ ismulti) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_bricks) return;
-  const uint32_t c = brick_count[b];
+  const uint32_t end = brick_count[b];
+  const uint32_t c = end ? end - brick_start[b] : 0u;
+  brick_count[b] = c;
   const uint32_t k = (c + chunk - 1) / chunk;
   counts[b] = k;
   multi[b] = k > 1 ? k : 0;
@@ -119,44 +158,50 @@ struct ProjArgs {
   unsigned int* counter;    // device work counter, zeroed before launch
   const double* edges;
   double* slab;
-  double* partials;  // [slot][PROJ_THREADS][CB]
+  double* partials;  // [slot][TILE_PIX][CB]
   double px_area;    // px_size_arcsec^2
   int zeroed;        // MTN_CUBE_ZEROED
   unsigned long long* exec_counts;  // COUNT instantiation only: [updates, weights, erfs]
 };
 
+constexpr int W_STRIDE = TILE_PIX + 1;  // odd row stride: lane-per-particle reads hit 32 banks
+
 struct ProjSmem {
   Record rec[2][PBATCH];
-  double S[PBATCH][CB];
-  double E[PBATCH][CB + 1];
+  double W[PBATCH][W_STRIDE];   // kernel integrals, valid inside the particle's box only
+  double ES[PBATCH][CB + 2];    // edge erfs (CB+1 per particle), then spectra S in place
   double edge[CB + 1];
   double inv_dv[CB];
-  uint32_t gmask[PBATCH];
+  uint32_t wprefix[PBATCH + 1];  // exclusive prefix of box areas
+  uint32_t eprefix[PBATCH + 1];  // exclusive prefix of unsaturated-edge counts
+  uint8_t box[PBATCH][4];        // tile-local box: x0, nx, y0, ny
+  uint8_t ewin[PBATCH][2];       // first unsaturated edge, count
   uint64_t bar[2];
   uint32_t item;
 };
 
-// store one thread's CB channel sums: out = (in + acc) / px_area   (martini.py:338,364-366)
-__device__ __forceinline__ void store_pixel(double* __restrict__ dst, const double* acc, int nch,
-                                            double px_area, bool add_in, bool vec_ok) {
-  if (vec_ok && nch == CB) {
-#pragma unroll
-    for (int c = 0; c < CB; c += 2) {
-      double2 o;
-      if (add_in) {
-        const double2 i2 = *reinterpret_cast<const double2*>(dst + c);
-        o.x = (i2.x + acc[c]) / px_area;
-        o.y = (i2.y + acc[c + 1]) / px_area;
-      } else {
-        o.x = acc[c] / px_area;
-        o.y = acc[c + 1] / px_area;
-      }
-      *reinterpret_cast<double2*>(dst + c) = o;
+// tile pixel (x, y) of pixel j of warp w's sub-block
+__device__ __forceinline__ int sub_x(int w, int j) { return (w / SUBS_Y) * SUB + (j >> 2); }
+__device__ __forceinline__ int sub_y(int w, int j) { return (w % SUBS_Y) * SUB + (j & 3); }
+
+// One thread stores its two channels of one pixel: out = (in + acc) / px_area
+// (martini.py:338, 364-366).  `nvalid` = how many of the lane's two channels exist.
+__device__ __forceinline__ void store2(double* __restrict__ dst, double a0, double a1, int nvalid,
+                                       double px_area, bool add_in, bool vec_ok) {
+  if (nvalid == 2 && vec_ok) {
+    double2 o;
+    if (add_in) {
+      const double2 i2 = *reinterpret_cast<const double2*>(dst);
+      o.x = (i2.x + a0) / px_area;
+      o.y = (i2.y + a1) / px_area;
+    } else {
+      o.x = a0 / px_area;
+      o.y = a1 / px_area;
     }
+    *reinterpret_cast<double2*>(dst) = o;
   } else {
-#pragma unroll
-    for (int c = 0; c < CB; ++c)
-      if (c < nch) dst[c] = ((add_in ? dst[c] : 0.0) + acc[c]) / px_area;
+    if (nvalid >= 1) dst[0] = ((add_in ? dst[0] : 0.0) + a0) / px_area;
+    if (nvalid >= 2) dst[1] = ((add_in ? dst[1] : 0.0) + a1) / px_area;
   }
 }
 
@@ -164,13 +209,10 @@ __device__ __forceinline__ void store_pixel(double* __restrict__ dst, const doub
 // algorithmic work (non-zero weight x non-zero spectrum terms, kernel integrals, edge erfs);
 // it is never the timed kernel.
 template <bool COUNT>
-__global__ void __launch_bounds__(PROJ_THREADS, 2) project_kernel(const ProjArgs a) {
+__global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel(const ProjArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ProjSmem& sm = *reinterpret_cast<ProjSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // warp -> 4 x 8 pixel sub-block of the tile, lane -> pixel inside it
-  const int sx = (warp >> 1) * SUB_X, sy = (warp & 1) * SUB_Y;
-  const int lx = lane >> 3, ly = lane & 7;
   const Geo& g = a.geo;
   const bool gaussian_line = g.spectrum == MTN_SPECTRUM_GAUSSIAN;
   const double sgn = g.edges_increasing ? 1.0 : -1.0;
@@ -195,19 +237,16 @@ __global__ void __launch_bounds__(PROJ_THREADS, 2) project_kernel(const ProjArgs
     const int ty = tile % g.nty, tx = tile / g.nty;
     const int x0 = g.x_lo + tx * TILE_X, y0 = ty * TILE_Y, c0 = cb * CB;
     const int nch = min(CB, g.C - c0);
-    // this thread's pixel and the warp's sub-block bounds (full-cube pixel coordinates)
-    const int gx = x0 + sx + lx, gy = y0 + sy + ly;
-    const double wx0 = (double)(x0 + sx), wx1 = (double)(x0 + sx + SUB_X - 1);
-    const double wy0 = (double)(y0 + sy), wy1 = (double)(y0 + sy + SUB_Y - 1);
-    const double fx = (double)gx, fy = (double)gy;
+    // pixels of the tile that exist in the slab / cube
+    const int x_last = min(x0 + TILE_X, g.x_hi) - 1, y_last = min(y0 + TILE_Y, g.ny) - 1;
 
-    if (tid <= CB) sm.edge[tid] = a.edges[min(c0 + tid, g.C)];
-    if (tid < CB)
-      sm.inv_dv[tid] = tid < nch ? 1.0 / fabs(a.edges[c0 + tid + 1] - a.edges[c0 + tid]) : 0.0;
+    for (int e = tid; e <= CB; e += PROJ_THREADS) sm.edge[e] = a.edges[min(c0 + e, g.C)];
+    for (int c = tid; c < CB; c += PROJ_THREADS)
+      sm.inv_dv[c] = c < nch ? 1.0 / fabs(a.edges[c0 + c + 1] - a.edges[c0 + c]) : 0.0;
 
-    double acc[CB];
+    double acc[SUB_PIX][2];
 #pragma unroll
-    for (int c = 0; c < CB; ++c) acc[c] = 0.0;
+    for (int j = 0; j < SUB_PIX; ++j) acc[j][0] = acc[j][1] = 0.0;
 
     const uint32_t n_part = it.end - it.begin;
     const uint32_t n_batch = (n_part + PBATCH - 1) / PBATCH;
@@ -223,93 +262,182 @@ __global__ void __launch_bounds__(PROJ_THREADS, 2) project_kernel(const ProjArgs
     };
 
     issue(0);
+    __syncthreads();  // edge table visible before the first setup step reads it
     for (uint32_t b = 0; b < n_batch; ++b) {
       const uint32_t buf = b & 1u;
       const int nb = (int)min((uint32_t)PBATCH, n_part - b * PBATCH);
       if (b + 1 < n_batch) issue(b + 1);
-      if (tid < PBATCH) sm.gmask[tid] = 0;
       mbar_wait(&sm.bar[buf], (phase >> buf) & 1u);
       phase ^= 1u << buf;
-      __syncthreads();  // gmask zeroed, edge table visible, records landed for everyone
 
-      // ---- spectra of the batch, once per CTA ----------------------------------------
-      if (gaussian_line) {
-        for (int idx = tid; idx < nb * (CB + 1); idx += PROJ_THREADS) {
-          const int p = idx / (CB + 1), e = idx - p * (CB + 1);
-          const Record& r = sm.rec[buf][p];
-          sm.E[p][e] = edge_erf(sm.edge[e], r.v, r.inv_s);
-          if (COUNT) n_erf += fabs((sm.edge[e] - r.v) * r.inv_s) < ERF_SAT;
+      // ---- setup (warp 0, lane = particle): box in the tile, window of unsaturated edges --
+      if (warp == 0) {
+        int bx0 = 0, bnx = 0, by0 = 0, bny = 0, e0 = 0, ne = 0;
+        if (lane < nb) {
+          const Record& r = sm.rec[buf][lane];
+          int lo, hi;
+          if (pixel_bounds(r.px, (double)r.r, x0, x_last, lo, hi)) {
+            bx0 = lo - x0;
+            bnx = hi - lo + 1;
+          }
+          if (pixel_bounds(r.py, (double)r.r, y0, y_last, lo, hi)) {
+            by0 = lo - y0;
+            bny = hi - lo + 1;
+          }
+          if (bnx == 0 || bny == 0) bnx = bny = 0;
+          if (gaussian_line) {
+            // g(e) = sgn * (edge[e] - v) * inv_s is non-decreasing in e; unsaturated edges are
+            // those with |g| < ERF_SAT: a contiguous run [e0, e0 + ne)
+            const double v = r.v, sc = sgn * r.inv_s;
+            int l = 0, h = CB + 1;
+            while (l < h) {  // first e with g(e) > -SAT
+              const int m = (l + h) >> 1;
+              if ((sm.edge[m] - v) * sc > -ERF_SAT) h = m; else l = m + 1;
+            }
+            e0 = l;
+            h = CB + 1;
+            while (l < h) {  // first e >= e0 with g(e) >= SAT
+              const int m = (l + h) >> 1;
+              if ((sm.edge[m] - v) * sc >= ERF_SAT) h = m; else l = m + 1;
+            }
+            ne = l - e0;
+          }
         }
-        __syncthreads();
-        for (int idx = tid; idx < nb * CB; idx += PROJ_THREADS) {
-          const int p = idx / CB, c = idx % CB;
-          // 0.5*[erf(hi) - erf(lo)] * A / dv / 2.36e5; the 0.5 lives in amp
-          const double s = sgn * (sm.E[p][c + 1] - sm.E[p][c]) * (sm.rec[buf][p].amp * sm.inv_dv[c]);
-          sm.S[p][c] = s;
-          if (s != 0.0) atomicOr(&sm.gmask[p], 1u << (c >> 3));
-        }
-      } else {
-        for (int idx = tid; idx < nb * CB; idx += PROJ_THREADS) {
-          const int p = idx / CB, c = idx % CB;
-          const double e0 = sm.edge[c], e1 = sm.edge[c + 1];
-          const double f = c < nch ? dirac_channel(fmin(e0, e1), fmax(e0, e1), sm.rec[buf][p].v) : 0.0;
-          const double s = f * (sm.rec[buf][p].amp * sm.inv_dv[c]);
-          sm.S[p][c] = s;
-          if (s != 0.0) atomicOr(&sm.gmask[p], 1u << (c >> 3));
+        sm.box[lane][0] = (uint8_t)bx0;
+        sm.box[lane][1] = (uint8_t)bnx;
+        sm.box[lane][2] = (uint8_t)by0;
+        sm.box[lane][3] = (uint8_t)bny;
+        sm.ewin[lane][0] = (uint8_t)e0;
+        sm.ewin[lane][1] = (uint8_t)ne;
+        const uint32_t area = (uint32_t)(bnx * bny);
+        const uint32_t wi = warp_incl_scan_u32(area, lane);
+        const uint32_t ei = warp_incl_scan_u32((uint32_t)ne, lane);
+        sm.wprefix[lane] = wi - area;
+        sm.eprefix[lane] = ei - (uint32_t)ne;
+        if (lane == 31) {
+          sm.wprefix[32] = wi;
+          sm.eprefix[32] = ei;
         }
       }
       __syncthreads();
 
-      // ---- weights + rank-1 accumulate, per warp ---------------------------------------
-      for (int p = 0; p < nb; ++p) {
-        const uint32_t gm = sm.gmask[p];
-        if (gm == 0) continue;
-        const Record& r = sm.rec[buf][p];
-        const double ppx = r.px, ppy = r.py, rr = (double)r.r;
-        // candidate box of martini.py:272-274 vs the warp's sub-block (warp-uniform)
-        if (!(fabs(__dsub_rn(wx0, ppx)) <= rr || fabs(__dsub_rn(wx1, ppx)) <= rr ||
-              (wx0 < ppx && ppx < wx1)))
-          continue;
-        if (!(fabs(__dsub_rn(wy0, ppy)) <= rr || fabs(__dsub_rn(wy1, ppy)) <= rr ||
-              (wy0 < ppy && ppy < wy1)))
-          continue;
-        double w = 0.0;
-        if (fabs(__dsub_rn(fx, ppx)) <= rr && fabs(__dsub_rn(fy, ppy)) <= rr) {
-          const int kid = r.kid;
-          // dij = pixcoords - ij (martini.py:276)
-          w = kernel_weight(a.table.kind[kid], __dsub_rn(ppx, fx), __dsub_rn(ppy, fy), r.h,
-                            r.inv_h2, a.table.truncate[kid], a.table.norm[kid]);
-        }
-        if (COUNT && fabs(__dsub_rn(fx, ppx)) <= rr && fabs(__dsub_rn(fy, ppy)) <= rr) ++n_w;
-        if (!__any_sync(0xffffffffu, w != 0.0)) continue;
-        const double* Sp = sm.S[p];
-        if (COUNT && w != 0.0) {
-          for (int c = 0; c < CB; ++c) n_upd += Sp[c] != 0.0;
-        }
+      // ---- phase A: kernel integrals (once per pair) and edge erfs (once per live edge) ---
+      {
+        const uint32_t total_w = sm.wprefix[PBATCH];
+        const uint32_t total = total_w + sm.eprefix[PBATCH];
+        for (uint32_t q = tid; q < total; q += PROJ_THREADS) {
+          const bool is_w = q < total_w;
+          const uint32_t* pre = is_w ? sm.wprefix : sm.eprefix;
+          const uint32_t qq = is_w ? q : q - total_w;
+          int lo = 0, hi = nb - 1;  // particle p with pre[p] <= qq < pre[p+1]
 #pragma unroll
-        for (int gq = 0; gq < CB / 8; ++gq) {
-          if (gm & (1u << gq)) {
-#pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-              const double2 s2 = *reinterpret_cast<const double2*>(Sp + gq * 8 + c);
-              acc[gq * 8 + c] = fma(w, s2.x, acc[gq * 8 + c]);
-              acc[gq * 8 + c + 1] = fma(w, s2.y, acc[gq * 8 + c + 1]);
-            }
+          for (int s = 0; s < 5; ++s) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (pre[mid] <= qq) lo = mid; else hi = mid - 1;
+          }
+          const int p = lo;
+          const uint32_t local = qq - pre[p];
+          const Record& r = sm.rec[buf][p];
+          if (is_w) {
+            const int bny = sm.box[p][3];
+            const int ix = (int)(((float)local + 0.5f) / (float)bny);
+            const int iy = (int)local - ix * bny;
+            const int tpx = sm.box[p][0] + ix, tpy = sm.box[p][2] + iy;
+            const int kid = r.kid;
+            // dij = pixcoords - ij (martini.py:276)
+            sm.W[p][tpx * TILE_Y + tpy] =
+                kernel_weight(a.table.kind[kid], __dsub_rn(r.px, (double)(x0 + tpx)),
+                              __dsub_rn(r.py, (double)(y0 + tpy)), r.h, r.inv_h2,
+                              a.table.truncate[kid], a.table.norm[kid]);
+            if (COUNT) ++n_w;
+          } else {
+            const int e = sm.ewin[p][0] + (int)local;
+            // stored in the g orientation (sign folded in): S[c] = E[c+1] - E[c] >= 0
+            sm.ES[p][e] = erf_tab((sm.edge[e] - r.v) * (sgn * r.inv_s));
+            if (COUNT) ++n_erf;
           }
         }
       }
-      __syncthreads();  // S, gmask and rec[buf] are free again
+      __syncthreads();
+
+      // ---- phase B: spectra in place of the edge erfs (warp per particle) ------------------
+      for (int p = warp; p < nb; p += PROJ_WARPS) {
+        const Record& r = sm.rec[buf][p];
+        double s0, s1;
+        const int c = 2 * lane;
+        if (gaussian_line) {
+          const int e0 = sm.ewin[p][0], e1 = e0 + sm.ewin[p][1];  // unsaturated: [e0, e1)
+          auto E = [&](int e) { return e < e0 ? -1.0 : (e >= e1 ? 1.0 : sm.ES[p][e]); };
+          const double ea = E(c), eb = E(c + 1), ec = E(c + 2);
+          // 0.5*[erf(hi) - erf(lo)] * A / dv / 2.36e5; the 0.5 lives in amp
+          s0 = (eb - ea) * (r.amp * sm.inv_dv[c]);
+          s1 = (ec - eb) * (r.amp * sm.inv_dv[c + 1]);
+        } else {
+          const double ea = sm.edge[c], eb = sm.edge[c + 1], ec = sm.edge[c + 2 > CB ? CB : c + 2];
+          const double f0 = c < nch ? dirac_channel(fmin(ea, eb), fmax(ea, eb), r.v) : 0.0;
+          const double f1 = c + 1 < nch ? dirac_channel(fmin(eb, ec), fmax(eb, ec), r.v) : 0.0;
+          s0 = f0 * (r.amp * sm.inv_dv[c]);
+          s1 = f1 * (r.amp * sm.inv_dv[c + 1]);
+        }
+        __syncwarp();  // every lane has read its edges before anyone overwrites them
+        *reinterpret_cast<double2*>(&sm.ES[p][c]) = make_double2(s0, s1);
+        // a particle whose line misses this channel block entirely has an all-zero box
+        if (__ballot_sync(0xffffffffu, s0 != 0.0 || s1 != 0.0) == 0 && lane == 0) sm.box[p][1] = 0;
+      }
+      __syncthreads();
+
+      // ---- warp-private list: which particles touch my sub-block, and on which pixels -----
+      uint32_t mymask = 0;
+      if (lane < nb && sm.box[lane][1] != 0) {
+        const int bx0 = sm.box[lane][0], bx1 = bx0 + sm.box[lane][1];
+        const int by0 = sm.box[lane][2], by1 = by0 + sm.box[lane][3];
+#pragma unroll
+        for (int j = 0; j < SUB_PIX; ++j) {
+          const int tpx = sub_x(warp, j), tpy = sub_y(warp, j);
+          if (tpx >= bx0 && tpx < bx1 && tpy >= by0 && tpy < by1 &&
+              sm.W[lane][tpx * TILE_Y + tpy] != 0.0)
+            mymask |= 1u << j;
+        }
+      }
+      uint32_t rel = __ballot_sync(0xffffffffu, mymask != 0);
+
+      // ---- phase C: acc[pixel][2 channels] += W * S for the masked pixels -----------------
+      while (rel) {
+        const int p = __ffs(rel) - 1;
+        rel &= rel - 1;
+        const uint32_t m = __shfl_sync(0xffffffffu, mymask, p);
+        const double2 s2 = *reinterpret_cast<const double2*>(&sm.ES[p][2 * lane]);
+        const double* Wp = sm.W[p];
+#pragma unroll
+        for (int j = 0; j < SUB_PIX; ++j) {
+          if (m & (1u << j)) {
+            const double w = Wp[sub_x(warp, j) * TILE_Y + sub_y(warp, j)];
+            acc[j][0] = fma(w, s2.x, acc[j][0]);
+            acc[j][1] = fma(w, s2.y, acc[j][1]);
+            if (COUNT) n_upd += (s2.x != 0.0) + (s2.y != 0.0);
+          }
+        }
+      }
+      __syncthreads();  // W, ES, boxes and rec[buf] are free again
     }
 
-    // ---- one store per voxel -----------------------------------------------------------
+    // ---- one store per voxel -------------------------------------------------------------
+    const int nvalid = max(0, min(2, nch - 2 * lane));
     if (it.slot >= 0) {
-      double* dst = a.partials + ((size_t)it.slot * PROJ_THREADS + tid) * CB;
+      double* dst = a.partials + (size_t)it.slot * TILE_PIX * CB + 2 * lane;
 #pragma unroll
-      for (int c = 0; c < CB; c += 2)
-        *reinterpret_cast<double2*>(dst + c) = make_double2(acc[c], acc[c + 1]);
-    } else if (gx < g.x_hi && gy < g.ny) {
-      double* dst = a.slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0;
-      store_pixel(dst, acc, nch, a.px_area, !a.zeroed, (g.C & 1) == 0);
+      for (int j = 0; j < SUB_PIX; ++j)
+        *reinterpret_cast<double2*>(dst + (size_t)(sub_x(warp, j) * TILE_Y + sub_y(warp, j)) * CB) =
+            make_double2(acc[j][0], acc[j][1]);
+    } else if (nvalid > 0) {
+#pragma unroll
+      for (int j = 0; j < SUB_PIX; ++j) {
+        const int gx = x0 + sub_x(warp, j), gy = y0 + sub_y(warp, j);
+        if (gx < g.x_hi && gy < g.ny) {
+          double* dst = a.slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + 2 * lane;
+          store2(dst, acc[j][0], acc[j][1], nvalid, a.px_area, !a.zeroed, (g.C & 1) == 0);
+        }
+      }
     }
   }
   if (COUNT) {
@@ -326,26 +454,23 @@ __global__ void __launch_bounds__(PROJ_THREADS) reduce_partials_kernel(
   if (blockIdx.x >= *n_multi) return;
   const MultiBrick m = multis[blockIdx.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int sx = (warp >> 1) * SUB_X, sy = (warp & 1) * SUB_Y;
   const int cb = m.brick % g.ncb, tile = m.brick / g.ncb;
-  const int gx = g.x_lo + (tile / g.nty) * TILE_X + sx + (lane >> 3);
-  const int gy = (tile % g.nty) * TILE_Y + sy + (lane & 7);
-  const int c0 = cb * CB, nch = min(CB, g.C - c0);
-  double acc[CB];
-#pragma unroll
-  for (int c = 0; c < CB; ++c) acc[c] = 0.0;
-  for (uint32_t j = 0; j < m.n; ++j) {
-    const double* src = partials + ((size_t)(m.slot0 + j) * PROJ_THREADS + tid) * CB;
-#pragma unroll
-    for (int c = 0; c < CB; c += 2) {
-      const double2 v = *reinterpret_cast<const double2*>(src + c);
-      acc[c] += v.x;
-      acc[c + 1] += v.y;
+  const int x0 = g.x_lo + (tile / g.nty) * TILE_X, y0 = (tile % g.nty) * TILE_Y, c0 = cb * CB;
+  const int nvalid = max(0, min(2, min(CB, g.C - c0) - 2 * lane));
+  for (int j = 0; j < SUB_PIX; ++j) {
+    const int tpx = sub_x(warp, j), tpy = sub_y(warp, j);
+    double a0 = 0.0, a1 = 0.0;
+    for (uint32_t k = 0; k < m.n; ++k) {
+      const double2 v = *reinterpret_cast<const double2*>(
+          partials + ((size_t)(m.slot0 + k) * TILE_PIX + tpx * TILE_Y + tpy) * CB + 2 * lane);
+      a0 += v.x;
+      a1 += v.y;
     }
-  }
-  if (gx < g.x_hi && gy < g.ny) {
-    double* dst = slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0;
-    store_pixel(dst, acc, nch, px_area, !zeroed, (g.C & 1) == 0);
+    const int gx = x0 + tpx, gy = y0 + tpy;
+    if (nvalid > 0 && gx < g.x_hi && gy < g.ny) {
+      double* dst = slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + 2 * lane;
+      store2(dst, a0, a1, nvalid, px_area, !zeroed, (g.C & 1) == 0);
+    }
   }
 }
 
@@ -355,14 +480,17 @@ __global__ void __launch_bounds__(PROJ_THREADS) empty_brick_kernel(
   const uint32_t brick = blockIdx.x;
   if (brick_count[brick] != 0) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int sx = (warp >> 1) * SUB_X, sy = (warp & 1) * SUB_Y;
   const int cb = brick % g.ncb, tile = brick / g.ncb;
-  const int gx = g.x_lo + (tile / g.nty) * TILE_X + sx + (lane >> 3);
-  const int gy = (tile % g.nty) * TILE_Y + sy + (lane & 7);
-  const int c0 = cb * CB, nch = min(CB, g.C - c0);
-  if (gx >= g.x_hi || gy >= g.ny) return;
-  double* dst = slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0;
-  for (int c = 0; c < nch; ++c) dst[c] = dst[c] / px_area;
+  const int x0 = g.x_lo + (tile / g.nty) * TILE_X, y0 = (tile % g.nty) * TILE_Y, c0 = cb * CB;
+  const int nvalid = max(0, min(2, min(CB, g.C - c0) - 2 * lane));
+  if (nvalid == 0) return;
+  for (int j = 0; j < SUB_PIX; ++j) {
+    const int gx = x0 + sub_x(warp, j), gy = y0 + sub_y(warp, j);
+    if (gx < g.x_hi && gy < g.ny) {
+      double* dst = slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + 2 * lane;
+      store2(dst, 0.0, 0.0, nvalid, px_area, true, (g.C & 1) == 0);
+    }
+  }
 }
 
 }  // namespace mtn
