@@ -22,11 +22,14 @@ namespace mtn {
 constexpr int TILE_X = MTN_TILE;      // pixels along x (slowest cube axis)
 constexpr int TILE_Y = MTN_TILE;      // pixels along y
 constexpr int TILE_PIX = TILE_X * TILE_Y;
-constexpr int CB = 64;                // channels per brick: each lane owns 2 adjacent channels
+constexpr int CH_HALF = 64;           // channels one warp covers: each lane owns 2 adjacent ones
+constexpr int N_HALF = 1;             // channel halves per brick, handled by different warps (1: brick = 64 channels)
+constexpr int CB = CH_HALF * N_HALF;  // channels per brick (unit of binning)
 constexpr int SUB = 4;                // a warp owns a SUB x SUB pixel sub-block of the tile
 constexpr int SUB_PIX = SUB * SUB;    // = accumulator pairs per thread
 constexpr int SUBS_Y = TILE_Y / SUB;  // sub-blocks per tile row
-constexpr int PROJ_WARPS = TILE_PIX / SUB_PIX;  // 4 (8x8 tile) or 16 (16x16 tile)
+constexpr int N_SUB = TILE_PIX / SUB_PIX;      // sub-blocks per tile
+constexpr int PROJ_WARPS = N_SUB * N_HALF;     // warp = (channel half, sub-block)
 constexpr int PROJ_THREADS = PROJ_WARPS * 32;
 constexpr int PROJ_CTAS_PER_SM = 512 / PROJ_THREADS;  // register-limited: 16 warps per SM
 constexpr int PBATCH = 32;            // particle records staged per batch (= one per lane)

@@ -82,6 +82,18 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t x, int lane) {
   return x;
 }
 
+// index p of the run [pre[p], pre[p+1]) that holds q; pre is a non-decreasing exclusive prefix
+// over n <= 32 entries (runs may be empty: the last p with pre[p] <= q is the owner)
+__device__ __forceinline__ int find_owner(const uint32_t* pre, int n, uint32_t q) {
+  int lo = 0, hi = n - 1;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (pre[mid] <= q) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
 // ------------------------------------------------------------------------------ work items
 // Bricks are found in the sorted pair array by their key boundaries: start[] gets the first
 // index, end_or_count[] the one-past-last index (rewritten to a count by item_count_kernel).
@@ -169,20 +181,25 @@ constexpr int W_STRIDE = TILE_PIX + 1;  // odd row stride: lane-per-particle rea
 struct ProjSmem {
   Record rec[2][PBATCH];
   double W[PBATCH][W_STRIDE];   // kernel integrals, valid inside the particle's box only
-  double ES[PBATCH][CB + 2];    // edge erfs (CB+1 per particle), then spectra S in place
+  double ES[PBATCH][CB + 2];    // edge erfs (up to CB+1 per particle), then spectra S in place
   double edge[CB + 1];
   double inv_dv[CB];
   uint32_t wprefix[PBATCH + 1];  // exclusive prefix of box areas
-  uint32_t eprefix[PBATCH + 1];  // exclusive prefix of unsaturated-edge counts
+  uint32_t eprefix[PBATCH + 1];  // exclusive prefix of edge-run lengths
+  float rny[PBATCH];             // 1 / (box height)
+  uint8_t wowner[PBATCH];        // particles with a non-empty box, in order
+  uint8_t eowner[PBATCH];        // particles with a non-empty edge run, in order
   uint8_t box[PBATCH][4];        // tile-local box: x0, nx, y0, ny
-  uint8_t ewin[PBATCH][2];       // first unsaturated edge, count
+  uint8_t erun[PBATCH][2];       // first edge to evaluate, number of edges
+  uint8_t chan[PBATCH][2];       // live channels of the brick: [cs, ce)
+  uint8_t hlive[PBATCH];         // bit h: channel half h of the brick holds a non-zero
   uint64_t bar[2];
   uint32_t item;
 };
 
-// tile pixel (x, y) of pixel j of warp w's sub-block
-__device__ __forceinline__ int sub_x(int w, int j) { return (w / SUBS_Y) * SUB + (j >> 2); }
-__device__ __forceinline__ int sub_y(int w, int j) { return (w % SUBS_Y) * SUB + (j & 3); }
+// tile pixel (x, y) of pixel j of sub-block s
+__device__ __forceinline__ int sub_x(int s, int j) { return (s / SUBS_Y) * SUB + (j >> 2); }
+__device__ __forceinline__ int sub_y(int s, int j) { return (s % SUBS_Y) * SUB + (j & 3); }
 
 // One thread stores its two channels of one pixel: out = (in + acc) / px_area
 // (martini.py:338, 364-366).  `nvalid` = how many of the lane's two channels exist.
@@ -205,6 +222,17 @@ __device__ __forceinline__ void store2(double* __restrict__ dst, double a0, doub
   }
 }
 
+// Cooperative owner lookup for 32 consecutive enumerated items starting at q0: lane k knows
+// where run k starts (`my_start`, `my_nonempty`); returns for this lane the ordinal (among
+// non-empty runs) of the run that holds item q0 + lane.
+__device__ __forceinline__ int owner_ordinal(uint32_t q0, uint32_t my_start, bool my_nonempty,
+                                             int lane) {
+  const uint32_t before = __popc(__ballot_sync(0xffffffffu, my_nonempty && my_start < q0));
+  const uint32_t rel = my_start - q0;
+  const uint32_t H = __reduce_or_sync(0xffffffffu, (my_nonempty && rel < 32u) ? (1u << rel) : 0u);
+  return (int)(before + __popc(H & ((2u << lane) - 1u))) - 1;
+}
+
 // COUNT = true is a diagnostic instantiation that additionally tallies the executed
 // algorithmic work (non-zero weight x non-zero spectrum terms, kernel integrals, edge erfs);
 // it is never the timed kernel.
@@ -213,6 +241,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ProjSmem& sm = *reinterpret_cast<ProjSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp / N_SUB, sub = warp % N_SUB;  // this warp's channel half and sub-block
   const Geo& g = a.geo;
   const bool gaussian_line = g.spectrum == MTN_SPECTRUM_GAUSSIAN;
   const double sgn = g.edges_increasing ? 1.0 : -1.0;
@@ -270,79 +299,100 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
       mbar_wait(&sm.bar[buf], (phase >> buf) & 1u);
       phase ^= 1u << buf;
 
-      // ---- setup (warp 0, lane = particle): box in the tile, window of unsaturated edges --
+      // ---- setup (warp 0, lane = particle): live channels, edge run, box in the tile -------
       if (warp == 0) {
-        int bx0 = 0, bnx = 0, by0 = 0, bny = 0, e0 = 0, ne = 0;
+        int bx0 = 0, bnx = 0, by0 = 0, bny = 0, w0 = 0, nw = 0, cs = 0, ce = 0;
         if (lane < nb) {
           const Record& r = sm.rec[buf][lane];
-          int lo, hi;
-          if (pixel_bounds(r.px, (double)r.r, x0, x_last, lo, hi)) {
-            bx0 = lo - x0;
-            bnx = hi - lo + 1;
+          // g(e) = sgn * (edge[e] - v) * inv_s is non-decreasing in the edge index e
+          const double v = r.v, sc = gaussian_line ? sgn * r.inv_s : sgn;
+          const double lo_t = gaussian_line ? -ERF_SAT : 0.0, hi_t = gaussian_line ? ERF_SAT : 0.0;
+          int l = 0, h = CB + 1;
+          while (l < h) {  // e0: first edge with g > -SAT (Gaussian) / g >= 0 (Dirac)
+            const int m = (l + h) >> 1;
+            const double x = (sm.edge[m] - v) * sc;
+            if (gaussian_line ? (x > lo_t) : (x >= lo_t)) h = m; else l = m + 1;
           }
-          if (pixel_bounds(r.py, (double)r.r, y0, y_last, lo, hi)) {
-            by0 = lo - y0;
-            bny = hi - lo + 1;
+          const int e0 = l;
+          l = gaussian_line ? e0 : 0;
+          h = CB + 1;
+          while (l < h) {  // e1: first edge with g >= SAT (Gaussian) / g > 0 (Dirac)
+            const int m = (l + h) >> 1;
+            const double x = (sm.edge[m] - v) * sc;
+            if (gaussian_line ? (x >= hi_t) : (x > hi_t)) h = m; else l = m + 1;
           }
-          if (bnx == 0 || bny == 0) bnx = bny = 0;
-          if (gaussian_line) {
-            // g(e) = sgn * (edge[e] - v) * inv_s is non-decreasing in e; unsaturated edges are
-            // those with |g| < ERF_SAT: a contiguous run [e0, e0 + ne)
-            const double v = r.v, sc = sgn * r.inv_s;
-            int l = 0, h = CB + 1;
-            while (l < h) {  // first e with g(e) > -SAT
-              const int m = (l + h) >> 1;
-              if ((sm.edge[m] - v) * sc > -ERF_SAT) h = m; else l = m + 1;
+          const int e1 = l;
+          // channel c can be non-zero only if edge c+1 >= e0 and edge c < e1:
+          //   Gaussian: some edge of the channel is unsaturated, or the saturation flips in it
+          //   Dirac   : lo <= v <= hi, both closed (spectral_models.py:564-569)
+          cs = max(e0 - 1, 0);
+          ce = min(e1, nch);
+          if (cs >= ce) cs = ce = 0;
+          if (ce > cs) {
+            if (gaussian_line) {  // edges to evaluate: the live channels' edges
+              w0 = cs;
+              nw = ce - cs + 1;
             }
-            e0 = l;
-            h = CB + 1;
-            while (l < h) {  // first e >= e0 with g(e) >= SAT
-              const int m = (l + h) >> 1;
-              if ((sm.edge[m] - v) * sc >= ERF_SAT) h = m; else l = m + 1;
+            int lo, hi;
+            if (pixel_bounds(r.px, (double)r.r, x0, x_last, lo, hi)) {
+              bx0 = lo - x0;
+              bnx = hi - lo + 1;
             }
-            ne = l - e0;
+            if (pixel_bounds(r.py, (double)r.r, y0, y_last, lo, hi)) {
+              by0 = lo - y0;
+              bny = hi - lo + 1;
+            }
+            if (bnx == 0 || bny == 0) bnx = bny = 0;
           }
         }
         sm.box[lane][0] = (uint8_t)bx0;
         sm.box[lane][1] = (uint8_t)bnx;
         sm.box[lane][2] = (uint8_t)by0;
         sm.box[lane][3] = (uint8_t)bny;
-        sm.ewin[lane][0] = (uint8_t)e0;
-        sm.ewin[lane][1] = (uint8_t)ne;
+        sm.rny[lane] = bny ? 1.0f / (float)bny : 0.0f;
+        sm.erun[lane][0] = (uint8_t)w0;
+        sm.erun[lane][1] = (uint8_t)nw;
+        sm.chan[lane][0] = (uint8_t)cs;
+        sm.chan[lane][1] = (uint8_t)ce;
+        uint32_t hl = 0;
+#pragma unroll
+        for (int hh = 0; hh < N_HALF; ++hh)
+          if (cs < (hh + 1) * CH_HALF && ce > hh * CH_HALF) hl |= 1u << hh;
+        sm.hlive[lane] = (uint8_t)hl;
         const uint32_t area = (uint32_t)(bnx * bny);
+        const uint32_t ne = area ? (uint32_t)nw : 0u;  // no pixels, no spectrum needed
         const uint32_t wi = warp_incl_scan_u32(area, lane);
-        const uint32_t ei = warp_incl_scan_u32((uint32_t)ne, lane);
+        const uint32_t ei = warp_incl_scan_u32(ne, lane);
         sm.wprefix[lane] = wi - area;
-        sm.eprefix[lane] = ei - (uint32_t)ne;
+        sm.eprefix[lane] = ei - ne;
         if (lane == 31) {
           sm.wprefix[32] = wi;
           sm.eprefix[32] = ei;
         }
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t wm = __ballot_sync(0xffffffffu, area != 0), em = __ballot_sync(0xffffffffu, ne != 0);
+        if (area != 0) sm.wowner[__popc(wm & lt)] = (uint8_t)lane;
+        if (ne != 0) sm.eowner[__popc(em & lt)] = (uint8_t)lane;
       }
       __syncthreads();
 
       // ---- phase A: kernel integrals (once per pair) and edge erfs (once per live edge) ---
+      // Items are enumerated through the prefix sums; a warp takes 32 consecutive items, so
+      // its lanes mostly share a particle (coherent branches, conflict-free rows).
       {
-        const uint32_t total_w = sm.wprefix[PBATCH];
-        const uint32_t total = total_w + sm.eprefix[PBATCH];
-        for (uint32_t q = tid; q < total; q += PROJ_THREADS) {
-          const bool is_w = q < total_w;
-          const uint32_t* pre = is_w ? sm.wprefix : sm.eprefix;
-          const uint32_t qq = is_w ? q : q - total_w;
-          int lo = 0, hi = nb - 1;  // particle p with pre[p] <= qq < pre[p+1]
-#pragma unroll
-          for (int s = 0; s < 5; ++s) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (pre[mid] <= qq) lo = mid; else hi = mid - 1;
-          }
-          const int p = lo;
-          const uint32_t local = qq - pre[p];
-          const Record& r = sm.rec[buf][p];
-          if (is_w) {
-            const int bny = sm.box[p][3];
-            const int ix = (int)(((float)local + 0.5f) / (float)bny);
-            const int iy = (int)local - ix * bny;
+        const uint32_t total = sm.wprefix[PBATCH];
+        const uint32_t my_start = sm.wprefix[lane];
+        const bool my_nonempty = sm.wprefix[lane + 1] > my_start;
+        for (uint32_t q0 = warp * 32; q0 < total; q0 += PROJ_THREADS) {
+          const uint32_t q = q0 + lane;
+          const int ord = owner_ordinal(q0, my_start, my_nonempty, lane);
+          if (q < total) {
+            const int p = sm.wowner[ord];
+            const uint32_t local = q - sm.wprefix[p];
+            const int ix = (int)(((float)local + 0.5f) * sm.rny[p]);
+            const int iy = (int)local - ix * sm.box[p][3];
             const int tpx = sm.box[p][0] + ix, tpy = sm.box[p][2] + iy;
+            const Record& r = sm.rec[buf][p];
             const int kid = r.kid;
             // dij = pixcoords - ij (martini.py:276)
             sm.W[p][tpx * TILE_Y + tpy] =
@@ -350,11 +400,25 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
                               __dsub_rn(r.py, (double)(y0 + tpy)), r.h, r.inv_h2,
                               a.table.truncate[kid], a.table.norm[kid]);
             if (COUNT) ++n_w;
-          } else {
-            const int e = sm.ewin[p][0] + (int)local;
-            // stored in the g orientation (sign folded in): S[c] = E[c+1] - E[c] >= 0
-            sm.ES[p][e] = erf_tab((sm.edge[e] - r.v) * (sgn * r.inv_s));
-            if (COUNT) ++n_erf;
+          }
+        }
+      }
+      if (gaussian_line) {
+        const uint32_t total = sm.eprefix[PBATCH];
+        const uint32_t my_start = sm.eprefix[lane];
+        const bool my_nonempty = sm.eprefix[lane + 1] > my_start;
+        for (uint32_t q0 = warp * 32; q0 < total; q0 += PROJ_THREADS) {
+          const uint32_t q = q0 + lane;
+          const int ord = owner_ordinal(q0, my_start, my_nonempty, lane);
+          if (q < total) {
+            const int p = sm.eowner[ord];
+            const int e = sm.erun[p][0] + (int)(q - sm.eprefix[p]);
+            const Record& r = sm.rec[buf][p];
+            // g orientation (sign folded in): S[c] = E[c+1] - E[c] >= 0; saturated edges at
+            // the ends of the run come out as exactly -1 / +1
+            const double t = (sm.edge[e] - r.v) * (sgn * r.inv_s);
+            sm.ES[p][e] = erf_tab(t);
+            if (COUNT) n_erf += fabs(t) < ERF_SAT;
           }
         }
       }
@@ -362,38 +426,42 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
 
       // ---- phase B: spectra in place of the edge erfs (warp per particle) ------------------
       for (int p = warp; p < nb; p += PROJ_WARPS) {
+        const int cs = sm.chan[p][0], ce = sm.chan[p][1];
+        if (sm.wprefix[p + 1] == sm.wprefix[p] || ce <= cs) continue;  // nothing to add
         const Record& r = sm.rec[buf][p];
-        double s0, s1;
-        const int c = 2 * lane;
-        if (gaussian_line) {
-          const int e0 = sm.ewin[p][0], e1 = e0 + sm.ewin[p][1];  // unsaturated: [e0, e1)
-          auto E = [&](int e) { return e < e0 ? -1.0 : (e >= e1 ? 1.0 : sm.ES[p][e]); };
-          const double ea = E(c), eb = E(c + 1), ec = E(c + 2);
-          // 0.5*[erf(hi) - erf(lo)] * A / dv / 2.36e5; the 0.5 lives in amp
-          s0 = (eb - ea) * (r.amp * sm.inv_dv[c]);
-          s1 = (ec - eb) * (r.amp * sm.inv_dv[c + 1]);
-        } else {
-          const double ea = sm.edge[c], eb = sm.edge[c + 1], ec = sm.edge[c + 2 > CB ? CB : c + 2];
-          const double f0 = c < nch ? dirac_channel(fmin(ea, eb), fmax(ea, eb), r.v) : 0.0;
-          const double f1 = c + 1 < nch ? dirac_channel(fmin(eb, ec), fmax(eb, ec), r.v) : 0.0;
-          s0 = f0 * (r.amp * sm.inv_dv[c]);
-          s1 = f1 * (r.amp * sm.inv_dv[c + 1]);
+        double s[N_HALF][2];
+#pragma unroll
+        for (int hh = 0; hh < N_HALF; ++hh) {
+          const int c = hh * CH_HALF + 2 * lane;
+          const bool in0 = c >= cs && c < ce, in1 = c + 1 >= cs && c + 1 < ce;
+          if (gaussian_line) {
+            const double2 eab = *reinterpret_cast<const double2*>(&sm.ES[p][c]);
+            const double ec = sm.ES[p][c + 2];
+            // 0.5*[erf(hi) - erf(lo)] * A / dv / 2.36e5; the 0.5 lives in amp
+            s[hh][0] = in0 ? (eab.y - eab.x) * (r.amp * sm.inv_dv[c]) : 0.0;
+            s[hh][1] = in1 ? (ec - eab.y) * (r.amp * sm.inv_dv[c + 1]) : 0.0;
+          } else {
+            // live channels are exactly those with lo <= v <= hi (setup)
+            s[hh][0] = in0 ? r.amp * sm.inv_dv[c] : 0.0;
+            s[hh][1] = in1 ? r.amp * sm.inv_dv[c + 1] : 0.0;
+          }
         }
         __syncwarp();  // every lane has read its edges before anyone overwrites them
-        *reinterpret_cast<double2*>(&sm.ES[p][c]) = make_double2(s0, s1);
-        // a particle whose line misses this channel block entirely has an all-zero box
-        if (__ballot_sync(0xffffffffu, s0 != 0.0 || s1 != 0.0) == 0 && lane == 0) sm.box[p][1] = 0;
+#pragma unroll
+        for (int hh = 0; hh < N_HALF; ++hh)
+          *reinterpret_cast<double2*>(&sm.ES[p][hh * CH_HALF + 2 * lane]) =
+              make_double2(s[hh][0], s[hh][1]);
       }
       __syncthreads();
 
       // ---- warp-private list: which particles touch my sub-block, and on which pixels -----
       uint32_t mymask = 0;
-      if (lane < nb && sm.box[lane][1] != 0) {
+      if (lane < nb && sm.box[lane][1] != 0 && ((sm.hlive[lane] >> half) & 1u)) {
         const int bx0 = sm.box[lane][0], bx1 = bx0 + sm.box[lane][1];
         const int by0 = sm.box[lane][2], by1 = by0 + sm.box[lane][3];
 #pragma unroll
         for (int j = 0; j < SUB_PIX; ++j) {
-          const int tpx = sub_x(warp, j), tpy = sub_y(warp, j);
+          const int tpx = sub_x(sub, j), tpy = sub_y(sub, j);
           if (tpx >= bx0 && tpx < bx1 && tpy >= by0 && tpy < by1 &&
               sm.W[lane][tpx * TILE_Y + tpy] != 0.0)
             mymask |= 1u << j;
@@ -406,12 +474,12 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         const int p = __ffs(rel) - 1;
         rel &= rel - 1;
         const uint32_t m = __shfl_sync(0xffffffffu, mymask, p);
-        const double2 s2 = *reinterpret_cast<const double2*>(&sm.ES[p][2 * lane]);
+        const double2 s2 = *reinterpret_cast<const double2*>(&sm.ES[p][half * CH_HALF + 2 * lane]);
         const double* Wp = sm.W[p];
 #pragma unroll
         for (int j = 0; j < SUB_PIX; ++j) {
           if (m & (1u << j)) {
-            const double w = Wp[sub_x(warp, j) * TILE_Y + sub_y(warp, j)];
+            const double w = Wp[sub_x(sub, j) * TILE_Y + sub_y(sub, j)];
             acc[j][0] = fma(w, s2.x, acc[j][0]);
             acc[j][1] = fma(w, s2.y, acc[j][1]);
             if (COUNT) n_upd += (s2.x != 0.0) + (s2.y != 0.0);
@@ -422,19 +490,20 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
     }
 
     // ---- one store per voxel -------------------------------------------------------------
-    const int nvalid = max(0, min(2, nch - 2 * lane));
+    const int cl = half * CH_HALF + 2 * lane;  // this lane's first channel within the brick
+    const int nvalid = max(0, min(2, nch - cl));
     if (it.slot >= 0) {
-      double* dst = a.partials + (size_t)it.slot * TILE_PIX * CB + 2 * lane;
+      double* dst = a.partials + (size_t)it.slot * TILE_PIX * CB + cl;
 #pragma unroll
       for (int j = 0; j < SUB_PIX; ++j)
-        *reinterpret_cast<double2*>(dst + (size_t)(sub_x(warp, j) * TILE_Y + sub_y(warp, j)) * CB) =
+        *reinterpret_cast<double2*>(dst + (size_t)(sub_x(sub, j) * TILE_Y + sub_y(sub, j)) * CB) =
             make_double2(acc[j][0], acc[j][1]);
     } else if (nvalid > 0) {
 #pragma unroll
       for (int j = 0; j < SUB_PIX; ++j) {
-        const int gx = x0 + sub_x(warp, j), gy = y0 + sub_y(warp, j);
+        const int gx = x0 + sub_x(sub, j), gy = y0 + sub_y(sub, j);
         if (gx < g.x_hi && gy < g.ny) {
-          double* dst = a.slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + 2 * lane;
+          double* dst = a.slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + cl;
           store2(dst, acc[j][0], acc[j][1], nvalid, a.px_area, !a.zeroed, (g.C & 1) == 0);
         }
       }
@@ -456,19 +525,20 @@ __global__ void __launch_bounds__(PROJ_THREADS) reduce_partials_kernel(
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cb = m.brick % g.ncb, tile = m.brick / g.ncb;
   const int x0 = g.x_lo + (tile / g.nty) * TILE_X, y0 = (tile % g.nty) * TILE_Y, c0 = cb * CB;
-  const int nvalid = max(0, min(2, min(CB, g.C - c0) - 2 * lane));
+  const int half = warp / N_SUB, sub = warp % N_SUB, cl = half * CH_HALF + 2 * lane;
+  const int nvalid = max(0, min(2, min(CB, g.C - c0) - cl));
   for (int j = 0; j < SUB_PIX; ++j) {
-    const int tpx = sub_x(warp, j), tpy = sub_y(warp, j);
+    const int tpx = sub_x(sub, j), tpy = sub_y(sub, j);
     double a0 = 0.0, a1 = 0.0;
     for (uint32_t k = 0; k < m.n; ++k) {
       const double2 v = *reinterpret_cast<const double2*>(
-          partials + ((size_t)(m.slot0 + k) * TILE_PIX + tpx * TILE_Y + tpy) * CB + 2 * lane);
+          partials + ((size_t)(m.slot0 + k) * TILE_PIX + tpx * TILE_Y + tpy) * CB + cl);
       a0 += v.x;
       a1 += v.y;
     }
     const int gx = x0 + tpx, gy = y0 + tpy;
     if (nvalid > 0 && gx < g.x_hi && gy < g.ny) {
-      double* dst = slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + 2 * lane;
+      double* dst = slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + cl;
       store2(dst, a0, a1, nvalid, px_area, !zeroed, (g.C & 1) == 0);
     }
   }
@@ -482,12 +552,13 @@ __global__ void __launch_bounds__(PROJ_THREADS) empty_brick_kernel(
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cb = brick % g.ncb, tile = brick / g.ncb;
   const int x0 = g.x_lo + (tile / g.nty) * TILE_X, y0 = (tile % g.nty) * TILE_Y, c0 = cb * CB;
-  const int nvalid = max(0, min(2, min(CB, g.C - c0) - 2 * lane));
+  const int half = warp / N_SUB, sub = warp % N_SUB, cl = half * CH_HALF + 2 * lane;
+  const int nvalid = max(0, min(2, min(CB, g.C - c0) - cl));
   if (nvalid == 0) return;
   for (int j = 0; j < SUB_PIX; ++j) {
-    const int gx = x0 + sub_x(warp, j), gy = y0 + sub_y(warp, j);
+    const int gx = x0 + sub_x(sub, j), gy = y0 + sub_y(sub, j);
     if (gx < g.x_hi && gy < g.ny) {
-      double* dst = slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + 2 * lane;
+      double* dst = slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + cl;
       store2(dst, 0.0, 0.0, nvalid, px_area, true, (g.C & 1) == 0);
     }
   }
