@@ -206,6 +206,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
+    from martini_b200 import dist as mdist
     from martini_b200 import pipeline
     from martini_b200.engine import Engine
 
@@ -223,8 +224,8 @@ def run_b200(args):
     case = make_workload(args.workload, n_gpus, args.particles)
     ctx = pipeline.prepare(case)
     nx, ny, nc = ctx.shape
-    rows = nx // n_gpus
-    x_lo, x_hi = rank * rows, (rank + 1) * rows if rank < n_gpus - 1 else nx
+    bounds = mdist.slab_bounds(nx, n_gpus)  # the weak-scaled discs are identical: equal rows
+    x_lo, x_hi = bounds[rank], bounds[rank + 1]
     pinned = pipeline.pin_case(case)
     dev = pipeline.upload(eng, case, pinned)
     slab = torch.zeros((x_hi - x_lo, ny, nc), dtype=torch.float64, device=dev_t)
@@ -235,9 +236,7 @@ def run_b200(args):
     def gather():
         if world == 1:
             return slab
-        lst = [full[r * rows:(r + 1) * rows if r < world - 1 else nx] for r in range(world)] if rank == 0 else None
-        dist.gather(slab, lst, dst=0)
-        return full
+        return mdist.gather_slabs(slab, bounds, full, dst=0)
 
     def step(e2e=False):
         if e2e:

@@ -1,0 +1,121 @@
+"""Multi-GPU decomposition of the projection: one process per GPU, the cube split into
+contiguous x-slabs.
+
+The path shards naturally.  Voxels are independent outputs and a particle only reaches the
+pixels of its candidate box, so rank r computes rows ``[x_lo, x_hi)`` of the cube from the
+particles whose box touches those rows (every rank filters the full particle list on the
+device with ``mtn_plan``; particles straddling a boundary are simply processed by both
+neighbours -- halo replication -- and each rank writes only its own rows).  There is no
+reduction and no atomics, so the assembled cube is the single-GPU cube.  x is the slowest
+array axis of the C-ordered ``(nx, ny, C)`` cube, hence a slab is one contiguous byte range
+and assembly is a pure concatenation: the one exchange step is a gather of slabs (NCCL over
+NVLink; gloo in the CPU tests).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+TILE = 8  # slab boundaries are kept on brick boundaries (csrc/common.cuh: MTN_TILE)
+
+
+def row_work(px, sm_range, nx, ny_weight=None):
+    """Per-row work estimate: how many particle boxes cover each cube row (optionally
+    weighted, e.g. by box height x live channels).  ``px``/``sm_range`` are host arrays."""
+    lo = np.clip(np.ceil(px - sm_range), 0, nx).astype(np.int64)
+    hi = np.clip(np.floor(px + sm_range) + 1, 0, nx).astype(np.int64)
+    ok = hi > lo
+    w = np.ones(px.shape) if ny_weight is None else np.asarray(ny_weight, dtype=np.float64)
+    diff = np.zeros(nx + 1)
+    np.add.at(diff, lo[ok], w[ok])
+    np.add.at(diff, hi[ok], -w[ok])
+    return np.cumsum(diff)[:nx]
+
+
+def slab_bounds(nx, world, work=None, align=TILE):
+    """``world + 1`` row boundaries 0 = b_0 <= ... <= b_world = nx.
+
+    Without ``work`` the rows are split evenly; with a per-row work estimate the boundaries
+    equalise the work prefix sum instead of the area.  Interior boundaries are multiples of
+    ``align`` so every slab starts on a brick boundary."""
+    if world < 1 or nx < 1:
+        raise ValueError("need world >= 1 and nx >= 1")
+    if work is None:
+        work = np.ones(nx)
+    work = np.asarray(work, dtype=np.float64) + 1e-12 * (np.sum(work) / nx + 1.0)  # strictly increasing prefix
+    prefix = np.concatenate(([0.0], np.cumsum(work)))
+    targets = prefix[-1] * np.arange(1, world) / world
+    cuts = np.searchsorted(prefix, targets)
+    cuts = (np.round(cuts / align) * align).astype(int)
+    b = np.concatenate(([0], np.clip(cuts, 0, nx), [nx]))
+    return np.maximum.accumulate(b).tolist()
+
+
+def gather_slabs(slab: torch.Tensor, bounds, full: torch.Tensor | None = None, dst: int = 0):
+    """Assemble the cube on rank ``dst`` from every rank's slab (rows bounds[r]:bounds[r+1]).
+
+    ``full`` (only needed on ``dst``) is the preallocated (nx, ny, C) result.  Slabs may have
+    different heights (work-balanced partition): rank ``dst`` posts one receive per peer
+    directly into the destination rows of ``full`` -- slabs are contiguous byte ranges, so no
+    staging copy is needed -- and copies its own slab locally."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        if full is not None and full.data_ptr() != slab.data_ptr():
+            full.copy_(slab)
+        return slab if full is None else full
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if rank == dst:
+        assert full is not None and full.shape[0] == bounds[-1]
+        reqs = []
+        for r in range(world):
+            rows = full[bounds[r]:bounds[r + 1]]
+            if r == dst:
+                rows.copy_(slab)
+            elif rows.numel():
+                reqs.append(dist.irecv(rows, src=r))
+        for q in reqs:
+            q.wait()
+        return full
+    if slab.numel():
+        dist.send(slab, dst=dst)
+    return None
+
+
+def allgather_slabs(slab: torch.Tensor, bounds, full: torch.Tensor):
+    """Every rank ends up with the whole cube (for callers that continue on all GPUs)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        full.copy_(slab)
+        return full
+    world = dist.get_world_size()
+    for r in range(world):
+        rows = full[bounds[r]:bounds[r + 1]]
+        if r == dist.get_rank():
+            rows.copy_(slab)
+        if rows.numel():
+            dist.broadcast(rows, src=r)
+    return full
+
+
+def insert_sharded(engine, case, dev=None, ctx=None, bounds=None, gather=True, full=None):
+    """Run the hot path for this rank's slab and (optionally) gather the cube on rank 0.
+
+    Returns (result dict of run_hot_path, assembled cube or None)."""
+    from . import pipeline
+
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    ctx = ctx or pipeline.prepare(case)
+    nx, ny, nc = ctx.shape
+    bounds = bounds or slab_bounds(nx, world)
+    x_lo, x_hi = bounds[rank], bounds[rank + 1]
+    if dev is None:
+        dev = pipeline.upload(engine, case)
+    slab = torch.zeros((x_hi - x_lo, ny, nc), dtype=torch.float64, device=engine.device)
+    out = pipeline.run_hot_path(engine, case, dev=dev, cube=slab, x_lo=x_lo, x_hi=x_hi, zeroed=True, ctx=ctx)
+    cube = None
+    if gather:
+        if rank == 0 and full is None:
+            full = torch.empty((nx, ny, nc), dtype=torch.float64, device=engine.device)
+        cube = gather_slabs(slab, bounds, full, dst=0)
+    return out, cube

@@ -1,0 +1,277 @@
+"""``Martini`` / ``GlobalProfile`` with the reference's constructor and method signatures
+(martini/martini.py), running the particle->datacube projection on the GPU.
+
+What changes relative to the reference is *where* four things run:
+
+* ``_prune_particles``            (martini.py:168-241)  -> ``mtn_prune``            (K1)
+* ``sph_kernel._init_sm_ranges`` / adaptive selection  -> ``mtn_smoothing_setup``  (K0)
+* ``spectral_model.init_spectra`` (spectral_models.py:63-147), ``sph_kernel._px_weight``
+  (sph_kernels.py:85-119) and the pixel loop of ``_insert_source_in_cube``
+  (martini.py:285-366)                                  -> ``mtn_plan`` + ``mtn_project``
+
+Everything else keeps the reference's semantics: the constructor pads the cube for the beam,
+initialises coordinates, prunes (raising ``RuntimeError("No non-zero mHI source particles in
+target region.")`` when nothing is left) and applies the mask to the host objects;
+``insert_source_in_cube`` validates the kernel (``RuntimeError`` ... "use this with care"
+unless ``skip_validation``), *adds* to whatever the cube holds and converts Jy/pix^2 to
+Jy/arcsec^2.  ``spectral_model.spectra`` stays ``None`` unless ``init_spectra()`` is called:
+the N x C spectra array is never needed.  Kernels or spectral models that are not the
+built-in classes raise ``NotImplementedError`` -- there is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .datacube import DataCube
+from .engine import Engine
+from .spectral_models import check_monotonic, spectrum_kind
+from .sph_kernels import DiracDeltaKernel, kernel_table
+
+
+class _BaseMartini:
+    """martini.py:47-624 (hot-path part)."""
+
+    def __init__(self, *, source, datacube, beam=None, noise=None, sph_kernel, spectral_model,
+                 quiet=False, _prune_kwargs=None, device="cuda:0", engine=None):
+        self.quiet = quiet
+        self.source = source
+        self._datacube = datacube
+        self.beam = beam
+        self.noise = noise
+        self.sph_kernel = sph_kernel
+        self.spectral_model = spectral_model
+        # unsupported plug-ins fail here, before any work (no CPU fallback)
+        self._table = kernel_table(sph_kernel)
+        self._spectrum = spectrum_kind(spectral_model)
+        self.engine = engine or Engine(device)
+        sph_kernel._engine = self.engine
+
+        if self.beam is not None:
+            self.beam.init_kernel(self._datacube)
+            self._datacube.add_pad(self.beam.needs_pad())
+
+        self.source._init_skycoords()
+        self.source._init_pixcoords(self._datacube)  # after datacube is padded
+        self._init_device_particles()
+        self._prune_particles(**(_prune_kwargs or {}))
+
+    # ------------------------------------------------------------------ device state
+    def _init_device_particles(self):
+        """Upload the seam arrays and run K0 (sph_kernels.py:235-262, 1241-1274)."""
+        eng, src = self.engine, self.source
+        n = src.npart
+        self._dev = {
+            "px": eng.to_device(src.pixcoords[0]), "py": eng.to_device(src.pixcoords[1]),
+            "pz": eng.to_device(src.pixcoords[2]),
+            "sm_length": eng.to_device(src.sm_lengths_px(self._datacube)),
+            "v": eng.to_device(src.radial_velocity),
+            "D": eng.to_device(np.broadcast_to(src.distance_p, (n,))),
+        }
+        self._dev["mHI"] = (eng.to_device(src.mHI_g) if np.ndim(src.mHI_g) > 0 else float(src.mHI_g))
+        hw = self.spectral_model.half_width(src)
+        self._dev["sigma"] = eng.to_device(hw) if np.ndim(hw) > 0 else float(hw)
+        kid, valid, sm_range, h_eff = eng.smoothing_setup(self._dev["sm_length"], self._table)
+        self._dev.update(kernel_id=kid, valid=valid, sm_range=sm_range, h_eff=h_eff)
+        self.sph_kernel._set_device_state(
+            self._dev["sm_length"].cpu().numpy(), sm_range.cpu().numpy(),
+            kid.cpu().numpy(), valid.cpu().numpy())
+
+    def _prune_particles(self, spatial=True, spectral=True, mass=True, obj_type_str="data cube"):
+        """martini.py:168-241; the accept mask is computed on the GPU and applied to the host
+        objects exactly like the reference (:233-234)."""
+        if not self.quiet:
+            print(f"Source module contained {self.source.npart} particles with total HI mass of "
+                  f"{np.sum(np.broadcast_to(self.source.mHI_g, (self.source.npart,))):.2e} Msun.")
+        dc, d = self._datacube, self._dev
+        edges = dc.velocity_channel_edges
+        check_monotonic(edges)
+        nx_tot, ny_tot = dc.n_px_x + 2 * dc.padx, dc.n_px_y + 2 * dc.pady
+        accept, _ = self.engine.prune(d["px"], d["py"], d["pz"], d["sm_range"], d["mHI"], d["sigma"],
+                                      float(np.max(np.abs(np.diff(edges)))), nx_tot, ny_tot,
+                                      dc.n_channels, spatial, spectral, mass)
+        self._dev["accept"] = accept
+        mask = accept.cpu().numpy().astype(bool)
+        self.source.apply_mask(mask)       # raises RuntimeError if nothing is left
+        self.sph_kernel._apply_mask(mask)
+        if not self.quiet:
+            print(f"Pruned particles that will not contribute to {obj_type_str}, "
+                  f"{self.source.npart} particles remaining with total HI mass of "
+                  f"{np.sum(np.broadcast_to(self.source.mHI_g, (self.source.npart,))):.2e} Msun.")
+
+    # ------------------------------------------------------------------ public methods
+    def init_spectra(self):
+        """martini.py:153-166.  Optional here: insertion never needs the N x C array."""
+        if not self.quiet:
+            print("Initializing spectra...")
+        self.spectral_model.init_spectra(self.source, self._datacube, engine=self.engine)
+        if not self.quiet:
+            print("Spectra initialized.")
+
+    def _insert_source_in_cube(self, skip_validation=False, progressbar=None, ncpu=1, quiet=None):
+        """martini.py:285-407.  ``progressbar`` and ``ncpu`` are accepted and ignored."""
+        dc = self._datacube
+        if dc.array_unit != "Jy/pix2":
+            raise RuntimeError("The data cube already holds an inserted source; call reset() first.")
+        self.sph_kernel._confirm_validation(noraise=skip_validation, quiet=self.quiet)
+        eng, d = self.engine, self._dev
+        arr = dc._array
+        shape3 = arr.shape[:3]
+        zero = not arr.any()
+        cube = (torch.zeros(shape3, dtype=torch.float64, device=eng.device) if zero
+                else eng.to_device(np.ascontiguousarray(arr.reshape(shape3))))
+        edges = eng.to_device(dc.velocity_channel_edges)
+        gauss = self._spectrum == L.SPECTRUM_GAUSSIAN
+        plan = eng.insert(px=d["px"], py=d["py"], h_eff=d["h_eff"], sm_range=d["sm_range"], v=d["v"],
+                          kernel_id=d["kernel_id"], sigma=d["sigma"] if gauss else 1.0,
+                          mHI=d["mHI"], D=d["D"], accept=d["accept"], table=self._table,
+                          spectrum=self._spectrum, edges=edges, cube=cube,
+                          px_size_arcsec=dc.px_size, zeroed=zero)
+        dc._array = cube.cpu().numpy().reshape(arr.shape)
+        dc.array_unit = "Jy/arcsec2"
+        self.last_plan = plan
+        if (quiet is None and not self.quiet) or (quiet is not None and not quiet):
+            self._print_summary()
+
+    def _print_summary(self):
+        """martini.py:367-406."""
+        dc = self._datacube
+        a = dc._array
+        if dc.padx > 0 and dc.pady > 0:
+            a = a[dc.padx:-dc.padx, dc.pady:-dc.pady, ...]
+        flux = np.sum(a) * dc.px_size**2
+        dv = np.abs(np.diff(dc.velocity_channel_edges))
+        mass = 2.36e5 * self.source.distance**2 * np.sum(
+            (a * dc.px_size**2).sum((0, 1)).squeeze() * dv)
+        nz = dc._array[dc._array > 0]
+        print("Source inserted.",
+              f"  Flux density in cube: {flux:.2e} Jy",
+              f"  Mass in cube (assuming distance {self.source.distance:.2f} Mpc and a spatially"
+              f" resolved source): {mass:.2e} Msun",
+              f"    [{mass / self.source.input_mass * 100:.0f}% of initial source mass]",
+              f"  Maximum pixel: {dc._array.max():.2e} Jy / arcsec2",
+              f"  Median non-zero pixel: {np.median(nz) if nz.size else 0.0:.2e} Jy / arcsec2",
+              sep="\n")
+
+    def reset(self):
+        """martini.py:409-425."""
+        dc = self._datacube
+        pad = (dc.padx, dc.pady)
+        new = DataCube(n_px_x=dc.n_px_x, n_px_y=dc.n_px_y, n_channels=dc.n_channels,
+                       px_size=dc.px_size, channel_width=dc.channel_width,
+                       spectral_centre=dc.spectral_centre, ra=dc.ra, dec=dc.dec,
+                       stokes_axis=dc.stokes_axis)
+        if self.beam is not None:
+            new.add_pad(pad)
+        self._datacube = new
+
+
+class Martini(_BaseMartini):
+    """martini.py:627-861."""
+
+    @property
+    def datacube(self):
+        return self._datacube
+
+    def insert_source_in_cube(self, skip_validation=False, progressbar=None, ncpu=1):
+        """Populate the DataCube with flux from the source particles (martini.py:827-861)."""
+        self._insert_source_in_cube(skip_validation=skip_validation, progressbar=progressbar, ncpu=ncpu)
+
+
+class GlobalProfile(_BaseMartini):
+    """Spatially integrated spectrum (martini.py:1369-1832): a 1 x 1 pixel cube, all particles
+    at pixel (0, 0), ``DiracDeltaKernel(size_in_fwhm=inf)``; pruning by velocity only."""
+
+    def __init__(self, *, source, spectral_model, n_channels=64, channel_width=4.0,
+                 spectral_centre=0.0, quiet=False, device="cuda:0", engine=None):
+        self._source_in = source
+        dc = DataCube(n_px_x=1, n_px_y=1, n_channels=n_channels, px_size=1.0,
+                      channel_width=channel_width, spectral_centre=spectral_centre,
+                      ra=source.ra if hasattr(source, "ra") else 0.0,
+                      dec=source.dec if hasattr(source, "dec") else 0.0)
+        self._inserted = False
+        super().__init__(source=_AtOrigin(source), datacube=dc, beam=None, noise=None,
+                         sph_kernel=DiracDeltaKernel(size_in_fwhm=np.inf), spectral_model=spectral_model,
+                         quiet=quiet, _prune_kwargs={"spatial": False, "obj_type_str": "spectrum"},
+                         device=device, engine=engine)
+
+    def insert_source_in_spectrum(self):
+        """martini.py:1551-1596."""
+        self._insert_source_in_cube(skip_validation=True, quiet=True)
+        self._inserted = True
+
+    @property
+    def spectrum(self):
+        """Jy per channel (martini.py:1598-1614)."""
+        if not self._inserted:
+            self.insert_source_in_spectrum()
+        dc = self._datacube
+        return dc._array.reshape(-1)[:dc.n_channels] * dc.px_size**2
+
+    @property
+    def channel_mids(self):
+        return self._datacube.velocity_channel_mids
+
+    @property
+    def channel_edges(self):
+        return self._datacube.velocity_channel_edges
+
+
+class _AtOrigin:
+    """Wrap a source so that every particle sits at pixel (0, 0) (martini.py:1541-1549)."""
+
+    def __init__(self, source):
+        self._s = source
+
+    def __getattr__(self, name):
+        return getattr(self._s, name)
+
+    def _init_skycoords(self):
+        self._s._init_skycoords()
+
+    def _init_pixcoords(self, datacube):
+        self._s._init_pixcoords(datacube)
+        self._s.pixcoords[:2] = 0.0
+
+    def sm_lengths_px(self, datacube):
+        # any positive length: sm_range = ceil(length * inf) = inf reaches the single pixel
+        # (martini.py:1537); the Dirac-delta weight itself ignores the smoothing length
+        return np.ones(self._s.npart)
+
+    def apply_mask(self, mask):
+        self._s.apply_mask(mask)
+
+
+class _PadOnlyBeam:
+    """Stand-in for the (out of scope) beam classes: only the pad size matters to the hot path
+    (beams.py:88-101, 277-295)."""
+
+    def __init__(self, pad):
+        self._pad = int(pad)
+
+    def init_kernel(self, datacube):
+        pass
+
+    def needs_pad(self):
+        return (self._pad, self._pad)
+
+
+def demo(quiet=False, device="cuda:0"):
+    """The hot-path slice of the reference's ``demo()`` (martini/_demo.py:95-161): the demo
+    source into the demo cube with CubicSplineKernel + GaussianSpectrum(7 km/s).  The 30 arcsec
+    Gaussian beam truncated at 4 sigma pads the cube by ceil(30*4/10 + 1) = 13 pixels; noise,
+    beam convolution and FITS output are outside this package's scope."""
+    from .sources import demo_source
+    from .spectral_models import GaussianSpectrum
+    from .sph_kernels import CubicSplineKernel
+
+    source = demo_source()
+    datacube = DataCube(n_px_x=128, n_px_y=128, n_channels=32, px_size=10.0, channel_width=10.0,
+                        spectral_centre=source.vsys)
+    m = Martini(source=source, datacube=datacube, beam=_PadOnlyBeam(13), noise=None,
+                spectral_model=GaussianSpectrum(sigma=7.0), sph_kernel=CubicSplineKernel(),
+                quiet=quiet, device=device)
+    m.insert_source_in_cube()
+    return m

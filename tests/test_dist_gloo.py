@@ -1,0 +1,92 @@
+"""CPU tests of the multi-GPU host logic: slab partition and the slab gather over a
+world-size-2 ``gloo`` process group (the GPU run uses the same code over NCCL)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from martini_b200 import dist as mdist
+
+
+def test_slab_bounds_even_and_aligned():
+    assert mdist.slab_bounds(256, 1) == [0, 256]
+    assert mdist.slab_bounds(256, 4) == [0, 64, 128, 192, 256]
+    b = mdist.slab_bounds(250, 3)
+    assert b[0] == 0 and b[-1] == 250 and all(x % 8 == 0 for x in b[1:-1]) and b == sorted(b)
+    b = mdist.slab_bounds(5, 8)  # more ranks than tiles: some slabs are empty, none negative
+    assert b[0] == 0 and b[-1] == 5 and b == sorted(b) and len(b) == 9
+
+
+def test_slab_bounds_balance_work_not_area():
+    rng = np.random.Generator(np.random.PCG64(3))
+    nx = 512
+    px = np.r_[rng.normal(120.0, 40.0, 90000), rng.uniform(0, nx, 10000)]  # mass piled up near row 120
+    r = np.full(px.size, 4.0)
+    work = mdist.row_work(px, r, nx)
+    assert work.shape == (nx,) and np.isclose(work.sum(), np.sum(np.clip(np.floor(px + r) + 1, 0, nx)
+                                                             - np.clip(np.ceil(px - r), 0, nx)))
+    b = mdist.slab_bounds(nx, 4, work)
+    per = [work[b[i]:b[i + 1]].sum() for i in range(4)]
+    assert max(per) / (sum(per) / 4) < 1.35          # work-balanced ...
+    assert (b[1] - b[0]) < nx // 4 and (b[4] - b[3]) > nx // 4  # ... by unequal areas
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, bounds, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ny, nc = 3, 4
+        rows = bounds[rank + 1] - bounds[rank]
+        # each rank's slab holds its global row index, so the assembled cube is checkable
+        slab = (torch.arange(bounds[rank], bounds[rank + 1], dtype=torch.float64)[:, None, None]
+                .expand(rows, ny, nc).contiguous())
+        full = torch.full((bounds[-1], ny, nc), -1.0, dtype=torch.float64) if rank == 0 else None
+        res = mdist.gather_slabs(slab, bounds, full, dst=0)
+        everyone = torch.full((bounds[-1], ny, nc), -1.0, dtype=torch.float64)
+        mdist.allgather_slabs(slab, bounds, everyone)
+        expect = torch.arange(bounds[-1], dtype=torch.float64)[:, None, None].expand(bounds[-1], ny, nc)
+        ok = bool(torch.equal(everyone, expect))
+        if rank == 0:
+            ok = ok and bool(torch.equal(res, expect))
+        else:
+            ok = ok and res is None
+        # max-over-ranks timing reduction used by bench.py
+        t = torch.tensor([float(rank + 1)])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok = ok and float(t) == world
+        out_q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bounds", ([0, 16, 40], [0, 40, 40], [0, 8, 24]))
+def test_gather_slabs_world2_gloo(bounds):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, bounds, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results == {0: True, 1: True}
+
+
+def test_single_process_gather_is_identity():
+    slab = torch.ones(4, 2, 2, dtype=torch.float64)
+    full = torch.zeros(4, 2, 2, dtype=torch.float64)
+    assert torch.equal(mdist.gather_slabs(slab, [0, 4], full), slab)

@@ -1,0 +1,175 @@
+"""GPU tests of the drop-in ``Martini`` class: the reference's own behavioural tests for the
+hot path (tests/test_martini.py of the reference), replayed against martini_b200."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from martini_b200 import DataCube, GlobalProfile, Martini, PixelSource, SPHSource, demo, demo_source  # noqa: E402
+from martini_b200 import synthetic  # noqa: E402
+from martini_b200.martini import _BaseMartini, _PadOnlyBeam  # noqa: E402
+from martini_b200.spectral_models import DiracDeltaSpectrum, GaussianSpectrum  # noqa: E402
+from martini_b200.sph_kernels import (CubicSplineKernel, DiracDeltaKernel, GaussianKernel,  # noqa: E402
+                                      WendlandC2Kernel, _CubicSplineKernel, _GaussianKernel,
+                                      _QuarticSplineKernel, _WendlandC2Kernel, _WendlandC6Kernel)
+from tests.parity import check_cube, oracle_hot_path  # noqa: E402
+
+KPC_PER_ARCSEC_DISTANCE = 1.0e-3 / np.deg2rad(1.0 / 3600.0)  # Mpc: 1 kpc subtends 1 arcsec
+
+
+def single_particle_source(ra_off=0.0, dec_off=0.0, v_off=0.0, mHI=1.0e4, hsm=1.0, distance=None):
+    """One particle offset by arcsec on the sky (1 kpc = 1 arcsec) and km/s in velocity."""
+    d = KPC_PER_ARCSEC_DISTANCE if distance is None else distance
+    return SPHSource(distance=d, h=0.7, T_g=np.ones(1) * 1e4, mHI_g=np.ones(1) * mHI,
+                     xyz_g=np.array([[0.0, ra_off, dec_off]]), vxyz_g=np.array([[v_off, 0.0, 0.0]]),
+                     hsm_g=np.ones(1) * hsm)
+
+
+def mass_in_cube(m):
+    dc = m.datacube
+    a = dc._array
+    if dc.padx:
+        a = a[dc.padx:-dc.padx, dc.pady:-dc.pady]
+    dv = np.abs(np.diff(dc.velocity_channel_edges))
+    return 2.36e5 * m.source.distance**2 * np.sum((a * dc.px_size**2).sum((0, 1)).squeeze() * dv)
+
+
+@pytest.mark.parametrize("ra_off,ra_in", ((0, True), (3, True), (9, False), (-3, True), (-9, False)))
+@pytest.mark.parametrize("dec_off,dec_in", ((0, True), (9, False), (-3, True)))
+@pytest.mark.parametrize("v_off,v_in", ((0, True), (3, True), (7, False), (-7, False)))
+@pytest.mark.parametrize("mass_off,mass_in", ((0, False), (1, True)))
+@pytest.mark.parametrize("flags", ((1, 1, 1), (1, 0, 1), (0, 1, 0), (0, 0, 0)))
+def test_prune_particles(ra_off, ra_in, dec_off, dec_in, v_off, v_in, mass_off, mass_in, flags):
+    """reference test_martini.py:330-443: 2x2x2 cube, pad 5, _CubicSplineKernel, sigma 1 km/s."""
+    spatial, spectral, mass = (bool(f) for f in flags)
+    expect = all(([ra_in, dec_in] if spatial else []) + ([v_in] if spectral else [])
+                 + ([mass_in] if mass else []))
+    source = single_particle_source(ra_off, dec_off, v_off, mHI=mass_off * 1.0e4)
+    datacube = DataCube(n_px_x=2, n_px_y=2, n_channels=2, spectral_centre=source.vsys, px_size=1.0,
+                        channel_width=1.0)
+    kwargs = dict(source=source, datacube=datacube, beam=_PadOnlyBeam(5), noise=None,
+                  sph_kernel=_CubicSplineKernel(), spectral_model=GaussianSpectrum(sigma=1.0),
+                  quiet=True, _prune_kwargs={"spatial": spatial, "spectral": spectral, "mass": mass})
+    if not expect:
+        with pytest.raises(RuntimeError, match="No non-zero mHI source particles in target region."):
+            _BaseMartini(**kwargs)
+    else:
+        assert _BaseMartini(**kwargs).source.npart == 1
+
+
+@pytest.mark.parametrize("kernel,hsm", ((_WendlandC2Kernel, 2.0), (_WendlandC6Kernel, 2.0),
+                                        (_CubicSplineKernel, 2.0), (_GaussianKernel, 2.5),
+                                        (_QuarticSplineKernel, 2.0), (DiracDeltaKernel, 0.3),
+                                        (WendlandC2Kernel, 1.0), (GaussianKernel, 0.7)))
+@pytest.mark.parametrize("spectrum", (GaussianSpectrum, DiracDeltaSpectrum))
+def test_mass_accuracy(kernel, hsm, spectrum):
+    """reference test_martini.py:205-241: mass recovered from the cube within 1 %."""
+    # 1 kpc pixels at 3 Mpc; positions kept off the pixel corners (the Dirac-delta kernel is
+    # strict: a particle exactly on a pixel edge lands nowhere, sph_kernels.py:1165)
+    source = SPHSource(distance=3.0, mHI_g=np.ones(4) * 1e6, T_g=np.ones(4) * 1e4,
+                       xyz_g=np.array([[0, 0.3, 0.2], [0, 1.3, 0.1], [0, 0.2, 1.4], [0, -1.3, -1.1]]),
+                       vxyz_g=np.array([[0, 0, 0], [5, 0, 0], [-5, 0, 0], [10.0, 0, 0]]),
+                       hsm_g=np.ones(4) * hsm)
+    datacube = DataCube(n_px_x=32, n_px_y=32, n_channels=32, px_size=68.75493542 / 1.0,
+                        channel_width=4.0, spectral_centre=source.vsys)  # 1 kpc pixels at 3 Mpc
+    m = Martini(source=source, datacube=datacube, sph_kernel=kernel(), spectral_model=spectrum(),
+                quiet=True)
+    m.insert_source_in_cube()
+    assert datacube.array_unit == "Jy/arcsec2"
+    assert np.isclose(mass_in_cube(m), 4e6, rtol=1e-2)
+
+
+def test_kernel_validation_raises_unless_skipped():
+    """reference test_sph_kernels.py:209-278: 'use this with care'."""
+    def build():
+        source = SPHSource(distance=3.0, mHI_g=np.ones(2) * 1e6, xyz_g=np.zeros((2, 3)),
+                           vxyz_g=np.zeros((2, 3)), hsm_g=np.array([0.5, 3.0]))  # 0.5 px < 1.51
+        dc = DataCube(n_px_x=16, n_px_y=16, n_channels=16, px_size=68.75493542, channel_width=4.0,
+                      spectral_centre=source.vsys)
+        return Martini(source=source, datacube=dc, sph_kernel=_WendlandC2Kernel(),
+                       spectral_model=GaussianSpectrum(), quiet=True)
+    with pytest.raises(RuntimeError, match="use this with care"):
+        build().insert_source_in_cube()
+    m = build()
+    m.insert_source_in_cube(skip_validation=True)
+    assert m.datacube._array.max() > 0
+
+
+def test_reset_and_reinsert():
+    """reference test_martini.py:495-507."""
+    m = demo(quiet=True)
+    first = m.datacube._array.copy()
+    assert first.shape == (154, 154, 32) and first.sum() > 0
+    with pytest.raises(RuntimeError, match="reset"):
+        m.insert_source_in_cube()
+    m.reset()
+    assert m.datacube._array.sum() == 0 and m.datacube._array.shape == (154, 154, 32)
+    m.insert_source_in_cube()
+    assert np.array_equal(m.datacube._array, first)
+
+
+def test_demo_mass_and_spectra_attribute():
+    """BASELINE config 1: demo source into the demo cube; reference test_martini.py:523-531."""
+    m = demo(quiet=True)
+    assert m.spectral_model.spectra is None  # never materialised by insertion
+    assert np.isclose(mass_in_cube(m), m.source.input_mass, rtol=2e-2)
+    m.init_spectra()
+    sp = m.spectral_model.spectra
+    assert sp.shape == (m.source.npart, 32) and sp.sum() > 0
+
+
+def test_noise_before_insertion_is_kept():
+    """martini.py:916-927: out = (in + inserted) / px^2."""
+    src = single_particle_source(hsm=3.0, mHI=1e6)
+    dc = DataCube(n_px_x=16, n_px_y=16, n_channels=8, px_size=1.0, channel_width=4.0, spectral_centre=src.vsys)
+    rng = np.random.Generator(np.random.PCG64(5))
+    noise = rng.normal(0, 1e-9, dc._array.shape)
+    dc._array += noise
+    m = Martini(source=src, datacube=dc, sph_kernel=_CubicSplineKernel(), spectral_model=GaussianSpectrum(), quiet=True)
+    m.insert_source_in_cube()
+    src2 = single_particle_source(hsm=3.0, mHI=1e6)
+    dc2 = DataCube(n_px_x=16, n_px_y=16, n_channels=8, px_size=1.0, channel_width=4.0, spectral_centre=src2.vsys)
+    m2 = Martini(source=src2, datacube=dc2, sph_kernel=_CubicSplineKernel(), spectral_model=GaussianSpectrum(), quiet=True)
+    m2.insert_source_in_cube()
+    assert np.allclose(m.datacube._array, m2.datacube._array + noise, rtol=1e-12, atol=1e-25)
+
+
+def test_martini_class_vs_oracle():
+    """The Martini class on a synthetic pixel-space source equals the oracle's cube."""
+    case = synthetic.make_case("cfg2", n=20000, nx=48, ny=40, nc=64, seed=21)
+    nx, ny, nc = case["shape"]
+    dc = DataCube(n_px_x=nx, n_px_y=ny, n_channels=nc, px_size=case["px_size"], channel_width=4.0)
+    assert np.allclose(dc.velocity_channel_edges, case["edges"])
+    m = Martini(source=PixelSource.from_case(case), datacube=dc, sph_kernel=WendlandC2Kernel(),
+                spectral_model=GaussianSpectrum(sigma=7.0), quiet=True)
+    ref = oracle_hot_path(case)
+    assert m.source.npart == int(ref["accept"].sum())
+    assert np.array_equal(m.sph_kernel.kernel_indices, ref["kernel"].kernel_indices)
+    assert np.array_equal(m.sph_kernel.sm_ranges, ref["kernel"].sm_ranges)
+    m.insert_source_in_cube()
+    check_cube(m.datacube._array, ref["cube"])
+
+
+def test_global_profile():
+    """reference test_martini.py:862-912: spectrum integrates to the source mass within 1 %,
+    sky position is ignored by the pruning."""
+    s = demo_source(N=400)
+    gp = GlobalProfile(source=s, spectral_model=GaussianSpectrum(sigma=7.0), n_channels=64,
+                       channel_width=10.0, spectral_centre=s.vsys, quiet=True)
+    spec = gp.spectrum
+    assert spec.shape == (64,)
+    mass = 2.36e5 * 3.0**2 * np.sum(spec * 10.0)
+    assert np.isclose(mass, 5.0e9, rtol=1e-2)
+
+
+def test_unsupported_plugins_raise_before_any_work():
+    class MyKernel(_CubicSplineKernel):
+        pass
+
+    src = single_particle_source()
+    dc = DataCube(n_px_x=4, n_px_y=4, n_channels=4, px_size=1.0, channel_width=1.0)
+    with pytest.raises(NotImplementedError, match="MyKernel"):
+        Martini(source=src, datacube=dc, sph_kernel=MyKernel(), spectral_model=GaussianSpectrum())
