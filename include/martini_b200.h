@@ -164,8 +164,9 @@ int mtn_prune(int64_t n0, const double* px, const double* py, const double* pz,
               int32_t nx_tot, int32_t ny_tot, int32_t n_channels, int32_t flags,
               uint8_t* accept_out, int64_t* n_accept_out, void* stream);
 
-/* Bytes of device scratch mtn_plan needs for n particles. */
-size_t mtn_plan_scratch_bytes(int64_t n);
+/* Bytes of device scratch mtn_plan needs for n particles and this cube slab.  The same
+ * scratch buffer must be handed, untouched, to the mtn_project call that follows. */
+size_t mtn_plan_scratch_bytes(int64_t n, const MtnCube* cube);
 
 /*
  * Plan the projection of `p` into `cube`: footprints, live channel windows, brick

@@ -116,7 +116,7 @@ SYMBOLS = {
          C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
          C.c_void_p, C.c_void_p, C.c_void_p],
     ),
-    "mtn_plan_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "mtn_plan_scratch_bytes": (C.c_size_t, [C.c_int64, C.POINTER(MtnCube)]),
     "mtn_plan": (
         C.c_int,
         [C.POINTER(MtnParticles), C.POINTER(MtnCube), C.c_void_p, C.c_size_t, C.POINTER(MtnPlan),

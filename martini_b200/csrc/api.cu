@@ -103,7 +103,8 @@ static int make_geo(const MtnCube* c, Geo* g, int edges_increasing) {
   g->x_hi = c->x_hi;
   g->ntx = (c->x_hi - c->x_lo + TILE_X - 1) / TILE_X;
   g->nty = (c->ny + TILE_Y - 1) / TILE_Y;
-  g->ncb = (c->n_channels + CB - 1) / CB;
+  g->ncb = (c->n_channels + CB - 1) / CB + 1;  // + the partial block below the tile's phase
+  g->phase = nullptr;
   const int64_t nb = (int64_t)g->ntx * g->nty * g->ncb;
   if (nb >= (1ll << 31)) return fail(MTN_ERR_LIMIT, "cube: too many bricks%s", "");
   g->n_bricks = (int)nb;
@@ -132,14 +133,21 @@ static PlanIn make_plan_in(const MtnParticles* p, const MtnCube* c) {
   return in;
 }
 
-// plan scratch: [blk_kept | blk_pairs | totals(4 x u64) | edge probe (2 doubles)]
+// plan scratch: [blk_kept | blk_pairs | totals(8 x u64) | tile_sum | tile_cnt | tile_phase]
 struct PlanScratch {
   int64_t nblk;
   int64_t* blk_kept;
   int64_t* blk_pairs;
   unsigned long long* totals;
+  unsigned long long* tile_sum;
+  unsigned int* tile_cnt;
+  int* tile_phase;
 };
-static size_t plan_scratch_layout(int64_t n, void* base, PlanScratch* s) {
+static int64_t num_tiles(const MtnCube* c) {
+  if (!c || c->x_hi <= c->x_lo || c->ny <= 0) return 1;
+  return (int64_t)((c->x_hi - c->x_lo + TILE_X - 1) / TILE_X) * ((c->ny + TILE_Y - 1) / TILE_Y);
+}
+static size_t plan_scratch_layout(int64_t n, int64_t n_tiles, void* base, PlanScratch* s) {
   const int64_t nblk = std::max<int64_t>(1, (n + PLAN_THREADS - 1) / PLAN_THREADS);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -150,11 +158,17 @@ static size_t plan_scratch_layout(int64_t n, void* base, PlanScratch* s) {
   char* a = take(nblk * sizeof(int64_t));
   char* b = take(nblk * sizeof(int64_t));
   char* t = take(8 * sizeof(unsigned long long));
+  char* ts = take((size_t)n_tiles * sizeof(unsigned long long));
+  char* tc = take((size_t)n_tiles * sizeof(unsigned int));
+  char* tp = take((size_t)n_tiles * sizeof(int));
   if (s) {
     s->nblk = nblk;
     s->blk_kept = (int64_t*)a;
     s->blk_pairs = (int64_t*)b;
     s->totals = (unsigned long long*)t;
+    s->tile_sum = (unsigned long long*)ts;
+    s->tile_cnt = (unsigned int*)tc;
+    s->tile_phase = (int*)tp;
   }
   return off;
 }
@@ -317,7 +331,9 @@ int mtn_prune(int64_t n0, const double* px, const double* py, const double* pz,
   return MTN_OK;
 }
 
-size_t mtn_plan_scratch_bytes(int64_t n) { return plan_scratch_layout(n, nullptr, nullptr); }
+size_t mtn_plan_scratch_bytes(int64_t n, const MtnCube* cube) {
+  return plan_scratch_layout(n, num_tiles(cube), nullptr, nullptr);
+}
 
 static int check_particles(const MtnParticles* p) {
   if (!p || p->n < 0) return fail(MTN_ERR_INVALID, "particles: bad n%s", "");
@@ -342,13 +358,25 @@ int mtn_plan(const MtnParticles* p, const MtnCube* cube, void* scratch, size_t s
   if (!cube || !cube->edges || !plan) return fail(MTN_ERR_INVALID, "plan: bad arguments%s", "");
   cudaStream_t st = (cudaStream_t)stream;
   PlanScratch ps;
-  if (plan_scratch_layout(p->n, scratch, &ps) > scratch_bytes || !scratch)
+  if (plan_scratch_layout(p->n, num_tiles(cube), scratch, &ps) > scratch_bytes || !scratch)
     return fail(MTN_ERR_WORKSPACE, "plan: scratch too small%s", "");
   int inc = 0;
   if (int rc = edges_direction(cube, st, &inc)) return rc;
   Geo g;
   if (int rc = make_geo(cube, &g, inc)) return rc;
+  g.phase = ps.tile_phase;
+  const int n_tiles = g.ntx * g.nty;
   MTN_CUDA(cudaMemsetAsync(ps.totals, 0, 8 * sizeof(unsigned long long), st));
+  MTN_CUDA(cudaMemsetAsync(ps.tile_sum, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
+  MTN_CUDA(cudaMemsetAsync(ps.tile_cnt, 0, (size_t)n_tiles * sizeof(unsigned int), st));
+  if (p->n > 0) {
+    tile_stats_kernel<<<(unsigned)((ps.nblk + TILE_STAT_STRIDE - 1) / TILE_STAT_STRIDE), PLAN_THREADS, 0,
+                        st>>>(make_plan_in(p, cube), g, ps.tile_sum, ps.tile_cnt);
+    MTN_LAUNCH_CHECK();
+  }
+  tile_phase_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>(n_tiles, ps.tile_sum, ps.tile_cnt,
+                                                                      ps.tile_phase);
+  MTN_LAUNCH_CHECK();
   if (p->n > 0) {
     plan_count_kernel<<<(unsigned)ps.nblk, PLAN_THREADS, 0, st>>>(make_plan_in(p, cube), g, ps.blk_kept,
                                                                  ps.blk_pairs, ps.totals + 2);
@@ -389,7 +417,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
   if (int rc = to_dev_table(table, &t)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   PlanScratch ps;
-  if (plan_scratch_layout(p->n, scratch, &ps) > scratch_bytes || !scratch)
+  if (plan_scratch_layout(p->n, num_tiles(cube), scratch, &ps) > scratch_bytes || !scratch)
     return fail(MTN_ERR_WORKSPACE, "project: scratch too small%s", "");
   Workspace ws;
   if (workspace_layout(plan->n_kept, plan->n_pairs, plan->n_bricks, plan->chunk, workspace, &ws) >
@@ -399,6 +427,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
   Geo g;
   if (int rc = make_geo(cube, &g, plan->edges_increasing)) return rc;
   if (g.n_bricks != plan->n_bricks) return fail(MTN_ERR_INVALID, "project: plan/cube mismatch%s", "");
+  g.phase = ps.tile_phase;  // written by mtn_plan into the caller's scratch
   const double px_area = cube->px_size_arcsec * cube->px_size_arcsec;
   const int zeroed = (cube->flags & MTN_CUBE_ZEROED) ? 1 : 0;
 
@@ -476,7 +505,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
       project_kernel<false><<<pgrid, PROJ_THREADS, sizeof(ProjSmem), st>>>(a);
     MTN_LAUNCH_CHECK();
     mark(4, st);
-    reduce_partials_kernel<<<(unsigned)ws.max_multi, PROJ_THREADS, 0, st>>>(
+    reduce_partials_kernel<<<dim3((unsigned)ws.max_multi, SUB_PIX), PROJ_THREADS, 0, st>>>(
         g, ws.multis, ws.scalars + 2, ws.partials, cube->slab, px_area, zeroed);
     MTN_LAUNCH_CHECK();
     if (g_count_exec) {

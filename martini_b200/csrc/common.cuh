@@ -52,8 +52,9 @@ constexpr double ERF_SAT = 6.0;
 struct Geo {
   int nx, ny, C;        // full cube
   int x_lo, x_hi;       // slab rows
-  int ntx, nty, ncb;    // bricks along x (slab), y, channel
+  int ntx, nty, ncb;    // bricks along x (slab), y, channel (ncb = ceil(C/CB) + 1, see phase)
   int n_bricks;
+  const int* phase;     // per-tile channel phase in [0, CB): block k = [ph + (k-1) CB, ph + k CB)
   int spectrum;         // MTN_SPECTRUM_*
   int edges_increasing; // 1 if edges[c+1] > edges[c]
 };

@@ -7,6 +7,7 @@
 namespace mtn {
 
 constexpr int PLAN_THREADS = 1024;
+constexpr int TILE_STAT_STRIDE = 16;
 
 // ---------------------------------------------------------------------------------------
 // K0: per-particle kernel choice, sm_range, h_eff.
@@ -189,14 +190,68 @@ __device__ __forceinline__ Foot footprint(const PlanIn& in, const Geo& g, int64_
   return f;
 }
 
-__device__ __forceinline__ void brick_range(const Foot& f, const Geo& g, int& tx0, int& tx1,
-                                            int& ty0, int& ty1, int& cb0, int& cb1) {
+// Tile range of a footprint, and the channel blocks it reaches in one tile.  Channel blocks
+// are CB wide with a per-tile phase ph in [0, CB): block k holds channels
+// [ph + (k-1) CB, ph + k CB), so block 0 is the (possibly empty) part below ph.  The phase is
+// chosen per tile (tile_phase_kernel) so that the tile's mean line centre sits mid-block:
+// most particles of a tile then need a single brick instead of straddling a fixed boundary.
+__device__ __forceinline__ void tile_range(const Foot& f, const Geo& g, int& tx0, int& tx1,
+                                           int& ty0, int& ty1) {
   tx0 = (f.i0 - g.x_lo) / TILE_X;
   tx1 = (f.i1 - g.x_lo) / TILE_X;
   ty0 = f.j0 / TILE_Y;
   ty1 = f.j1 / TILE_Y;
-  cb0 = f.c0 / CB;
-  cb1 = f.c1 / CB;
+}
+__device__ __forceinline__ void block_range(const Foot& f, int ph, int& k0, int& k1) {
+  k0 = (f.c0 - ph + CB) / CB;
+  k1 = (f.c1 - ph + CB) / CB;
+}
+
+// Pass 0a: per tile, sum and count of the line centres (in half channels) of the particles
+// that reach it.  Integer atomics: the result does not depend on the order of arrival.
+__global__ void __launch_bounds__(PLAN_THREADS) tile_stats_kernel(
+    PlanIn in, Geo g, unsigned long long* __restrict__ tile_sum, unsigned int* __restrict__ tile_cnt) {
+  // the phase is a heuristic: a 1-in-TILE_STAT_STRIDE sample of the particles decides it
+  const int64_t i = ((int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x) * TILE_STAT_STRIDE;
+  if (i >= in.n) return;
+  const Foot f = footprint(in, g, i);
+  if (!f.live) return;
+  int tx0, tx1, ty0, ty1;
+  tile_range(f, g, tx0, tx1, ty0, ty1);
+  const unsigned long long centre2 = (unsigned long long)(f.c0 + f.c1 + 1);
+  for (int tx = tx0; tx <= tx1; ++tx)
+    for (int ty = ty0; ty <= ty1; ++ty) {
+      atomicAdd(tile_sum + tx * g.nty + ty, centre2);
+      atomicAdd(tile_cnt + tx * g.nty + ty, 1u);
+    }
+}
+
+// Pass 0b: phase = (mean centre - CB/2) mod CB, even (keeps 16-byte store alignment).
+__global__ void __launch_bounds__(256) tile_phase_kernel(int n_tiles,
+                                                         const unsigned long long* __restrict__ tile_sum,
+                                                         const unsigned int* __restrict__ tile_cnt,
+                                                         int* __restrict__ phase) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  int ph = 0;
+  if (tile_cnt[t]) {
+    const long long mean = (long long)(tile_sum[t] / (2ull * tile_cnt[t]));
+    ph = (int)(((mean - CB / 2) % CB + CB) % CB) & ~1;
+  }
+  phase[t] = ph;
+}
+
+__device__ __forceinline__ int64_t count_pairs(const Foot& f, const Geo& g) {
+  int tx0, tx1, ty0, ty1;
+  tile_range(f, g, tx0, tx1, ty0, ty1);
+  int64_t n = 0;
+  for (int tx = tx0; tx <= tx1; ++tx)
+    for (int ty = ty0; ty <= ty1; ++ty) {
+      int k0, k1;
+      block_range(f, g.phase[tx * g.nty + ty], k0, k1);
+      n += k1 - k0 + 1;
+    }
+  return n;
 }
 
 // Pass 1: per-block totals of (kept particles, bricks overlapped) and the slab's U_dense.
@@ -210,10 +265,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(
     const Foot f = footprint(in, g, i);
     if (f.box) upd = (int64_t)(f.i1 - f.i0 + 1) * (f.j1 - f.j0 + 1) * g.C;
     if (f.live) {
-      int tx0, tx1, ty0, ty1, cb0, cb1;
-      brick_range(f, g, tx0, tx1, ty0, ty1, cb0, cb1);
       kept = 1;
-      pairs = (int64_t)(tx1 - tx0 + 1) * (ty1 - ty0 + 1) * (cb1 - cb0 + 1);
+      pairs = count_pairs(f, g);
     }
   }
   int64_t tk, tp, tu;
@@ -237,13 +290,11 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
   int64_t kept = 0, npair = 0;
   Foot f;
   f.live = false;
-  int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1, cb0 = 0, cb1 = -1;
   if (i < in.n) {
     f = footprint(in, g, i);
     if (f.live) {
-      brick_range(f, g, tx0, tx1, ty0, ty1, cb0, cb1);
       kept = 1;
-      npair = (int64_t)(tx1 - tx0 + 1) * (ty1 - ty0 + 1) * (cb1 - cb0 + 1);
+      npair = count_pairs(f, g);
     }
   }
   int64_t tk, tp;
@@ -271,12 +322,18 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
   rec.r = (float)in.sm_range[i];
   rec.kid = in.kernel_id ? (int32_t)in.kernel_id[i] : 0;
   records[ridx] = rec;
+  int tx0, tx1, ty0, ty1;
+  tile_range(f, g, tx0, tx1, ty0, ty1);
   for (int tx = tx0; tx <= tx1; ++tx)
-    for (int ty = ty0; ty <= ty1; ++ty)
-      for (int cb = cb0; cb <= cb1; ++cb) {
-        const uint32_t key = (uint32_t)((tx * g.nty + ty) * g.ncb + cb);
+    for (int ty = ty0; ty <= ty1; ++ty) {
+      const int tile = tx * g.nty + ty;
+      int k0, k1;
+      block_range(f, g.phase[tile], k0, k1);
+      for (int k = k0; k <= k1; ++k) {
+        const uint32_t key = (uint32_t)(tile * g.ncb + k);
         pairs_out[off++] = ((uint64_t)key << 32) | (uint64_t)(uint32_t)ridx;
       }
+    }
 }
 
 }  // namespace mtn

@@ -264,14 +264,15 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
     const int cb = it.brick % g.ncb;
     const int tile = it.brick / g.ncb;
     const int ty = tile % g.nty, tx = tile / g.nty;
-    const int x0 = g.x_lo + tx * TILE_X, y0 = ty * TILE_Y, c0 = cb * CB;
-    const int nch = min(CB, g.C - c0);
+    // channels [c0, c0 + CB) of the cube; c0 may be negative (block 0 of a phased tile)
+    const int x0 = g.x_lo + tx * TILE_X, y0 = ty * TILE_Y, c0 = g.phase[tile] + (cb - 1) * CB;
+    const int clo = max(0, -c0), nch = min(CB, g.C - c0);  // valid brick channels: [clo, nch)
     // pixels of the tile that exist in the slab / cube
     const int x_last = min(x0 + TILE_X, g.x_hi) - 1, y_last = min(y0 + TILE_Y, g.ny) - 1;
 
-    for (int e = tid; e <= CB; e += PROJ_THREADS) sm.edge[e] = a.edges[min(c0 + e, g.C)];
+    for (int e = tid; e <= CB; e += PROJ_THREADS) sm.edge[e] = a.edges[min(max(c0 + e, 0), g.C)];
     for (int c = tid; c < CB; c += PROJ_THREADS)
-      sm.inv_dv[c] = c < nch ? 1.0 / fabs(a.edges[c0 + c + 1] - a.edges[c0 + c]) : 0.0;
+      sm.inv_dv[c] = (c >= clo && c < nch) ? 1.0 / fabs(a.edges[c0 + c + 1] - a.edges[c0 + c]) : 0.0;
 
     double acc[SUB_PIX][2];
 #pragma unroll
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
           // channel c can be non-zero only if edge c+1 >= e0 and edge c < e1:
           //   Gaussian: some edge of the channel is unsaturated, or the saturation flips in it
           //   Dirac   : lo <= v <= hi, both closed (spectral_models.py:564-569)
-          cs = max(e0 - 1, 0);
+          cs = max(e0 - 1, clo);
           ce = min(e1, nch);
           if (cs >= ce) cs = ce = 0;
           if (ce > cs) {
@@ -491,7 +492,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
 
     // ---- one store per voxel -------------------------------------------------------------
     const int cl = half * CH_HALF + 2 * lane;  // this lane's first channel within the brick
-    const int nvalid = max(0, min(2, nch - cl));
+    const int nvalid = cl < clo ? 0 : max(0, min(2, nch - cl));
     if (it.slot >= 0) {
       double* dst = a.partials + (size_t)it.slot * TILE_PIX * CB + cl;
 #pragma unroll
@@ -524,15 +525,19 @@ __global__ void __launch_bounds__(PROJ_THREADS) reduce_partials_kernel(
   const MultiBrick m = multis[blockIdx.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cb = m.brick % g.ncb, tile = m.brick / g.ncb;
-  const int x0 = g.x_lo + (tile / g.nty) * TILE_X, y0 = (tile % g.nty) * TILE_Y, c0 = cb * CB;
+  const int x0 = g.x_lo + (tile / g.nty) * TILE_X, y0 = (tile % g.nty) * TILE_Y;
+  const int c0 = g.phase[tile] + (cb - 1) * CB;
   const int half = warp / N_SUB, sub = warp % N_SUB, cl = half * CH_HALF + 2 * lane;
-  const int nvalid = max(0, min(2, min(CB, g.C - c0) - cl));
-  for (int j = 0; j < SUB_PIX; ++j) {
+  const int nvalid = c0 + cl < 0 ? 0 : max(0, min(2, min(CB, g.C - c0) - cl));
+  {
+    const int j = blockIdx.y;  // one pixel of every sub-block per grid row: the hottest brick
+                               // (most partials) is spread over SUB_PIX blocks
     const int tpx = sub_x(sub, j), tpy = sub_y(sub, j);
+    const double* src = partials + ((size_t)m.slot0 * TILE_PIX + tpx * TILE_Y + tpy) * CB + cl;
     double a0 = 0.0, a1 = 0.0;
-    for (uint32_t k = 0; k < m.n; ++k) {
-      const double2 v = *reinterpret_cast<const double2*>(
-          partials + ((size_t)(m.slot0 + k) * TILE_PIX + tpx * TILE_Y + tpy) * CB + cl);
+#pragma unroll 8
+    for (uint32_t k = 0; k < m.n; ++k) {  // chunk order: deterministic
+      const double2 v = *reinterpret_cast<const double2*>(src + (size_t)k * TILE_PIX * CB);
       a0 += v.x;
       a1 += v.y;
     }
@@ -551,9 +556,10 @@ __global__ void __launch_bounds__(PROJ_THREADS) empty_brick_kernel(
   if (brick_count[brick] != 0) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cb = brick % g.ncb, tile = brick / g.ncb;
-  const int x0 = g.x_lo + (tile / g.nty) * TILE_X, y0 = (tile % g.nty) * TILE_Y, c0 = cb * CB;
+  const int x0 = g.x_lo + (tile / g.nty) * TILE_X, y0 = (tile % g.nty) * TILE_Y;
+  const int c0 = g.phase[tile] + (cb - 1) * CB;
   const int half = warp / N_SUB, sub = warp % N_SUB, cl = half * CH_HALF + 2 * lane;
-  const int nvalid = max(0, min(2, min(CB, g.C - c0) - cl));
+  const int nvalid = c0 + cl < 0 ? 0 : max(0, min(2, min(CB, g.C - c0) - cl));
   if (nvalid == 0) return;
   for (int j = 0; j < SUB_PIX; ++j) {
     const int gx = x0 + sub_x(sub, j), gy = y0 + sub_y(sub, j);

@@ -173,7 +173,7 @@ class Engine:
         tc = table.to_c()
         stream = self._stream()
 
-        sbytes = self.lib.mtn_plan_scratch_bytes(n)
+        sbytes = self.lib.mtn_plan_scratch_bytes(n, C.byref(c))
         scratch = self._grow("_scratch", sbytes)
         plan = L.MtnPlan()
         L.check(self.lib.mtn_plan(C.byref(p), C.byref(c), _ptr(scratch), scratch.numel(),
@@ -183,7 +183,7 @@ class Engine:
                                      _ptr(scratch), scratch.numel(), _ptr(ws), ws.numel(), stream),
                 "mtn_project")
         self.last_plan = plan
-        self.last_launches = self.lib.mtn_last_launch_count() + 3  # + mtn_plan's three kernels
+        self.last_launches = self.lib.mtn_last_launch_count() + 5  # + mtn_plan's five kernels
         del keep
         return plan
 
