@@ -216,10 +216,16 @@ int mtn_fp64_peak(double* tflops_out, double* ms_out, void* stream);
 /*
  * Device-function probes used by the parity tests: evaluate the kernel integral
  * (w_out[i] = W(dx[i], dy[i], h[i])) or the per-particle channel spectrum
- * (s_out[i*C + c]) exactly as the projection kernel does.
+ * (s_out[i*C + c]) exactly as the projection kernel does.  closed_form != 0 evaluates the
+ * reference's closed-form expression instead of the tabulated one (Wendland C2 and the cubic
+ * spline are tabulated, csrc/tables.cuh).  mtn_table_error returns the worst deviation of a
+ * kind's table from its closed form, relative to W(0), found when the table was built (host
+ * memory; 0 for kinds without a table).
  */
-int mtn_probe_kernel_integral(const MtnKernelEntry* entry, int64_t n, const double* dx,
-                              const double* dy, const double* h, double* w_out, void* stream);
+int mtn_table_error(int32_t kind, double* err_out);
+int mtn_probe_kernel_integral(const MtnKernelEntry* entry, int32_t closed_form, int64_t n,
+                              const double* dx, const double* dy, const double* h, double* w_out,
+                              void* stream);
 int mtn_probe_spectra(int32_t spectrum, int64_t n, const double* v, const double* sigma,
                       double sigma_scalar, const double* amp, int32_t n_channels,
                       const double* edges, double* s_out, void* stream);

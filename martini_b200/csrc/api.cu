@@ -7,6 +7,7 @@
 #include "project.cuh"
 #include "scan.cuh"
 #include "sort.cuh"
+#include "tables_host.hpp"
 
 namespace mtn {
 thread_local char g_err[512] = "";
@@ -61,30 +62,29 @@ static int sm_count() {
   return n;
 }
 
-// Taylor coefficients of erf about the interval centres, computed in x87 extended precision:
-// erf^(k)(x) = (2/sqrt(pi)) (-1)^(k-1) H_(k-1)(x) exp(-x^2), H = physicists' Hermite.
-static int ensure_erf_table() {
+// Fill the device tables (erf, kernel integrals) once per device; see tables_host.hpp.
+static double g_table_err[WT_KINDS] = {0};
+static int ensure_tables() {
   static bool done[64] = {false};
   int dev = 0;
   MTN_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && done[dev]) return MTN_OK;
-  static double tab[ERF_NINT * ERF_NCOEF];
-  const long double two_over_sqrt_pi = 1.1283791670955125738961589031215452L;
-  for (int i = 0; i < ERF_NINT; ++i) {
-    const long double c = ((long double)i + 0.5L) / ERF_INV_W;
-    const long double ex = expl(-c * c);
-    long double h_prev = 0.0L, h = 1.0L, fact = 1.0L;  // H_(-1) := 0, H_0 = 1
-    tab[i * ERF_NCOEF + 0] = (double)erfl(c);
-    for (int k = 1; k <= ERF_DEG; ++k) {
-      fact *= k;
-      const long double sign = ((k - 1) & 1) ? -1.0L : 1.0L;
-      tab[i * ERF_NCOEF + k] = (double)(two_over_sqrt_pi * sign * h * ex / fact);
-      const long double h_next = 2.0L * c * h - 2.0L * (k - 1) * h_prev;  // H_k from H_(k-1), H_(k-2)
-      h_prev = h;
-      h = h_next;
-    }
+  static double erf_tab_host[ERF_NINT * ERF_NCOEF];
+  static HostTables T;
+  static bool built = false;
+  if (!built) {
+    build_erf_table(erf_tab_host);
+    T = build_kernel_tables();
+    for (int k = 0; k < WT_KINDS; ++k) g_table_err[k] = T.max_err[k];
+    built = true;
   }
-  MTN_CUDA(cudaMemcpyToSymbol(g_erf_table, tab, sizeof(tab)));
+  if (T.rows.size() > (size_t)WT_MAX_ROWS * WT_ROW)
+    return fail(MTN_ERR_LIMIT, "kernel tables exceed WT_MAX_ROWS%s", "");
+  MTN_CUDA(cudaMemcpyToSymbol(g_erf_table, erf_tab_host, sizeof(erf_tab_host)));
+  MTN_CUDA(cudaMemcpyToSymbol(c_wreg, T.reg, sizeof(T.reg)));
+  MTN_CUDA(cudaMemcpyToSymbol(c_wnreg, T.nreg, sizeof(T.nreg)));
+  MTN_CUDA(cudaMemcpyToSymbol(c_wscale, T.scale, sizeof(T.scale)));
+  MTN_CUDA(cudaMemcpyToSymbol(g_wtab_rows, T.rows.data(), T.rows.size() * sizeof(double)));
   if (dev >= 0 && dev < 64) done[dev] = true;
   return MTN_OK;
 }
@@ -249,12 +249,13 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
 }
 
 __global__ void __launch_bounds__(256) probe_kernel_integral_kernel(
-    int kind, double truncate, double norm, int64_t n, const double* __restrict__ dx,
+    int kind, double truncate, double norm, int closed_form, int64_t n, const double* __restrict__ dx,
     const double* __restrict__ dy, const double* __restrict__ h, double* __restrict__ w) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double hh = h[i];
-  w[i] = kernel_weight(kind, dx[i], dy[i], hh, 1.0 / (hh * hh), truncate, norm);
+  w[i] = closed_form ? kernel_weight_closed(kind, dx[i], dy[i], hh, 1.0 / (hh * hh), truncate, norm)
+                     : kernel_weight(kind, dx[i], dy[i], hh, 1.0 / (hh * hh), truncate, norm);
 }
 
 __global__ void __launch_bounds__(256) probe_spectra_kernel(
@@ -408,7 +409,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
                 const MtnPlan* plan, void* scratch, size_t scratch_bytes, void* workspace,
                 size_t workspace_bytes, void* stream) {
   g_launches = 0;
-  if (int rc = ensure_erf_table()) return rc;
+  if (int rc = ensure_tables()) return rc;
   if (int rc = check_particles(p)) return rc;
   if (!cube || !cube->edges || !cube->slab || !plan)
     return fail(MTN_ERR_INVALID, "project: bad arguments%s", "");
@@ -577,12 +578,21 @@ int mtn_fp64_peak(double* tflops_out, double* ms_out, void* stream) {
   return MTN_OK;
 }
 
-int mtn_probe_kernel_integral(const MtnKernelEntry* entry, int64_t n, const double* dx,
-                              const double* dy, const double* h, double* w_out, void* stream) {
+int mtn_table_error(int32_t kind, double* err_out) {
+  if (kind < 0 || kind >= WT_KINDS || !err_out) return fail(MTN_ERR_INVALID, "table_error: bad kind%s", "");
+  if (int rc = ensure_tables()) return rc;
+  *err_out = g_table_err[kind];
+  return MTN_OK;
+}
+
+int mtn_probe_kernel_integral(const MtnKernelEntry* entry, int32_t closed_form, int64_t n,
+                              const double* dx, const double* dy, const double* h, double* w_out,
+                              void* stream) {
   if (!entry || n < 0) return fail(MTN_ERR_INVALID, "probe: bad arguments%s", "");
+  if (int rc = ensure_tables()) return rc;
   if (n == 0) return MTN_OK;
   probe_kernel_integral_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      entry->kind, entry->truncate, entry->norm, n, dx, dy, h, w_out);
+      entry->kind, entry->truncate, entry->norm, closed_form, n, dx, dy, h, w_out);
   MTN_LAUNCH_CHECK();
   return MTN_OK;
 }
@@ -592,7 +602,7 @@ int mtn_probe_spectra(int32_t spectrum, int64_t n, const double* v, const double
                       const double* edges, double* s_out, void* stream) {
   if (n < 0 || n_channels <= 0) return fail(MTN_ERR_INVALID, "probe: bad arguments%s", "");
   if (n == 0) return MTN_OK;
-  if (int rc = ensure_erf_table()) return rc;
+  if (int rc = ensure_tables()) return rc;
   const int64_t tot = n * n_channels;
   probe_spectra_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       spectrum, n, v, sigma, sigma_scalar, amp, n_channels, edges, s_out);

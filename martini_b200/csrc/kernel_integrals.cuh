@@ -9,6 +9,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "tables.cuh"
 
 namespace mtn {
 
@@ -122,11 +123,11 @@ __device__ __forceinline__ double w_gaussian(double dx, double dy, double h, dou
   double ez = 0.0;
   if (truncate > u) {
     const double zmax = sqrt(__dsub_rn(__dmul_rn(truncate, truncate), __dmul_rn(u, u)));
-    ez = erf(zmax / 1.4142135623730951);
+    ez = erf_tab(zmax / 1.4142135623730951);
   }
   const double c = 1.0 / (h * 1.4142135623730951 * sig);
-  const double ex = erf((dx + 0.5) * c) - erf((dx - 0.5) * c);
-  const double ey = erf((dy + 0.5) * c) - erf((dy - 0.5) * c);
+  const double ex = erf_tab((dx + 0.5) * c) - erf_tab((dx - 0.5) * c);
+  const double ey = erf_tab((dy + 0.5) * c) - erf_tab((dy - 0.5) * c);
   return 0.25 * ez * ex * ey / norm;
 }
 
@@ -165,11 +166,10 @@ __device__ __forceinline__ double w_quartic_spline(double dr2, double h, double 
   return val * (2.0 * 15625.0 / 512.0 / CUDART_PI) * inv_h2;
 }
 
-// Dispatch on the primitive kernel kind (warp-uniform in the projection kernel: a warp
-// works on one particle at a time).  dx, dy = particle - pixel centre, as in
-// martini.py:275-277.
-__device__ __forceinline__ double kernel_weight(int kind, double dx, double dy, double h,
-                                                double inv_h2, double truncate, double norm) {
+// Closed forms, dispatched on the primitive kernel kind.  dx, dy = particle - pixel centre,
+// as in martini.py:275-277.
+__device__ __forceinline__ double kernel_weight_closed(int kind, double dx, double dy, double h,
+                                                       double inv_h2, double truncate, double norm) {
   switch (kind) {
     case MTN_KERNEL_WENDLANDC2:
       return w_wendland_c2(sq_dist(dx, dy), inv_h2);
@@ -188,6 +188,14 @@ __device__ __forceinline__ double kernel_weight(int kind, double dx, double dy, 
   }
 }
 
+// The weight the projection kernel uses: the tabulated form where one exists (Wendland C2,
+// cubic spline; tables.cuh), the closed form otherwise.
+__device__ __forceinline__ double kernel_weight(int kind, double dx, double dy, double h,
+                                                double inv_h2, double truncate, double norm) {
+  if (wtab_has(kind)) return wtab_eval(kind, sq_dist(dx, dy) * inv_h2) * inv_h2;
+  return kernel_weight_closed(kind, dx, dy, h, inv_h2, truncate, norm);
+}
+
 // ---------------------------------------------------------------------------------------
 // Spectra.  For channel c with edges (lo, hi) = (min, max) of edges[c], edges[c+1]:
 //   Gaussian  : 0.5 * [erf((hi - v) / sqrt2 / sigma) - erf((lo - v) / sqrt2 / sigma)]
@@ -195,34 +203,6 @@ __device__ __forceinline__ double kernel_weight(int kind, double dx, double dy, 
 //   DiracDelta: heaviside(v - lo, 1) * heaviside(hi - v, 1)   spectral_models.py:544-570
 // then * mHI * D^-2 / |hi - lo| / 2.36e5 (spectral_models.py:119-145).
 // ---------------------------------------------------------------------------------------
-
-// Table of Taylor coefficients of erf (filled once by the host in extended precision, see
-// api.cu: init_erf_table).  Row i holds erf^(k)(c_i)/k!, k = 0..ERF_DEG, at the centre
-// c_i = (i + 1/2)/ERF_INV_W of the interval [i, i+1)/ERF_INV_W.
-__device__ double g_erf_table[ERF_NINT * ERF_NCOEF];
-
-// erf(t) to ~1 ulp: exactly +-1 for |t| >= ERF_SAT (where erf rounds to 1 in float64 anyway),
-// otherwise a degree-9 Taylor polynomial about the centre of the 1/16-wide interval holding
-// |t| (|u| <= 1/32: truncation < 5e-18).  ~10 FMAs instead of libm's ~100 instructions.
-__device__ __forceinline__ double erf_tab(double t) {
-  const double a = fabs(t);
-  if (a >= ERF_SAT) return copysign(1.0, t);
-  const int i = (int)(a * ERF_INV_W);
-  const double u = a - ((double)i + 0.5) * (1.0 / ERF_INV_W);
-  const double2* row = reinterpret_cast<const double2*>(g_erf_table + i * ERF_NCOEF);
-  const double2 c89 = __ldg(row + 4), c67 = __ldg(row + 3), c45 = __ldg(row + 2),
-                c23 = __ldg(row + 1), c01 = __ldg(row);
-  double r = fma(c89.y, u, c89.x);
-  r = fma(r, u, c67.y);
-  r = fma(r, u, c67.x);
-  r = fma(r, u, c45.y);
-  r = fma(r, u, c45.x);
-  r = fma(r, u, c23.y);
-  r = fma(r, u, c23.x);
-  r = fma(r, u, c01.y);
-  r = fmin(fma(r, u, c01.x), 1.0);
-  return copysign(r, t);
-}
 
 // erf of a channel edge seen from a particle.
 __device__ __forceinline__ double edge_erf(double edge, double v, double inv_s) {

@@ -190,6 +190,7 @@ struct ProjSmem {
   uint8_t wowner[PBATCH];        // particles with a non-empty box, in order
   uint8_t eowner[PBATCH];        // particles with a non-empty edge run, in order
   uint8_t box[PBATCH][4];        // tile-local box: x0, nx, y0, ny
+  uint8_t e01[PBATCH][2];        // setup scratch: first / one-past-last live edge
   uint8_t erun[PBATCH][2];       // first edge to evaluate, number of edges
   uint8_t chan[PBATCH][2];       // live channels of the brick: [cs, ce)
   uint8_t hlive[PBATCH];         // bit h: channel half h of the brick holds a non-zero
@@ -300,107 +301,133 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
       mbar_wait(&sm.bar[buf], (phase >> buf) & 1u);
       phase ^= 1u << buf;
 
-      // ---- setup (warp 0, lane = particle): live channels, edge run, box in the tile -------
-      if (warp == 0) {
-        int bx0 = 0, bnx = 0, by0 = 0, bny = 0, w0 = 0, nw = 0, cs = 0, ce = 0;
+      // ---- setup, lane = particle.  Stage 1: the four independent searches (x box, y box,
+      // first / last live edge) run on different warps; stage 2: warps 0 and 1 combine them
+      // into the live-channel range, the enumeration prefixes and the owner lists. -----------
+      for (int task = warp; task < 4; task += PROJ_WARPS) {
+        int v0 = 0, v1 = 0;
         if (lane < nb) {
           const Record& r = sm.rec[buf][lane];
-          // g(e) = sgn * (edge[e] - v) * inv_s is non-decreasing in the edge index e
-          const double v = r.v, sc = gaussian_line ? sgn * r.inv_s : sgn;
-          const double lo_t = gaussian_line ? -ERF_SAT : 0.0, hi_t = gaussian_line ? ERF_SAT : 0.0;
-          int l = 0, h = CB + 1;
-          while (l < h) {  // e0: first edge with g > -SAT (Gaussian) / g >= 0 (Dirac)
-            const int m = (l + h) >> 1;
-            const double x = (sm.edge[m] - v) * sc;
-            if (gaussian_line ? (x > lo_t) : (x >= lo_t)) h = m; else l = m + 1;
-          }
-          const int e0 = l;
-          l = gaussian_line ? e0 : 0;
-          h = CB + 1;
-          while (l < h) {  // e1: first edge with g >= SAT (Gaussian) / g > 0 (Dirac)
-            const int m = (l + h) >> 1;
-            const double x = (sm.edge[m] - v) * sc;
-            if (gaussian_line ? (x >= hi_t) : (x > hi_t)) h = m; else l = m + 1;
-          }
-          const int e1 = l;
-          // channel c can be non-zero only if edge c+1 >= e0 and edge c < e1:
-          //   Gaussian: some edge of the channel is unsaturated, or the saturation flips in it
-          //   Dirac   : lo <= v <= hi, both closed (spectral_models.py:564-569)
-          cs = max(e0 - 1, clo);
-          ce = min(e1, nch);
-          if (cs >= ce) cs = ce = 0;
-          if (ce > cs) {
-            if (gaussian_line) {  // edges to evaluate: the live channels' edges
-              w0 = cs;
-              nw = ce - cs + 1;
-            }
+          if (task < 2) {  // candidate box of martini.py:272-274 along x (task 0) or y (task 1)
             int lo, hi;
-            if (pixel_bounds(r.px, (double)r.r, x0, x_last, lo, hi)) {
-              bx0 = lo - x0;
-              bnx = hi - lo + 1;
+            const bool any = task == 0 ? pixel_bounds(r.px, (double)r.r, x0, x_last, lo, hi)
+                                       : pixel_bounds(r.py, (double)r.r, y0, y_last, lo, hi);
+            if (any) {
+              v0 = lo - (task == 0 ? x0 : y0);
+              v1 = hi - lo + 1;
             }
-            if (pixel_bounds(r.py, (double)r.r, y0, y_last, lo, hi)) {
-              by0 = lo - y0;
-              bny = hi - lo + 1;
+          } else {
+            // g(e) = sgn * (edge[e] - v) * inv_s is non-decreasing in the edge index e.
+            // task 2: e0 = first edge with g > -SAT (Gaussian) / g >= 0 (Dirac)
+            // task 3: e1 = first edge with g >= SAT (Gaussian) / g > 0 (Dirac)
+            const double v = r.v, sc = gaussian_line ? sgn * r.inv_s : sgn;
+            const double thr = gaussian_line ? (task == 2 ? -ERF_SAT : ERF_SAT) : 0.0;
+            const bool strict = gaussian_line ? task == 2 : task == 3;  // '>' vs '>='
+            int l = 0, h = CB + 1;
+            while (l < h) {
+              const int m = (l + h) >> 1;
+              const double x = (sm.edge[m] - v) * sc;
+              if (strict ? (x > thr) : (x >= thr)) h = m; else l = m + 1;
             }
-            if (bnx == 0 || bny == 0) bnx = bny = 0;
+            v0 = l;
           }
         }
-        sm.box[lane][0] = (uint8_t)bx0;
-        sm.box[lane][1] = (uint8_t)bnx;
-        sm.box[lane][2] = (uint8_t)by0;
-        sm.box[lane][3] = (uint8_t)bny;
-        sm.rny[lane] = bny ? 1.0f / (float)bny : 0.0f;
-        sm.erun[lane][0] = (uint8_t)w0;
-        sm.erun[lane][1] = (uint8_t)nw;
-        sm.chan[lane][0] = (uint8_t)cs;
-        sm.chan[lane][1] = (uint8_t)ce;
-        uint32_t hl = 0;
-#pragma unroll
-        for (int hh = 0; hh < N_HALF; ++hh)
-          if (cs < (hh + 1) * CH_HALF && ce > hh * CH_HALF) hl |= 1u << hh;
-        sm.hlive[lane] = (uint8_t)hl;
-        const uint32_t area = (uint32_t)(bnx * bny);
-        const uint32_t ne = area ? (uint32_t)nw : 0u;  // no pixels, no spectrum needed
-        const uint32_t wi = warp_incl_scan_u32(area, lane);
-        const uint32_t ei = warp_incl_scan_u32(ne, lane);
-        sm.wprefix[lane] = wi - area;
-        sm.eprefix[lane] = ei - ne;
-        if (lane == 31) {
-          sm.wprefix[32] = wi;
-          sm.eprefix[32] = ei;
+        if (task < 2) {
+          sm.box[lane][2 * task] = (uint8_t)v0;
+          sm.box[lane][2 * task + 1] = (uint8_t)v1;
+          if (task == 1) sm.rny[lane] = v1 ? 1.0f / (float)v1 : 0.0f;
+        } else {
+          sm.e01[lane][task - 2] = (uint8_t)v0;
         }
+      }
+      __syncthreads();
+      if (warp < 2) {
+        // channel c can be non-zero only if edge c+1 >= e0 and edge c < e1:
+        //   Gaussian: some edge of the channel is unsaturated, or the saturation flips in it
+        //   Dirac   : lo <= v <= hi, both closed (spectral_models.py:564-569)
+        const int e0 = sm.e01[lane][0], e1 = sm.e01[lane][1];
+        int cs = max(e0 - 1, clo), ce = min(e1, nch);
+        if (cs >= ce || lane >= nb) cs = ce = 0;
+        const int bnx = sm.box[lane][1], bny = sm.box[lane][3];
+        const uint32_t area = (ce > cs && bnx && bny) ? (uint32_t)(bnx * bny) : 0u;
+        // edges to evaluate: those of the live channels; none if no pixel is reached
+        const uint32_t ne = (area && gaussian_line) ? (uint32_t)(ce - cs + 1) : 0u;
         const uint32_t lt = (1u << lane) - 1u;
-        const uint32_t wm = __ballot_sync(0xffffffffu, area != 0), em = __ballot_sync(0xffffffffu, ne != 0);
-        if (area != 0) sm.wowner[__popc(wm & lt)] = (uint8_t)lane;
-        if (ne != 0) sm.eowner[__popc(em & lt)] = (uint8_t)lane;
+        if (warp == 0) {
+          sm.chan[lane][0] = (uint8_t)cs;
+          sm.chan[lane][1] = (uint8_t)ce;
+          uint32_t hl = 0;
+#pragma unroll
+          for (int hh = 0; hh < N_HALF; ++hh)
+            if (cs < (hh + 1) * CH_HALF && ce > hh * CH_HALF) hl |= 1u << hh;
+          sm.hlive[lane] = (uint8_t)(area ? hl : 0u);
+          const uint32_t wi = warp_incl_scan_u32(area, lane);
+          sm.wprefix[lane] = wi - area;
+          if (lane == 31) sm.wprefix[32] = wi;
+          const uint32_t wm = __ballot_sync(0xffffffffu, area != 0);
+          if (area != 0) sm.wowner[__popc(wm & lt)] = (uint8_t)lane;
+        }
+        if (warp == PROJ_WARPS - 1 || warp == 1) {  // warp 1, or warp 0 again in a 1-warp CTA
+          sm.erun[lane][0] = (uint8_t)cs;
+          sm.erun[lane][1] = (uint8_t)ne;
+          const uint32_t ei = warp_incl_scan_u32(ne, lane);
+          sm.eprefix[lane] = ei - ne;
+          if (lane == 31) sm.eprefix[32] = ei;
+          const uint32_t em = __ballot_sync(0xffffffffu, ne != 0);
+          if (ne != 0) sm.eowner[__popc(em & lt)] = (uint8_t)lane;
+        }
       }
       __syncthreads();
 
       // ---- phase A: kernel integrals (once per pair) and edge erfs (once per live edge) ---
-      // Items are enumerated through the prefix sums; a warp takes 32 consecutive items, so
-      // its lanes mostly share a particle (coherent branches, conflict-free rows).
+      // Items are enumerated through the prefix sums; a warp takes 2 x 32 consecutive items
+      // per step, so its lanes mostly share a particle (coherent branches, conflict-free
+      // rows) and every lane carries two independent dependency chains (the tabulated
+      // evaluators are straight-line code, so the two interleave).
       {
         const uint32_t total = sm.wprefix[PBATCH];
         const uint32_t my_start = sm.wprefix[lane];
         const bool my_nonempty = sm.wprefix[lane + 1] > my_start;
-        for (uint32_t q0 = warp * 32; q0 < total; q0 += PROJ_THREADS) {
-          const uint32_t q = q0 + lane;
-          const int ord = owner_ordinal(q0, my_start, my_nonempty, lane);
-          if (q < total) {
-            const int p = sm.wowner[ord];
-            const uint32_t local = q - sm.wprefix[p];
+        for (uint32_t q0 = warp * 64; q0 < total; q0 += PROJ_WARPS * 64) {
+          const int ord[2] = {owner_ordinal(q0, my_start, my_nonempty, lane),
+                              owner_ordinal(q0 + 32, my_start, my_nonempty, lane)};
+          bool ok[2];
+          int pp[2], pix[2], kind[2];
+          double dx[2], dy[2], R2[2], ih2[2], tv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t q = q0 + 32 * u + lane;
+            ok[u] = q < total;
+            const int p = ok[u] ? sm.wowner[ord[u]] : sm.wowner[0];
+            const uint32_t local = ok[u] ? q - sm.wprefix[p] : 0u;
             const int ix = (int)(((float)local + 0.5f) * sm.rny[p]);
             const int iy = (int)local - ix * sm.box[p][3];
             const int tpx = sm.box[p][0] + ix, tpy = sm.box[p][2] + iy;
             const Record& r = sm.rec[buf][p];
-            const int kid = r.kid;
+            pp[u] = p;
+            pix[u] = tpx * TILE_Y + tpy;
+            kind[u] = a.table.kind[r.kid];
             // dij = pixcoords - ij (martini.py:276)
-            sm.W[p][tpx * TILE_Y + tpy] =
-                kernel_weight(a.table.kind[kid], __dsub_rn(r.px, (double)(x0 + tpx)),
-                              __dsub_rn(r.py, (double)(y0 + tpy)), r.h, r.inv_h2,
-                              a.table.truncate[kid], a.table.norm[kid]);
-            if (COUNT) ++n_w;
+            dx[u] = __dsub_rn(r.px, (double)(x0 + tpx));
+            dy[u] = __dsub_rn(r.py, (double)(y0 + tpy));
+            ih2[u] = r.inv_h2;
+            R2[u] = sq_dist(dx[u], dy[u]) * ih2[u];
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u)  // straight-line, both chains in flight together
+            tv[u] = wtab_eval(wtab_has(kind[u]) ? kind[u] : MTN_KERNEL_WENDLANDC2, R2[u]) * ih2[u];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (ok[u]) {
+              double w = tv[u];
+              if (!wtab_has(kind[u])) {  // kernels without a table: closed form
+                const Record& r = sm.rec[buf][pp[u]];
+                w = kernel_weight_closed(kind[u], dx[u], dy[u], r.h, r.inv_h2, a.table.truncate[r.kid],
+                                         a.table.norm[r.kid]);
+              }
+              sm.W[pp[u]][pix[u]] = w;
+              if (COUNT) ++n_w;
+            }
           }
         }
       }
@@ -408,18 +435,33 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         const uint32_t total = sm.eprefix[PBATCH];
         const uint32_t my_start = sm.eprefix[lane];
         const bool my_nonempty = sm.eprefix[lane + 1] > my_start;
-        for (uint32_t q0 = warp * 32; q0 < total; q0 += PROJ_THREADS) {
-          const uint32_t q = q0 + lane;
-          const int ord = owner_ordinal(q0, my_start, my_nonempty, lane);
-          if (q < total) {
-            const int p = sm.eowner[ord];
-            const int e = sm.erun[p][0] + (int)(q - sm.eprefix[p]);
+        for (uint32_t q0 = warp * 64; q0 < total; q0 += PROJ_WARPS * 64) {
+          const int ord[2] = {owner_ordinal(q0, my_start, my_nonempty, lane),
+                              owner_ordinal(q0 + 32, my_start, my_nonempty, lane)};
+          bool ok[2];
+          int pp[2], ee[2];
+          double t[2], ev[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t q = q0 + 32 * u + lane;
+            ok[u] = q < total;
+            const int p = ok[u] ? sm.eowner[ord[u]] : sm.eowner[0];
+            const int e = ok[u] ? sm.erun[p][0] + (int)(q - sm.eprefix[p]) : 0;
             const Record& r = sm.rec[buf][p];
+            pp[u] = p;
+            ee[u] = e;
             // g orientation (sign folded in): S[c] = E[c+1] - E[c] >= 0; saturated edges at
             // the ends of the run come out as exactly -1 / +1
-            const double t = (sm.edge[e] - r.v) * (sgn * r.inv_s);
-            sm.ES[p][e] = erf_tab(t);
-            if (COUNT) n_erf += fabs(t) < ERF_SAT;
+            t[u] = (sm.edge[e] - r.v) * (sgn * r.inv_s);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) ev[u] = erf_tab(t[u]);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (ok[u]) {
+              sm.ES[pp[u]][ee[u]] = ev[u];
+              if (COUNT) n_erf += fabs(t[u]) < ERF_SAT;
+            }
           }
         }
       }
@@ -457,7 +499,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
 
       // ---- warp-private list: which particles touch my sub-block, and on which pixels -----
       uint32_t mymask = 0;
-      if (lane < nb && sm.box[lane][1] != 0 && ((sm.hlive[lane] >> half) & 1u)) {
+      if (lane < nb && ((sm.hlive[lane] >> half) & 1u)) {
         const int bx0 = sm.box[lane][0], bx1 = bx0 + sm.box[lane][1];
         const int by0 = sm.box[lane][2], by1 = by0 + sm.box[lane][3];
 #pragma unroll

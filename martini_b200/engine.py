@@ -212,14 +212,19 @@ class Engine:
         L.check(self.lib.mtn_fp64_peak(C.byref(t), C.byref(ms), self._stream()), "mtn_fp64_peak")
         return t.value
 
-    def probe_kernel_integral(self, entry: dict, dx, dy, h):
+    def probe_kernel_integral(self, entry: dict, dx, dy, h, closed_form=False):
         e = KernelTable([entry]).to_c().k[0]
         dx, dy, h = (self.to_device(a) for a in (dx, dy, h))
         out = torch.empty_like(dx)
-        L.check(self.lib.mtn_probe_kernel_integral(C.byref(e), dx.numel(), _ptr(dx), _ptr(dy),
-                                                   _ptr(h), _ptr(out), self._stream()),
+        L.check(self.lib.mtn_probe_kernel_integral(C.byref(e), int(closed_form), dx.numel(), _ptr(dx),
+                                                   _ptr(dy), _ptr(h), _ptr(out), self._stream()),
                 "mtn_probe_kernel_integral")
         return out
+
+    def table_error(self, kind: int) -> float:
+        err = C.c_double()
+        L.check(self.lib.mtn_table_error(int(kind), C.byref(err)), "mtn_table_error")
+        return err.value
 
     def probe_spectra(self, spectrum, v, sigma, amp, edges):
         v, amp, edges = (self.to_device(a) for a in (v, amp, edges))

@@ -83,6 +83,28 @@ def test_kernel_integral_vs_reference(eng, tag):
     assert np.abs(w[big] / ref[big] - 1).max() < 1e-9
 
 
+@pytest.mark.parametrize("tag", ("_WendlandC2Kernel", "_CubicSplineKernel"))
+def test_tabulated_kernels_match_their_closed_form(eng, tag):
+    """Wendland C2 and the cubic spline are evaluated from piecewise-polynomial tables built
+    from the reference's closed forms in extended precision (csrc/tables_host.hpp); the table
+    must agree with the closed form evaluated on the device to 1e-13 of the kernel peak."""
+    name, kw = PRIMS[tag]
+    k = getattr(K, name)(**kw)
+    assert 0 < eng.table_error(k._kind) < 2e-14  # worst fit error found when the table was built
+    rng = np.random.Generator(np.random.PCG64(77))
+    n = 200000
+    h = rng.uniform(0.5, 20.0, n)
+    r = np.r_[rng.uniform(0, 1.05, n - 1000) ** 1.5, rng.uniform(0, 1e-3, 500), 1 - rng.uniform(0, 1e-6, 500)] * h
+    phi = rng.uniform(0, 2 * np.pi, n)
+    dx, dy = r * np.cos(phi), r * np.sin(phi)
+    tab = eng.probe_kernel_integral(k._entry(), dx, dy, h).cpu().numpy()
+    closed = eng.probe_kernel_integral(k._entry(), dx, dy, h, closed_form=True).cpu().numpy()
+    scale = (closed * h * h).max()
+    assert np.abs((tab - closed) * h * h).max() <= 1e-13 * scale
+    assert np.array_equal(tab != 0, closed != 0)
+    assert eng.table_error(K.DiracDeltaKernel._kind) == 0.0  # no table: closed form is used
+
+
 @pytest.mark.parametrize("edir", ("dec", "inc"))
 @pytest.mark.parametrize("sname", ("gauss7", "gaussP", "dirac"))
 def test_spectra_vs_reference(eng, sname, edir):
