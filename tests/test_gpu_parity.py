@@ -336,3 +336,40 @@ def test_cfg2_full_size_mass_and_slabs(eng, cfg2_full):
     nx = case["shape"][0]
     parts = [run_hot_path(eng, case, x_lo=a, x_hi=b)["cube"] for a, b in ((0, 120), (120, nx))]
     assert_same_cube(torch.cat(parts, dim=0), cube)
+
+
+def sampled_pixel_check(eng, case, n_pix, seed, bright_box=None):
+    """Run the hot path and compare seeded pixel columns with the reference-structured oracle."""
+    out = run_hot_path(eng, case)
+    cube = out["cube"]
+    peak = float(cube.abs().max())
+    nx, ny, nc = case["shape"]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pix = [(int(rng.integers(0, nx)), int(rng.integers(0, ny))) for _ in range(n_pix // 2)]
+    lo, hi = bright_box or (nx // 2 - nx // 8, nx // 2 + nx // 8)
+    pix += [(int(rng.integers(lo, hi)), int(rng.integers(lo, hi))) for _ in range(n_pix - len(pix))]
+    ref = oracle_pixels(case, pix)
+    got = np.array([cube[i, j].cpu().numpy() for i, j in pix])
+    assert np.abs(ref).max() > 0.05 * peak
+    assert np.abs(got - ref).max() <= 1e-6 * peak
+    return out
+
+
+def test_cfg3_thermal_adaptive_cubic_midsize(eng):
+    """BASELINE config 3 shape (TNG-like: adaptive CubicSplineKernel, per-particle thermal
+    sigma, sub-pixel to 15-pixel smoothing lengths) at 1e6 particles / 256x256x128: sampled
+    pixel columns against the oracle, all three adaptive branches present."""
+    case = synthetic.make_case("cfg3", n=1_000_000, nx=256, ny=256, nc=128)
+    out = sampled_pixel_check(eng, case, 32, seed=303)
+    kid = out["kernel_id"].cpu().numpy()
+    assert set(np.unique(kid)) == {0, 1, 2}
+
+
+def test_cfg4_wide_footprints_midsize(eng):
+    """BASELINE config 4 shape (GaussianKernel(truncate=3) with footprints up to ~100 pixels
+    across, DiracDeltaSpectrum) at 1e5 particles / 256x256x64: every particle overlaps
+    hundreds of bricks."""
+    case = synthetic.make_case("cfg4", n=100_000, nx=256, ny=256, nc=64)
+    case["sm_length"] = case["sm_length"] * 2.0  # keep 8..40 px smoothing lengths at this cube size
+    out = sampled_pixel_check(eng, case, 24, seed=404, bright_box=(64, 192))
+    assert out["plan"].n_pairs > 50 * out["plan"].n_kept
