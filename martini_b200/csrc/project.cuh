@@ -8,17 +8,18 @@
 // into shared memory with cp.async.bulk (one 64-byte bulk copy per record, completion on an
 // mbarrier, double buffered).  Per batch of 32 staged particles:
 //
-//   setup  warp 0, one lane per particle: the particle's candidate box inside the tile
-//          (martini.py:272-274, exact predicate) and its window of unsaturated channel
-//          edges; prefix sums of box areas and window lengths;
-//   A      every (particle, box pixel) pair and every (particle, unsaturated edge) pair is
-//          handed to one thread through those prefix sums -- all lanes hold real work --
-//          which evaluates the SPH-kernel pixel integral, or the edge erf, ONCE into shared
-//          memory;
-//   B      edge erfs -> per-channel line spectra S[p][c], in place; each warp builds, with one
-//          ballot, the list of particles that touch its sub-block and their pixel masks;
-//   C      each warp walks its own list: the lane loads its two S values once and does
-//          acc[pixel] += W * S for the masked pixels (W is a shared-memory broadcast).
+//   setup  one lane per particle; the four independent searches (candidate box along x and
+//          y -- martini.py:272-274, exact predicate -- first and last live channel edge)
+//          run on different warps, then warps 0/1 turn them into prefix sums of box areas
+//          and edge-run lengths;
+//   A      every (particle, box pixel) pair and every (particle, live edge) pair is handed to
+//          one thread through those prefix sums -- all lanes hold real work, two items per
+//          lane so two dependency chains are in flight -- which evaluates the SPH-kernel
+//          pixel integral (tabulated, tables.cuh) or the edge erf ONCE into shared memory;
+//   C      each warp builds, with one ballot, the list of particles that touch its sub-block
+//          and their pixel masks, then walks it: the lane forms its two spectrum values
+//          S = (E[c+1] - E[c]) amp / dv from the shared edge erfs and does acc[pixel] += W * S
+//          for the masked pixels (W is a shared-memory broadcast).
 //
 // No atomics on the data path; every voxel is stored exactly once, as a 16-byte vector store
 // (a warp writes 512 contiguous bytes per pixel).
@@ -80,18 +81,6 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t x, int lane) {
     if (lane >= d) x += y;
   }
   return x;
-}
-
-// index p of the run [pre[p], pre[p+1]) that holds q; pre is a non-decreasing exclusive prefix
-// over n <= 32 entries (runs may be empty: the last p with pre[p] <= q is the owner)
-__device__ __forceinline__ int find_owner(const uint32_t* pre, int n, uint32_t q) {
-  int lo = 0, hi = n - 1;
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (pre[mid] <= q) lo = mid; else hi = mid - 1;
-  }
-  return lo;
 }
 
 // ------------------------------------------------------------------------------ work items
@@ -181,9 +170,9 @@ constexpr int W_STRIDE = TILE_PIX + 1;  // odd row stride: lane-per-particle rea
 struct ProjSmem {
   Record rec[2][PBATCH];
   double W[PBATCH][W_STRIDE];   // kernel integrals, valid inside the particle's box only
-  double ES[PBATCH][CB + 2];    // edge erfs (up to CB+1 per particle), then spectra S in place
+  double ES[PBATCH][CB + 2];    // edge erfs of the live channels (up to CB+1 per particle)
+  double inv_dv[CB];            // (16-byte aligned: read as double2)
   double edge[CB + 1];
-  double inv_dv[CB];
   uint32_t wprefix[PBATCH + 1];  // exclusive prefix of box areas
   uint32_t eprefix[PBATCH + 1];  // exclusive prefix of edge-run lengths
   float rny[PBATCH];             // 1 / (box height)
@@ -467,36 +456,6 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
       }
       __syncthreads();
 
-      // ---- phase B: spectra in place of the edge erfs (warp per particle) ------------------
-      for (int p = warp; p < nb; p += PROJ_WARPS) {
-        const int cs = sm.chan[p][0], ce = sm.chan[p][1];
-        if (sm.wprefix[p + 1] == sm.wprefix[p] || ce <= cs) continue;  // nothing to add
-        const Record& r = sm.rec[buf][p];
-        double s[N_HALF][2];
-#pragma unroll
-        for (int hh = 0; hh < N_HALF; ++hh) {
-          const int c = hh * CH_HALF + 2 * lane;
-          const bool in0 = c >= cs && c < ce, in1 = c + 1 >= cs && c + 1 < ce;
-          if (gaussian_line) {
-            const double2 eab = *reinterpret_cast<const double2*>(&sm.ES[p][c]);
-            const double ec = sm.ES[p][c + 2];
-            // 0.5*[erf(hi) - erf(lo)] * A / dv / 2.36e5; the 0.5 lives in amp
-            s[hh][0] = in0 ? (eab.y - eab.x) * (r.amp * sm.inv_dv[c]) : 0.0;
-            s[hh][1] = in1 ? (ec - eab.y) * (r.amp * sm.inv_dv[c + 1]) : 0.0;
-          } else {
-            // live channels are exactly those with lo <= v <= hi (setup)
-            s[hh][0] = in0 ? r.amp * sm.inv_dv[c] : 0.0;
-            s[hh][1] = in1 ? r.amp * sm.inv_dv[c + 1] : 0.0;
-          }
-        }
-        __syncwarp();  // every lane has read its edges before anyone overwrites them
-#pragma unroll
-        for (int hh = 0; hh < N_HALF; ++hh)
-          *reinterpret_cast<double2*>(&sm.ES[p][hh * CH_HALF + 2 * lane]) =
-              make_double2(s[hh][0], s[hh][1]);
-      }
-      __syncthreads();
-
       // ---- warp-private list: which particles touch my sub-block, and on which pixels -----
       uint32_t mymask = 0;
       if (lane < nb && ((sm.hlive[lane] >> half) & 1u)) {
@@ -517,7 +476,24 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         const int p = __ffs(rel) - 1;
         rel &= rel - 1;
         const uint32_t m = __shfl_sync(0xffffffffu, mymask, p);
-        const double2 s2 = *reinterpret_cast<const double2*>(&sm.ES[p][half * CH_HALF + 2 * lane]);
+        // this lane's two channels of the particle's line spectrum, from the shared edge erfs
+        // (adjacent channels share an edge):  S = 0.5 [erf(hi) - erf(lo)] A / dv / 2.36e5,
+        // the 0.5 and 2.36e5 live in amp; channels outside the live range are exactly zero
+        const int c = half * CH_HALF + 2 * lane;
+        const uint32_t cs = sm.chan[p][0], span = sm.chan[p][1] - cs;
+        const bool in0 = (uint32_t)c - cs < span, in1 = (uint32_t)c + 1u - cs < span;
+        const double amp = sm.rec[buf][p].amp;
+        const double2 idv = *reinterpret_cast<const double2*>(&sm.inv_dv[c]);
+        double2 s2;
+        if (gaussian_line) {
+          const double2 eab = *reinterpret_cast<const double2*>(&sm.ES[p][c]);
+          const double ec = sm.ES[p][c + 2];
+          s2.x = in0 ? (eab.y - eab.x) * (amp * idv.x) : 0.0;
+          s2.y = in1 ? (ec - eab.y) * (amp * idv.y) : 0.0;
+        } else {  // Dirac line: the live channels are exactly those with lo <= v <= hi
+          s2.x = in0 ? amp * idv.x : 0.0;
+          s2.y = in1 ? amp * idv.y : 0.0;
+        }
         const double* Wp = sm.W[p];
 #pragma unroll
         for (int j = 0; j < SUB_PIX; ++j) {
