@@ -1,5 +1,6 @@
 // C ABI of libmartini_b200.so -- see include/martini_b200.h for the contract.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernel_integrals.cuh"
@@ -228,7 +229,12 @@ static size_t workspace_layout(int64_t n_kept, int64_t n_pairs, int64_t n_bricks
 
 static int64_t choose_chunk(int64_t n_pairs) {
   // enough work items for ~8 rounds over the resident CTAs, never smaller than 8 batches
-  const int64_t target = (int64_t)sm_count() * PROJ_CTAS_PER_SM * 8;
+  static int rounds = 0;
+  if (!rounds) {  // MTN_ITEM_ROUNDS: tuning knob, work items per resident CTA
+    const char* e = getenv("MTN_ITEM_ROUNDS");
+    rounds = e ? std::max(1, atoi(e)) : 8;
+  }
+  const int64_t target = (int64_t)sm_count() * PROJ_CTAS_PER_SM * rounds;
   int64_t chunk = std::max<int64_t>(8 * PBATCH, (n_pairs + target - 1) / target);
   return (chunk + PBATCH - 1) / PBATCH * PBATCH;
 }
