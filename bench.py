@@ -82,7 +82,8 @@ def workload_config(case, name, n_gpus):
         "particles": int(case["px"].size), "cube": [int(nx), int(ny), int(nc)],
         "kernel": case["kernel"][0], "spectrum": case["spectrum"],
         "partition": "1 GPU" if n_gpus == 1 else f"{n_gpus} x-slabs of {nx // n_gpus} rows, halo "
-                     "particles replicated, NCCL gather to rank 0",
+                     "particles replicated, slabs stored into rank 0's cube over NVLink (peer "
+                     "stores from the projection kernel; NCCL gather as fallback)",
         "l2": "L2 flushed between timed steps by writing a 512 MiB buffer",
     }
 
@@ -228,22 +229,38 @@ def run_b200(args):
     x_lo, x_hi = bounds[rank], bounds[rank + 1]
     pinned = pipeline.pin_case(case)
     dev = pipeline.upload(eng, case, pinned)
-    slab = torch.zeros((x_hi - x_lo, ny, nc), dtype=torch.float64, device=dev_t)
-    full = torch.empty((nx, ny, nc), dtype=torch.float64, device=dev_t) if (world > 1 and rank == 0) else None
+    # N > 1: the slabs are stored straight into rank 0's cube over NVLink (fused assembly,
+    # martini_b200.dist.PeerCube); NCCL gather if symmetric memory is unavailable
+    peer = None
+    if world > 1:
+        try:
+            peer = mdist.PeerCube((nx, ny, nc), bounds, dev_t)
+        except Exception as exc:  # noqa: BLE001
+            if rank == 0:
+                print(f"symmetric memory unavailable ({exc}); falling back to the NCCL gather", file=sys.stderr)
+        ok = torch.tensor([1.0 if peer is not None else 0.0], device=dev_t)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            peer = None
+    slab = peer.rows if peer is not None else torch.zeros((x_hi - x_lo, ny, nc), dtype=torch.float64, device=dev_t)
+    full = torch.empty((nx, ny, nc), dtype=torch.float64, device=dev_t) if (world > 1 and rank == 0 and peer is None) else None
     host_cube = torch.empty((nx, ny, nc), dtype=torch.float64).pin_memory() if rank == 0 else None
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev_t)
-
-    def gather():
-        if world == 1:
-            return slab
-        return mdist.gather_slabs(slab, bounds, full, dst=0)
 
     def step(e2e=False):
         if e2e:
             pipeline.upload(eng, case, pinned, out=dev)
-        slab.zero_()
+        if peer is not None:
+            peer.begin()  # rank 0 zeroes the cube, barrier
+        else:
+            slab.zero_()
         out = pipeline.run_hot_path(eng, case, dev=dev, cube=slab, x_lo=x_lo, x_hi=x_hi, zeroed=True, ctx=ctx)
-        res = gather()
+        if peer is not None:
+            res = peer.end()  # barrier: every rank's stores have landed in rank 0's cube
+        elif world == 1:
+            res = slab
+        else:
+            res = mdist.gather_slabs(slab, bounds, full, dst=0)
         if e2e and rank == 0:
             host_cube.copy_(res, non_blocking=True)
         return out

@@ -97,6 +97,44 @@ def allgather_slabs(slab: torch.Tensor, bounds, full: torch.Tensor):
     return full
 
 
+class PeerCube:
+    """Fused assembly: the projection kernel's voxel stores go straight into the destination
+    rank's cube over NVLink, so no gather pass follows the compute.
+
+    The cube is allocated in symmetric memory (``torch.distributed._symmetric_memory``: every
+    rank allocates the buffer, the CUDA driver maps all of them into every process); rank r
+    gets ``rows`` = a tensor aliasing rows [bounds[r], bounds[r+1]) of rank ``dst``'s buffer and
+    hands it to ``mtn_project`` as its slab.  The C ABI needs nothing special: a slab is just a
+    device pointer, and every voxel is stored once, as 16-byte vector stores (512 contiguous
+    bytes per warp) -- the access pattern NVLink peer stores like.  Use with MTN_CUBE_ZEROED
+    only (accumulate mode would read the cube back over the link).
+
+    Per insertion: ``begin()`` (dst zeroes its buffer, then a barrier so no store can overtake
+    the memset), the ranks project, ``end()`` (barrier: all stores have landed)."""
+
+    def __init__(self, shape, bounds, device, dst=0, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group or dist.group.WORLD
+        self.rank, self.dst = dist.get_rank(), dst
+        nx, ny, nc = shape
+        self.buf = symm_mem.empty((nx, ny, nc), dtype=torch.float64, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        lo, hi = bounds[self.rank], bounds[self.rank + 1]
+        self.rows = self.hdl.get_buffer(dst, (hi - lo, ny, nc), torch.float64, storage_offset=lo * ny * nc)
+
+    def begin(self):
+        if self.rank == self.dst:
+            self.buf.zero_()
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.group)
+
+    def end(self):
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.group)
+        return self.buf if self.rank == self.dst else None
+
+
 def insert_sharded(engine, case, dev=None, ctx=None, bounds=None, gather=True, full=None):
     """Run the hot path for this rank's slab and (optionally) gather the cube on rank 0.
 

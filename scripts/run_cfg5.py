@@ -76,6 +76,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--check-pixels", type=int, default=12)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--fused", action="store_true",
+                    help="store the slabs straight into rank 0's cube over NVLink (no gather pass)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -103,8 +105,10 @@ def main():
     del r_est, lo, hi, diff, w, ok
     bounds = mdist.slab_bounds(nx, world, work)
     x_lo, x_hi = bounds[rank], bounds[rank + 1]
-    slab = torch.zeros((x_hi - x_lo, ny, a.nc), dtype=torch.float64, device=eng.device)
-    full = torch.empty((nx, ny, a.nc), dtype=torch.float64, device=eng.device) if (rank == 0 and world > 1) else None
+    fused = a.fused and world > 1
+    peer = mdist.PeerCube((nx, ny, a.nc), bounds, eng.device) if fused else None
+    slab = peer.rows if fused else torch.zeros((x_hi - x_lo, ny, a.nc), dtype=torch.float64, device=eng.device)
+    full = torch.empty((nx, ny, a.nc), dtype=torch.float64, device=eng.device) if (rank == 0 and world > 1 and not fused) else None
 
     def step():
         slab.zero_()
@@ -119,10 +123,13 @@ def main():
         torch.cuda.synchronize()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
-        slab.zero_()
+        if fused:
+            peer.begin()
+        else:
+            slab.zero_()
         out = pipeline.run_hot_path(eng, case, dev=dev, cube=slab, x_lo=x_lo, x_hi=x_hi, zeroed=True, ctx=ctx)
         e1.record()
-        cube = mdist.gather_slabs(slab, bounds, full, dst=0)
+        cube = peer.end() if fused else mdist.gather_slabs(slab, bounds, full, dst=0)
         e2.record()
         torch.cuda.synchronize()
         if s > 0:  # first pass sizes the workspaces
@@ -143,6 +150,7 @@ def main():
             "workload": f"config 5: {a.particles} particles, {nx}x{ny}x{a.nc} cube, WendlandC2Kernel + "
                         "GaussianSpectrum(7 km/s), 64 discs + 10% background", "n_gpus": world,
             "scaling": "strong", "slab_bounds": bounds,
+            "assembly": "fused peer stores over NVLink (symmetric memory)" if fused else "NCCL gather",
             "ms_per_insertion": float(t[0]), "ms_compute_max_rank": float(t[1]),
             "updates_dense": float(u[0]), "updates_per_s": float(u[0]) / (float(t[0]) * 1e-3),
             "pairs_per_rank": [float(p[1]) for p in per_rank], "kept_per_rank": [float(p[2]) for p in per_rank],
