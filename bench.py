@@ -354,6 +354,23 @@ def run_b200(args):
             "gpu_launches_per_step": int(out["launches"]),
             "clocks": clocks, "roofline": roofline,
         }
+        if n_gpus == 1:
+            # for information: the same insertion through the MARTINI-compatible classes
+            # (Martini.__init__ prunes the host objects with numpy, insert_source_in_cube copies
+            # the cube back into DataCube._array) -- not part of any timed region above
+            from martini_b200 import DataCube, Martini, PixelSource
+            from martini_b200.spectral_models import DiracDeltaSpectrum, GaussianSpectrum
+
+            t0 = time.perf_counter()
+            dc = DataCube(n_px_x=nx, n_px_y=ny, n_channels=nc, px_size=case["px_size"],
+                          channel_width=float(abs(case["edges"][1] - case["edges"][0])))
+            spec = GaussianSpectrum(sigma=case["sigma"]) if case["spectrum"] == "gaussian" else DiracDeltaSpectrum()
+            if case["spectrum"] == "gaussian" and np.ndim(case["sigma"]) > 0:
+                spec.half_width = lambda source, _s=case["sigma"]: _s  # per-particle widths as given
+            m = Martini(source=PixelSource.from_case(case), datacube=dc, spectral_model=spec,
+                        sph_kernel=pipeline.kernel_from_spec(case["kernel"]), quiet=True, engine=eng)
+            m.insert_source_in_cube(skip_validation=True)
+            line["martini_class_wall_ms"] = (time.perf_counter() - t0) * 1e3
         if n_gpus == 1 and not args.no_cpu_baseline:
             val, t_full, desc, ncpu, _ = cpu_reference_arm(
                 make_workload(args.workload, 1, args.particles), args.sample_pixels, 3, 1)
