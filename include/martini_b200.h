@@ -207,6 +207,18 @@ int mtn_set_count_exec(int enable);
 int mtn_last_exec_counts(int64_t* out3);
 
 /*
+ * Beam convolution, the step after the projection.  Replaces the
+ * per-channel scipy.signal.fftconvolve(slice, beam.kernel, mode="same") loop of
+ * Martini.convolve_beam (martini/martini.py:863-901):
+ *   cube_out[x, y, c] = scale * sum_{a,b} cube_in[x + ka/2 - a, y + kb/2 - b, c] * kernel[a, b]
+ * with zeros outside the (nx, ny, nc) cube; kernel is the (ka, kb) beam image (odd sizes,
+ * device memory, row-major); scale carries the Jy/arcsec^2 -> Jy/beam factor (beam area).
+ * Out of place.
+ */
+int mtn_convolve_beam(const double* cube_in, double* cube_out, int32_t nx, int32_t ny, int32_t nc,
+                      const double* kernel, int32_t ka, int32_t kb, double scale, void* stream);
+
+/*
  * FP64 FMA throughput microbenchmark (register-resident dependent-chain FMAs), used by
  * bench.py as the measured roofline denominator for the projection kernel.  Returns the
  * achieved TFLOP/s (2 flops per FMA) in *tflops_out (host).  Synchronises.

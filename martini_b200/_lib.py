@@ -132,6 +132,11 @@ SYMBOLS = {
     "mtn_set_count_exec": (C.c_int, [C.c_int]),
     "mtn_last_exec_counts": (C.c_int, [C.POINTER(C.c_int64)]),
     "mtn_fp64_peak": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]),
+    "mtn_convolve_beam": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+         C.c_double, C.c_void_p],
+    ),
     "mtn_table_error": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     "mtn_probe_kernel_integral": (
         C.c_int,

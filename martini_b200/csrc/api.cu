@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "convolve.cuh"
 #include "kernel_integrals.cuh"
 #include "plan.cuh"
 #include "project.cuh"
@@ -581,6 +582,27 @@ int mtn_fp64_peak(double* tflops_out, double* ms_out, void* stream) {
   const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
   if (tflops_out) *tflops_out = flops / (best * 1e-3) / 1e12;
   if (ms_out) *ms_out = best;
+  return MTN_OK;
+}
+
+int mtn_convolve_beam(const double* cube_in, double* cube_out, int32_t nx, int32_t ny, int32_t nc,
+                      const double* kernel, int32_t ka, int32_t kb, double scale, void* stream) {
+  if (!cube_in || !cube_out || !kernel || cube_in == cube_out)
+    return fail(MTN_ERR_INVALID, "convolve_beam: bad pointers (in-place is not supported)%s", "");
+  if (nx <= 0 || ny <= 0 || nc <= 0 || ka <= 0 || kb <= 0 || !(ka & 1) || !(kb & 1) ||
+      (int64_t)ka * kb > CONV_MAX_TAPS)
+    return fail(MTN_ERR_INVALID, "convolve_beam: bad shape (beam image must be odd x odd, <= 96 x 96)%s", "");
+  const size_t smem = (size_t)ka * kb * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTN_CUDA(cudaFuncSetAttribute(convolve_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(CONV_MAX_TAPS * sizeof(double))));
+    attr_set = true;
+  }
+  const dim3 grid((nc + 31) / 32, (ny + 4 * CONV_TY - 1) / (4 * CONV_TY), nx);
+  convolve_beam_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(cube_in, cube_out, nx, ny, nc, kernel,
+                                                                   ka, kb, scale);
+  MTN_LAUNCH_CHECK();
   return MTN_OK;
 }
 

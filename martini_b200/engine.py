@@ -187,6 +187,17 @@ class Engine:
         del keep
         return plan
 
+    # ------------------------------------------------------------------ beam convolution
+    def convolve_beam(self, cube: torch.Tensor, kernel: torch.Tensor, scale: float = 1.0):
+        """out[x,y,c] = scale * (cube[:, :, c] (*) kernel)[x, y], 'same' size; see mtn_convolve_beam."""
+        assert cube.ndim == 3 and cube.dtype == torch.float64 and cube.is_contiguous()
+        kernel = self.to_device(kernel)
+        out = torch.empty_like(cube)
+        L.check(self.lib.mtn_convolve_beam(_ptr(cube), _ptr(out), cube.shape[0], cube.shape[1],
+                                           cube.shape[2], _ptr(kernel), kernel.shape[0], kernel.shape[1],
+                                           float(scale), self._stream()), "mtn_convolve_beam")
+        return out
+
     # ------------------------------------------------------------------ diagnostics
     STAGES = ("emit", "sort", "items", "project", "reduce", "finalize")
 

@@ -180,6 +180,38 @@ class Martini(_BaseMartini):
         self._insert_source_in_cube(skip_validation=skip_validation, progressbar=progressbar, ncpu=ncpu)
 
 
+    def convolve_beam(self):
+        """Convolve the cube with the beam, drop the pad, convert to Jy/beam
+        (martini.py:863-901), on the GPU (``mtn_convolve_beam``)."""
+        from warnings import warn
+
+        if self.beam is None:
+            warn("Skipping beam convolution, no beam object provided to Martini.")
+            return
+        dc = self._datacube
+        need = self.beam.needs_pad()
+        if dc.padx < need[0] or dc.pady < need[1]:
+            raise ValueError(
+                "datacube padding insufficient for beam convolution (perhaps you loaded a"
+                " datacube state with datacube.load_state that was previously initialized"
+                " by martini with a smaller beam?)")
+        if dc.array_unit != "Jy/arcsec2":
+            raise RuntimeError("convolve_beam expects a cube in Jy/arcsec2: insert the source first.")
+        eng = self.engine
+        arr = dc._array
+        cube = eng.to_device(np.ascontiguousarray(arr.reshape(arr.shape[:3])))
+        out = eng.convolve_beam(cube, self.beam.kernel, scale=self.beam.area)  # x area: -> Jy/beam
+        dc._array = out.cpu().numpy().reshape(arr.shape)
+        dc.drop_pad()
+        dc.array_unit = "Jy/beam"
+        if not self.quiet:
+            nz = dc._array[dc._array > 0]
+            print("Beam convolved.",
+                  f"  Data cube RMS after beam convolution: {np.std(dc._array):.2e} Jy / beam",
+                  f"  Maximum pixel: {dc._array.max():.2e} Jy / beam",
+                  f"  Median non-zero pixel: {np.median(nz) if nz.size else 0.0:.2e} Jy / beam", sep="\n")
+
+
 class GlobalProfile(_BaseMartini):
     """Spatially integrated spectrum (martini.py:1369-1832): a 1 x 1 pixel cube, all particles
     at pixel (0, 0), ``DiracDeltaKernel(size_in_fwhm=inf)``; pruning by velocity only."""
@@ -258,20 +290,26 @@ class _PadOnlyBeam:
         return (self._pad, self._pad)
 
 
-def demo(quiet=False, device="cuda:0"):
+def demo(quiet=False, device="cuda:0", convolve=False):
     """The hot-path slice of the reference's ``demo()`` (martini/_demo.py:95-161): the demo
     source into the demo cube with CubicSplineKernel + GaussianSpectrum(7 km/s).  The 30 arcsec
     Gaussian beam truncated at 4 sigma pads the cube by ceil(30*4/10 + 1) = 13 pixels; noise,
-    beam convolution and FITS output are outside this package's scope."""
+    and FITS output are outside this package's scope; ``convolve=True`` also runs the beam
+    convolution with the demo's 30 arcsec Gaussian beam."""
     from .sources import demo_source
     from .spectral_models import GaussianSpectrum
     from .sph_kernels import CubicSplineKernel
 
+    from .beams import GaussianBeam
+
     source = demo_source()
     datacube = DataCube(n_px_x=128, n_px_y=128, n_channels=32, px_size=10.0, channel_width=10.0,
                         spectral_centre=source.vsys)
-    m = Martini(source=source, datacube=datacube, beam=_PadOnlyBeam(13), noise=None,
+    beam = GaussianBeam(bmaj=30.0, bmin=30.0, bpa=0.0, truncate=4.0) if convolve else _PadOnlyBeam(13)
+    m = Martini(source=source, datacube=datacube, beam=beam, noise=None,
                 spectral_model=GaussianSpectrum(sigma=7.0), sph_kernel=CubicSplineKernel(),
                 quiet=quiet, device=device)
     m.insert_source_in_cube()
+    if convolve:
+        m.convolve_beam()
     return m

@@ -173,3 +173,37 @@ def test_unsupported_plugins_raise_before_any_work():
     dc = DataCube(n_px_x=4, n_px_y=4, n_channels=4, px_size=1.0, channel_width=1.0)
     with pytest.raises(NotImplementedError, match="MyKernel"):
         Martini(source=src, datacube=dc, sph_kernel=MyKernel(), spectral_model=GaussianSpectrum())
+
+
+@pytest.mark.parametrize("bmaj,bmin,bpa", ((30.0, 30.0, 0.0), (40.0, 20.0, 30.0)))
+def test_convolve_beam_vs_fftconvolve(bmaj, bmin, bpa):
+    """Martini.convolve_beam (martini.py:863-901) on the GPU against the
+    reference's per-channel scipy fftconvolve, incl. pad drop and the Jy/beam conversion."""
+    from martini_b200.beams import GaussianBeam
+    from oracle import martini_oracle as O
+
+    s = demo_source(N=300)
+    dc = DataCube(n_px_x=48, n_px_y=40, n_channels=16, px_size=10.0, channel_width=20.0, spectral_centre=s.vsys)
+    beam = GaussianBeam(bmaj=bmaj, bmin=bmin, bpa=bpa, truncate=4.0)
+    m = Martini(source=s, datacube=dc, beam=beam, spectral_model=GaussianSpectrum(sigma=7.0),
+                sph_kernel=CubicSplineKernel(), quiet=True)
+    pad = beam.needs_pad()
+    assert pad == (int(np.ceil(bmaj * 4 / 10 + 1)),) * 2 and dc._array.shape == (48 + 2 * pad[0], 40 + 2 * pad[1], 16)
+    assert np.isclose(beam.kernel.sum(), 1.0, rtol=2e-3)  # truncated at 4 FWHM
+    m.insert_source_in_cube()
+    before = m.datacube._array.copy()
+    ref = O.convolve_beam(before, beam.kernel, beam.area, *pad)
+    m.convolve_beam()
+    got = m.datacube._array
+    assert got.shape == (48, 40, 16) and m.datacube.padx == 0 and m.datacube.array_unit == "Jy/beam"
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert np.abs(ref).max() > 0
+
+
+def test_convolve_beam_needs_pad_and_beam():
+    s = demo_source(N=50)
+    dc = DataCube(n_px_x=16, n_px_y=16, n_channels=4, px_size=10.0, channel_width=50.0, spectral_centre=s.vsys)
+    m = Martini(source=s, datacube=dc, spectral_model=GaussianSpectrum(), sph_kernel=CubicSplineKernel(), quiet=True)
+    m.insert_source_in_cube()
+    with pytest.warns(UserWarning, match="no beam object"):
+        m.convolve_beam()
