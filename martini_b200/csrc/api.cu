@@ -83,12 +83,40 @@ static int ensure_tables() {
   if (T.rows.size() > (size_t)WT_MAX_ROWS * WT_ROW)
     return fail(MTN_ERR_LIMIT, "kernel tables exceed WT_MAX_ROWS%s", "");
   MTN_CUDA(cudaMemcpyToSymbol(g_erf_table, erf_tab_host, sizeof(erf_tab_host)));
-  MTN_CUDA(cudaMemcpyToSymbol(c_wreg, T.reg, sizeof(T.reg)));
-  MTN_CUDA(cudaMemcpyToSymbol(c_wnreg, T.nreg, sizeof(T.nreg)));
+  MTN_CUDA(cudaMemcpyToSymbol(c_wzone, T.zone, sizeof(T.zone)));
+  MTN_CUDA(cudaMemcpyToSymbol(c_wnz, T.nz, sizeof(T.nz)));
   MTN_CUDA(cudaMemcpyToSymbol(c_wscale, T.scale, sizeof(T.scale)));
+  MTN_CUDA(cudaMemcpyToSymbol(c_wend, T.end, sizeof(T.end)));
   MTN_CUDA(cudaMemcpyToSymbol(g_wtab_rows, T.rows.data(), T.rows.size() * sizeof(double)));
   if (dev >= 0 && dev < 64) done[dev] = true;
   return MTN_OK;
+}
+
+// One instantiation of the projection kernel per (diagnostic counting, uniform kernel kind).
+template <bool COUNT, int KIND>
+static int launch_project_as(const ProjArgs& a, unsigned grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTN_CUDA(cudaFuncSetAttribute(project_kernel<COUNT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(ProjSmem)));
+    attr_set = true;
+  }
+  project_kernel<COUNT, KIND><<<grid, PROJ_THREADS, sizeof(ProjSmem), st>>>(a);
+  return MTN_OK;
+}
+
+template <bool COUNT>
+static int launch_project_count(const ProjArgs& a, int uniform_kind, unsigned grid, cudaStream_t st) {
+  switch (uniform_kind) {
+    case MTN_KERNEL_WENDLANDC2: return launch_project_as<COUNT, MTN_KERNEL_WENDLANDC2>(a, grid, st);
+    case MTN_KERNEL_CUBICSPLINE: return launch_project_as<COUNT, MTN_KERNEL_CUBICSPLINE>(a, grid, st);
+    default: return launch_project_as<COUNT, -1>(a, grid, st);
+  }
+}
+
+static int launch_project(const ProjArgs& a, int uniform_kind, bool count, unsigned grid, cudaStream_t st) {
+  return count ? launch_project_count<true>(a, uniform_kind, grid, st)
+               : launch_project_count<false>(a, uniform_kind, grid, st);
 }
 
 static int make_geo(const MtnCube* c, Geo* g, int edges_increasing) {
@@ -494,23 +522,14 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
     a.px_area = px_area;
     a.zeroed = zeroed;
     a.exec_counts = (unsigned long long*)(ws.scalars + 8);  // zeroed with the scalars
-    static bool attr_set = false;
-    if (!attr_set) {
-      MTN_CUDA(cudaFuncSetAttribute(project_kernel<false>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sizeof(ProjSmem)));
-      MTN_CUDA(cudaFuncSetAttribute(project_kernel<true>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sizeof(ProjSmem)));
-      attr_set = true;
-    }
+    // every particle on one tabulated SPH kernel: the specialised instantiation
+    int uniform_kind = t.kind[0];
+    for (int k = 1; k < t.n; ++k)
+      if (t.kind[k] != uniform_kind) uniform_kind = -1;
     const unsigned pgrid =
         (unsigned)std::min<int64_t>(ws.max_items, (int64_t)sm_count() * PROJ_CTAS_PER_SM);
     mark(3, st);
-    if (g_count_exec)
-      project_kernel<true><<<pgrid, PROJ_THREADS, sizeof(ProjSmem), st>>>(a);
-    else
-      project_kernel<false><<<pgrid, PROJ_THREADS, sizeof(ProjSmem), st>>>(a);
+    if (int rc = launch_project(a, uniform_kind, g_count_exec != 0, pgrid, st)) return rc;
     MTN_LAUNCH_CHECK();
     mark(4, st);
     reduce_partials_kernel<<<dim3((unsigned)ws.max_multi, SUB_PIX), PROJ_THREADS, 0, st>>>(

@@ -25,13 +25,21 @@ constexpr int TILE_PIX = TILE_X * TILE_Y;
 constexpr int CH_HALF = 64;           // channels one warp covers: each lane owns 2 adjacent ones
 constexpr int N_HALF = 1;             // channel halves per brick, handled by different warps (1: brick = 64 channels)
 constexpr int CB = CH_HALF * N_HALF;  // channels per brick (unit of binning)
-constexpr int SUB = 4;                // a warp owns a SUB x SUB pixel sub-block of the tile
-constexpr int SUB_PIX = SUB * SUB;    // = accumulator pairs per thread
-constexpr int SUBS_Y = TILE_Y / SUB;  // sub-blocks per tile row
+#ifndef MTN_SUB_Y
+#define MTN_SUB_Y 4
+#endif
+#ifndef MTN_CTAS_PER_SM
+#define MTN_CTAS_PER_SM 0
+#endif
+constexpr int SUB_X = 4;              // a warp owns a SUB_X x SUB_Y pixel sub-block of the tile
+constexpr int SUB_Y = MTN_SUB_Y;
+constexpr int SUB_PIX = SUB_X * SUB_Y;  // = accumulator pairs per thread
+constexpr int SUBS_Y = TILE_Y / SUB_Y;  // sub-blocks per tile row
 constexpr int N_SUB = TILE_PIX / SUB_PIX;      // sub-blocks per tile
 constexpr int PROJ_WARPS = N_SUB * N_HALF;     // warp = (channel half, sub-block)
 constexpr int PROJ_THREADS = PROJ_WARPS * 32;
-constexpr int PROJ_CTAS_PER_SM = 512 / PROJ_THREADS;  // register-limited: 16 warps per SM
+// resident CTAs per SM: register-limited (16 warps per SM at 128 registers) unless overridden
+constexpr int PROJ_CTAS_PER_SM = MTN_CTAS_PER_SM ? MTN_CTAS_PER_SM : 512 / PROJ_THREADS;
 constexpr int PBATCH = 32;            // particle records staged per batch (= one per lane)
 static_assert(PBATCH == 32, "the batch is indexed by lane in several places");
 

@@ -188,8 +188,8 @@ struct ProjSmem {
 };
 
 // tile pixel (x, y) of pixel j of sub-block s
-__device__ __forceinline__ int sub_x(int s, int j) { return (s / SUBS_Y) * SUB + (j >> 2); }
-__device__ __forceinline__ int sub_y(int s, int j) { return (s % SUBS_Y) * SUB + (j & 3); }
+__device__ __forceinline__ int sub_x(int s, int j) { return (s / SUBS_Y) * SUB_X + j / SUB_Y; }
+__device__ __forceinline__ int sub_y(int s, int j) { return (s % SUBS_Y) * SUB_Y + j % SUB_Y; }
 
 // One thread stores its two channels of one pixel: out = (in + acc) / px_area
 // (martini.py:338, 364-366).  `nvalid` = how many of the lane's two channels exist.
@@ -225,8 +225,10 @@ __device__ __forceinline__ int owner_ordinal(uint32_t q0, uint32_t my_start, boo
 
 // COUNT = true is a diagnostic instantiation that additionally tallies the executed
 // algorithmic work (non-zero weight x non-zero spectrum terms, kernel integrals, edge erfs);
-// it is never the timed kernel.
-template <bool COUNT>
+// it is never the timed kernel.  KIND >= 0: every particle uses that (tabulated) SPH kernel, so
+// the weight evaluation is the bare table look-up with compile-time zone bounds; KIND = -1 is
+// the general case (adaptive kernel mixes, kernels evaluated through their closed forms).
+template <bool COUNT, int KIND>
 __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel(const ProjArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ProjSmem& sm = *reinterpret_cast<ProjSmem*>(smem_raw);
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
             const Record& r = sm.rec[buf][p];
             pp[u] = p;
             pix[u] = tpx * TILE_Y + tpy;
-            kind[u] = a.table.kind[r.kid];
+            kind[u] = KIND >= 0 ? KIND : a.table.kind[r.kid];
             // dij = pixcoords - ij (martini.py:276)
             dx[u] = __dsub_rn(r.px, (double)(x0 + tpx));
             dy[u] = __dsub_rn(r.py, (double)(y0 + tpy));
@@ -404,12 +406,12 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u)  // straight-line, both chains in flight together
-            tv[u] = wtab_eval(wtab_has(kind[u]) ? kind[u] : MTN_KERNEL_WENDLANDC2, R2[u]) * ih2[u];
+            tv[u] = wtab_eval(KIND >= 0 || wtab_has(kind[u]) ? kind[u] : MTN_KERNEL_WENDLANDC2, R2[u]) * ih2[u];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             if (ok[u]) {
               double w = tv[u];
-              if (!wtab_has(kind[u])) {  // kernels without a table: closed form
+              if (KIND < 0 && !wtab_has(kind[u])) {  // kernels without a table: closed form
                 const Record& r = sm.rec[buf][pp[u]];
                 w = kernel_weight_closed(kind[u], dx[u], dy[u], r.h, r.inv_h2, a.table.truncate[r.kid],
                                          a.table.norm[r.kid]);

@@ -5,13 +5,9 @@
 //
 //  * erf: Taylor coefficients about the centres of 1/16-wide intervals on [0, 6);
 //  * pixel-integrated SPH kernels W(R^2) for the kernels whose closed form costs a log and
-//    two square roots (Wendland C2, cubic spline): piecewise degree-9 polynomials in a
-//    variable chosen per region so that the function is analytic there --
-//       x = sqrt(s)        near the centre, on dyadic intervals [2^-k-1, 2^-k) split in 4
-//                          (the s^2 log s term of the closed forms is only C^3 at s = 0),
-//       x = sqrt(a^2 - s)  towards a knot or the edge of the support (the closed forms are
-//                          odd analytic functions of sqrt(1 - R^2) resp. sqrt(4 - R^2) there).
-//    ~40 straight-line instructions instead of ~145 branchy ones, and two evaluations
+//    two square roots (Wendland C2, cubic spline): piecewise degree-9 polynomials in R^2 on
+//    intervals refined towards the points where the closed form is not analytic (below).
+//    ~35 straight-line instructions instead of ~145 branchy ones, and two evaluations
 //    interleave (the projection kernel evaluates two pixels per lane).
 #pragma once
 
@@ -46,54 +42,55 @@ __device__ __forceinline__ double erf_tab(double t) {
 }
 
 // ------------------------------------------------------------------- kernel-integral tables
+// W(s), s = R^2 * scale, is tabulated directly in s -- no square root on the device.  The
+// closed forms are analytic in s except at a few points: s = 0 (an s^2 log s term) and the
+// ends of the kernel's pieces (half-integer powers of a^2 - s).  The support is cut into
+// zones, each with one such anchor point at one end, and a zone is covered by intervals
+// that shrink geometrically towards its anchor: with u = |s - anchor|, octave [2^e, 2^(e+1))
+// of u is split into 8 equal intervals, so (interval width) / (distance to the anchor) <=
+// 1/8 everywhere and a degree-9 interpolant converges like 33^-10; u < 2^-kmin is one "core"
+// interval, where the non-analytic term itself is below 1e-16 of W(0).  The interval index
+// is read off the exponent and top 3 mantissa bits of u, and the polynomial's variable is
+// u - (interval centre): u = |s - anchor| is exact in float64 for every zone below.
 constexpr int WT_DEG = 9;
-constexpr int WT_ROW = 12;          // c0..c9, interval centre, 1 / half-width
-constexpr int WT_MAX_REGIONS = 4;
+constexpr int WT_ROW = 12;          // c0..c9 (in t = u - centre), interval centre, unused
+constexpr int WT_MAX_ZONES = 4;
 constexpr int WT_KINDS = 6;         // indexed by MTN_KERNEL_*
-constexpr int WT_MAX_ROWS = 256;
-constexpr int WT_DYADIC_KMIN = 8;   // first dyadic interval is [0, 2^-8)
-constexpr int WT_DYADIC_SUB = 4;    // sub-intervals per octave
+constexpr int WT_MAX_ROWS = 2048;
+constexpr int WT_SUB_BITS = 3;      // 8 intervals per octave
 
-struct WRegion {
-  double s_max;   // region holds s <= s_max (regions ascending; s = R^2 * scale)
-  double a2;      // x = sqrt(sgn * s + a2): (sgn, a2) = (+1, 0) or (-1, a^2)
-  double sgn;
-  double x_lo;    // uniform regions: first interval starts here
-  double inv_w;   // uniform regions: 1 / interval width
-  int row0;       // first table row of the region
-  int n_int;      // number of intervals (rows)
-  int dyadic;     // 1: dyadic intervals in x, 0: uniform
+struct WZone {
+  double s_lo;    // the zone holds s_lo <= s < (next zone).s_lo; +inf for unused zones
+  double anchor;  // u = |s - anchor|
+  int off;        // row = clamp((hi32(u) >> 17) + off, row0, last)
+  int row0;       // the zone's core interval
+  int last;       // the zone's last row
   int pad;
 };
 
-__constant__ WRegion c_wreg[WT_KINDS][WT_MAX_REGIONS];
-__constant__ int c_wnreg[WT_KINDS];      // 0: no table for this kind (closed form is used)
+__constant__ WZone c_wzone[WT_KINDS][WT_MAX_ZONES];
+__constant__ int c_wnz[WT_KINDS];        // 0: no table for this kind (closed form is used)
 __constant__ double c_wscale[WT_KINDS];  // s = R^2 * scale (cubic spline: 4, its dij *= 2)
+__constant__ double c_wend[WT_KINDS];    // W = 0 for s >= c_wend (edge of the support)
 __device__ double g_wtab_rows[WT_MAX_ROWS * WT_ROW];
 
-__device__ __forceinline__ bool wtab_has(int kind) { return c_wnreg[kind] > 0; }
+__device__ __forceinline__ bool wtab_has(int kind) { return c_wnz[kind] > 0; }
 
 // Table value of the pixel-integrated kernel (normalisation included, 1/h^2 not) at
-// R2 = |d|^2 / h^2.  Straight-line code: selects, no divergent branches.
+// R2 = |d|^2 / h^2.  Straight-line code; with a compile-time `kind` the zone bounds fold
+// into constant-bank operands.
 __device__ __forceinline__ double wtab_eval(int kind, double R2) {
   const double s = R2 * c_wscale[kind];
-  const int nreg = c_wnreg[kind];
-  int r = 0;
+  int z = 0;
 #pragma unroll
-  for (int k = 0; k < WT_MAX_REGIONS - 1; ++k) r += (k + 1 < nreg && s > c_wreg[kind][k].s_max) ? 1 : 0;
-  const WRegion& reg = c_wreg[kind][r];
-  const double arg = fmax(fma(reg.sgn, s, reg.a2), 0.0);
-  const double x = arg > 0.0 ? arg * rsqrt(arg) : 0.0;
-  const int hi = __double2hiint(x);
-  const int idx_dy = x < 1.0 / (1 << WT_DYADIC_KMIN)
-                         ? 0
-                         : (((hi >> 20) - 1023 + WT_DYADIC_KMIN) * WT_DYADIC_SUB + ((hi >> 18) & 3) + 1);
-  const int idx_un = (int)((x - reg.x_lo) * reg.inv_w);
-  const int idx = min(max(reg.dyadic ? idx_dy : idx_un, 0), reg.n_int - 1);
-  const double2* row = reinterpret_cast<const double2*>(g_wtab_rows + (reg.row0 + idx) * WT_ROW);
+  for (int k = 1; k < WT_MAX_ZONES; ++k) z += s >= c_wzone[kind][k].s_lo ? 1 : 0;
+  const WZone& zn = c_wzone[kind][z];
+  const double u = fabs(s - zn.anchor);
+  const int idx = min(max((__double2hiint(u) >> (20 - WT_SUB_BITS)) + zn.off, zn.row0), zn.last);
+  const double2* row = reinterpret_cast<const double2*>(g_wtab_rows + idx * WT_ROW);
   const double2 cw = __ldg(row + 5), c89 = __ldg(row + 4), c67 = __ldg(row + 3), c45 = __ldg(row + 2),
                 c23 = __ldg(row + 1), c01 = __ldg(row);
-  const double t = (x - cw.x) * cw.y;
+  const double t = u - cw.x;
   double v = fma(c89.y, t, c89.x);
   v = fma(v, t, c67.y);
   v = fma(v, t, c67.x);
@@ -103,9 +100,7 @@ __device__ __forceinline__ double wtab_eval(int kind, double R2) {
   v = fma(v, t, c23.x);
   v = fma(v, t, c01.y);
   v = fma(v, t, c01.x);
-  // at and beyond the end of the last region: outside the kernel's support (the closed forms
-  // are exactly 0 at the edge itself)
-  return (r == nreg - 1 && s >= reg.s_max) ? 0.0 : v;
+  return s >= c_wend[kind] ? 0.0 : v;  // the closed forms are exactly 0 from the edge on
 }
 
 }  // namespace mtn

@@ -3,11 +3,13 @@
 // Every table entry is derived from the reference's own closed forms -- erf's derivatives,
 // and the `_kernel_integral` expressions of martini/sph_kernels.py (WendlandC2 :430-441,
 // CubicSpline :821-858) evaluated in long double -- by Chebyshev interpolation on each
-// interval; the fit is then checked against the closed form on a dense sample and the
-// worst error kept (mtn_table_error), so a bad table cannot go unnoticed.
+// interval of tables.cuh's zone layout; the fit is then checked against the closed form on
+// a dense sample and the worst error kept (mtn_table_error), so a bad table cannot go
+// unnoticed.
 #pragma once
 
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "tables.cuh"
@@ -17,25 +19,30 @@ namespace mtn {
 typedef long double ld;
 
 // ----------------------------------------------------------------------------- closed forms
+// Every closed form takes s as (anchor, ds) with s = anchor + ds, so that a^2 - s is formed as
+// (a^2 - anchor) - ds: near a zone anchor the distance to it keeps its full relative
+// precision (the cubic spline's sqrt(1 - s) term needs that down to 1 - s = 2^-53).
 static const ld PI_L = 3.14159265358979323846264338327950288L;
 
 // _WendlandC2Kernel._kernel_integral * h^2, s = R^2
-static ld F_wendland_c2(ld s) {
-  if (s >= 1.0L) return 0.0L;
+static ld F_wendland_c2(ld anchor, ld ds) {
+  const ld s = anchor + ds, om = (1.0L - anchor) - ds;  // 1 - s
+  if (om <= 0.0L) return 0.0L;
   const ld norm = 21.0L / 2.0L / PI_L;
   if (s <= 0.0L) return norm * 2.0L / 3.0L;
-  const ld A = sqrtl(1.0L - s);
+  const ld A = sqrtl(om);
   return norm * (5.0L * s * s * (0.5L * s + 3.0L) * logl((1.0L + A) / sqrtl(s)) +
                  A * (-27.0L / 2.0L * s * s - 14.0L / 3.0L * s + 2.0L / 3.0L));
 }
 
 // _CubicSplineKernel._kernel_integral * h^2, s = R2 of the reference (= 4 |d|^2 / h^2)
-static ld F_cubic_spline(ld s) {
+static ld F_cubic_spline(ld anchor, ld ds) {
+  const ld s = anchor + ds, om = (1.0L - anchor) - ds, fm = (4.0L - anchor) - ds;  // 1 - s, 4 - s
   const ld scale = 4.0L / 1.59689476201133L;
-  if (s > 4.0L) return 0.0L;
+  if (fm < 0.0L) return 0.0L;
   if (s <= 0.0L) return scale * (11.0L / 16.0L + 0.25L * 0.25L);
-  if (s <= 1.0L) {
-    const ld A = sqrtl(1.0L - s), B = sqrtl(4.0L - s);
+  if (om >= 0.0L) {
+    const ld A = sqrtl(om), B = sqrtl(fm);
     const ld I1 = A - 0.5L * A * A * A - 1.5L * s * A + 3.0L / 32.0L * A * (3.0L * s + 2.0L) +
                   9.0L / 32.0L * s * s * (logl(1.0L + A) - logl(sqrtl(s)));
     const ld I3 = -B * (3.0L * s + 56.0L) / 4.0L + A * (4.0L * s + 50.0L) / 8.0L -
@@ -43,7 +50,7 @@ static ld F_cubic_spline(ld s) {
                   2.0L * (3.0L * s + 4.0L) * (B - A) + 2.0L * (B * B * B - A * A * A);
     return scale * (I1 + 0.25L * I3);
   }
-  const ld B = sqrtl(4.0L - s);
+  const ld B = sqrtl(fm);
   const ld I2 = -B * (3.0L * s + 56.0L) / 4.0L -
                 3.0L / 8.0L * s * (s + 16.0L) * logl((2.0L + B) / sqrtl(s)) +
                 2.0L * (3.0L * s + 4.0L) * B + 2.0L * B * B * B;
@@ -51,14 +58,16 @@ static ld F_cubic_spline(ld s) {
 }
 
 // --------------------------------------------------------------------------------- fitting
-// Degree-WT_DEG Chebyshev interpolant of f on [a, b], returned as monomial coefficients in
-// t = (x - centre) / halfwidth.
+// Degree-WT_DEG Chebyshev interpolant of g(u) = f(anchor, dir * u) on u in [a, b], returned as
+// monomial coefficients in t = u - centre (unscaled: the half-widths are powers of two, so
+// dividing the coefficients of the scaled variable by hw^k is exact up to the final rounding
+// to double; the centre is a dyadic number of the interval's own magnitude, hence exact too).
 template <typename F>
-static void fit_interval(F f, ld a, ld b, double* row) {
+static void fit_interval(F f, ld anchor, ld dir, ld a, ld b, double* row) {
   const int n = WT_DEG + 1;
   ld fx[n], cheb[n];
   const ld c = 0.5L * (a + b), hw = 0.5L * (b - a);
-  for (int k = 0; k < n; ++k) fx[k] = f(c + hw * cosl(PI_L * (k + 0.5L) / n));
+  for (int k = 0; k < n; ++k) fx[k] = f(anchor, dir * (c + hw * cosl(PI_L * (k + 0.5L) / n)));
   for (int j = 0; j < n; ++j) {
     ld sum = 0.0L;
     for (int k = 0; k < n; ++k) sum += fx[k] * cosl(PI_L * j * (k + 0.5L) / n);
@@ -79,102 +88,107 @@ static void fit_interval(F f, ld a, ld b, double* row) {
       Tcur[i] = Tnext[i];
     }
   }
-  for (int i = 0; i < n; ++i) row[i] = (double)mono[i];
+  ld scale = 1.0L;
+  for (int i = 0; i < n; ++i) {
+    row[i] = (double)(mono[i] * scale);
+    scale /= hw;
+  }
   row[WT_DEG + 1] = (double)c;
-  row[WT_DEG + 2] = (double)(1.0L / hw);
+  row[WT_DEG + 2] = 0.0;
 }
 
-struct RegionSpec {
-  ld s_max;     // region holds s <= s_max
-  int var;      // 0: x = sqrt(s), 1: x = sqrt(a2 - s)
-  ld a2;
-  int dyadic;   // 1: dyadic intervals on [0, x_hi), 0: n uniform intervals on [x_lo, x_hi]
-  ld x_lo, x_hi;
-  int n;
+// One zone of the support: s_lo <= s < s_hi, intervals refined towards `anchor` (one of the
+// two ends); u < 2^-kmin is the core interval.
+struct ZoneSpec {
+  ld s_lo, s_hi, anchor;
+  int kmin;
 };
 
 struct HostTables {
-  WRegion reg[WT_KINDS][WT_MAX_REGIONS];
-  int nreg[WT_KINDS];
+  WZone zone[WT_KINDS][WT_MAX_ZONES];
+  int nz[WT_KINDS];
   double scale[WT_KINDS];
+  double end[WT_KINDS];
   std::vector<double> rows;
   double max_err[WT_KINDS];  // worst |table - closed form| / F(0) on a dense sample
 };
 
+static int hi32(double x) {
+  long long b;
+  memcpy(&b, &x, sizeof(b));
+  return (int)(b >> 32);
+}
+
 // double-precision replica of the device evaluator (tables.cuh: wtab_eval)
 static double host_wtab_eval(const HostTables& T, int kind, double R2) {
   const double s = R2 * T.scale[kind];
-  const int nreg = T.nreg[kind];
-  int r = 0;
-  for (int k = 0; k < WT_MAX_REGIONS - 1; ++k) r += (k + 1 < nreg && s > T.reg[kind][k].s_max) ? 1 : 0;
-  const WRegion& reg = T.reg[kind][r];
-  if (r == nreg - 1 && s >= reg.s_max) return 0.0;
-  const double arg = std::fmax(std::fma(reg.sgn, s, reg.a2), 0.0);
-  const double x = std::sqrt(arg);
-  int idx;
-  if (reg.dyadic) {
-    int e;
-    const double m = std::frexp(x, &e);  // x = m 2^e, m in [0.5, 1)
-    idx = x < 1.0 / (1 << WT_DYADIC_KMIN)
-              ? 0
-              : ((e - 1 + WT_DYADIC_KMIN) * WT_DYADIC_SUB + ((int)(m * 8.0) & 3) + 1);
-  } else {
-    idx = (int)((x - reg.x_lo) * reg.inv_w);
-  }
-  idx = std::min(std::max(idx, 0), reg.n_int - 1);
-  const double* row = T.rows.data() + (size_t)(reg.row0 + idx) * WT_ROW;
-  const double t = (x - row[10]) * row[11];
+  int z = 0;
+  for (int k = 1; k < WT_MAX_ZONES; ++k) z += s >= T.zone[kind][k].s_lo ? 1 : 0;
+  const WZone& zn = T.zone[kind][z];
+  if (s >= T.end[kind]) return 0.0;
+  const double u = std::fabs(s - zn.anchor);
+  const int idx = std::min(std::max((hi32(u) >> (20 - WT_SUB_BITS)) + zn.off, zn.row0), zn.last);
+  const double* row = T.rows.data() + (size_t)idx * WT_ROW;
+  const double t = u - row[10];
   double v = row[9];
   for (int k = 8; k >= 0; --k) v = std::fma(v, t, row[k]);
   return v;
 }
 
 template <typename F>
-static void build_kind(HostTables& T, int kind, double scale, F f, const std::vector<RegionSpec>& specs) {
+static void build_kind(HostTables& T, int kind, double scale, F f, const std::vector<ZoneSpec>& specs) {
+  const int nsub = 1 << WT_SUB_BITS;
   T.scale[kind] = scale;
-  T.nreg[kind] = (int)specs.size();
-  for (size_t r = 0; r < specs.size(); ++r) {
-    const RegionSpec& sp = specs[r];
-    WRegion& reg = T.reg[kind][r];
-    reg.s_max = (double)sp.s_max;
-    reg.a2 = (double)sp.a2;
-    reg.sgn = sp.var == 0 ? 1.0 : -1.0;
-    reg.dyadic = sp.dyadic;
-    reg.row0 = (int)(T.rows.size() / WT_ROW);
-    reg.pad = 0;
-    auto g = [&](ld x) { return f(sp.var == 0 ? x * x : sp.a2 - x * x); };
-    std::vector<std::pair<ld, ld>> ivals;
-    if (sp.dyadic) {
-      ivals.push_back({0.0L, ldexpl(1.0L, -WT_DYADIC_KMIN)});
-      for (int k = WT_DYADIC_KMIN; k >= 1; --k) {
-        const ld lo = ldexpl(1.0L, -k), w = lo / WT_DYADIC_SUB;
-        for (int j = 0; j < WT_DYADIC_SUB; ++j)
-          if (lo + j * w < sp.x_hi) ivals.push_back({lo + j * w, lo + (j + 1) * w});
-      }
-      reg.x_lo = 0.0;
-      reg.inv_w = 0.0;
-    } else {
-      const ld w = (sp.x_hi - sp.x_lo) / sp.n;
-      for (int j = 0; j < sp.n; ++j) ivals.push_back({sp.x_lo + j * w, sp.x_lo + (j + 1) * w});
-      reg.x_lo = (double)sp.x_lo;
-      reg.inv_w = (double)(1.0L / w);
-    }
-    reg.n_int = (int)ivals.size();
-    for (auto& iv : ivals) {
+  T.nz[kind] = (int)specs.size();
+  T.end[kind] = (double)specs.back().s_hi;
+  for (size_t z = 0; z < specs.size(); ++z) {
+    const ZoneSpec& sp = specs[z];
+    WZone& zn = T.zone[kind][z];
+    const bool up = sp.anchor <= sp.s_lo;  // u = s - anchor grows with s
+    const ld u_max = up ? sp.s_hi - sp.anchor : sp.anchor - sp.s_lo;
+    zn.s_lo = (double)sp.s_lo;
+    zn.anchor = (double)sp.anchor;
+    zn.row0 = (int)(T.rows.size() / WT_ROW);
+    zn.off = zn.row0 + 1 - ((1023 - sp.kmin) << WT_SUB_BITS);
+    zn.pad = 0;
+    auto add = [&](ld u0, ld u1) {  // interval [u0, u1) of u
       T.rows.resize(T.rows.size() + WT_ROW);
-      fit_interval(g, iv.first, iv.second, T.rows.data() + T.rows.size() - WT_ROW);
+      fit_interval(f, sp.anchor, up ? 1.0L : -1.0L, u0, u1, T.rows.data() + T.rows.size() - WT_ROW);
+    };
+    add(0.0L, ldexpl(1.0L, -sp.kmin));
+    for (int e = -sp.kmin;; ++e) {
+      const ld lo = ldexpl(1.0L, e), w = lo / nsub;
+      bool more = true;
+      for (int j = 0; j < nsub && more; ++j) {
+        if (lo + j * w > u_max) more = false;  // u == u_max itself still needs its interval
+        else add(lo + j * w, lo + (j + 1) * w);
+      }
+      if (!more) break;
     }
+    zn.last = (int)(T.rows.size() / WT_ROW) - 1;
   }
-  // verify on a dense sample of s over the whole support
-  const ld f0 = f(0.0L);
-  const ld s_end = specs.back().s_max;
+  for (size_t z = specs.size(); z < (size_t)WT_MAX_ZONES; ++z)
+    T.zone[kind][z] = WZone{HUGE_VAL, 0.0, 0, 0, 0, 0};
+  // verify on a dense sample of s: uniform over the support, and geometrically approaching
+  // every zone anchor from inside the zone
+  const ld f0 = f(0.0L, 0.0L);
   double worst = 0.0;
-  for (int i = 0; i <= 20000; ++i) {
-    const ld u = (ld)i / 20000.0L;
-    const ld s = (i % 2 ? u : u * u * u) * s_end * (1.0L - 1e-12L);  // dense near 0 too
-    const double got = host_wtab_eval(T, kind, (double)(s / scale));
-    const double err = (double)(fabsl((ld)got - f((ld)(double)(s / scale) * scale)) / f0);
+  auto check = [&](ld anchor, ld s) {  // the truth is taken at the double the device sees
+    const double R2 = (double)(s / scale);
+    const double sd = R2 * scale;
+    const double got = host_wtab_eval(T, kind, R2);
+    const double err = (double)(fabsl((ld)got - f(anchor, (ld)sd - anchor)) / f0);
     if (err > worst) worst = err;
+  };
+  const ld s_end = specs.back().s_hi;
+  for (int i = 0; i <= 40000; ++i) check(0.0L, (ld)i / 40000.0L * s_end * (1.0L - 1e-12L));
+  for (const ZoneSpec& sp : specs) {
+    const bool up = sp.anchor <= sp.s_lo;
+    const ld u_max = up ? sp.s_hi - sp.anchor : sp.anchor - sp.s_lo;
+    for (int i = 0; i < 6000; ++i) {
+      const ld u = u_max * powl(2.0L, -(ld)i / 100.0L);  // 60 octaves, 100 samples each
+      check(sp.anchor, up ? sp.anchor + u : sp.anchor - u);
+    }
   }
   T.max_err[kind] = worst;
 }
@@ -182,20 +196,22 @@ static void build_kind(HostTables& T, int kind, double scale, F f, const std::ve
 static HostTables build_kernel_tables() {
   HostTables T;
   for (int k = 0; k < WT_KINDS; ++k) {
-    T.nreg[k] = 0;
+    T.nz[k] = 0;
     T.scale[k] = 1.0;
+    T.end[k] = 0.0;
     T.max_err[k] = 0.0;
-    for (int r = 0; r < WT_MAX_REGIONS; ++r) T.reg[k][r] = WRegion{0, 0, 1, 0, 0, 0, 1, 0, 0};
+    for (int z = 0; z < WT_MAX_ZONES; ++z) T.zone[k][z] = WZone{HUGE_VAL, 0.0, 0, 0, 0, 0};
   }
-  const ld x_in = 0.625L;  // inner (dyadic) regions reach x = 0.625
+  // Wendland C2: s^2 log s at 0, (1 - s)^(9/2) at the edge
   build_kind(T, MTN_KERNEL_WENDLANDC2, 1.0, F_wendland_c2,
-             {{x_in * x_in, 0, 0.0L, 1, 0.0L, x_in, 0},
-              {1.0L, 1, 1.0L, 0, 0.0L, sqrtl(1.0L - x_in * x_in), 24}});
+             {{0.0L, 0.5L, 0.0L, 28}, {0.5L, 1.0L, 1.0L, 12}});
+  // cubic spline (s = 4 |d|^2 / h^2): s^2 log s at 0; below the knot s = 1 the reference's
+  // expression carries a small (~2e-3 W(0)) sqrt(1 - s) term, so that zone is refined down to
+  // u = 2^-54, below the smallest non-zero 1 - s a double s can give (rows that are
+  // practically never touched); analytic above the knot;
+  // (4 - s)^(7/2) at the edge
   build_kind(T, MTN_KERNEL_CUBICSPLINE, 4.0, F_cubic_spline,
-             {{x_in * x_in, 0, 0.0L, 1, 0.0L, x_in, 0},
-              {1.0L, 1, 1.0L, 0, 0.0L, sqrtl(1.0L - x_in * x_in), 24},
-              {2.56L, 0, 0.0L, 0, 1.0L, 1.6L, 32},
-              {4.0L, 1, 4.0L, 0, 0.0L, 1.2L, 48}});
+             {{0.0L, 0.5L, 0.0L, 28}, {0.5L, 1.0L, 1.0L, 54}, {1.0L, 2.5L, 1.0L, 6}, {2.5L, 4.0L, 4.0L, 16}});
   return T;
 }
 
