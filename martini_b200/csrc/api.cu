@@ -7,6 +7,7 @@
 #include "kernel_integrals.cuh"
 #include "plan.cuh"
 #include "project.cuh"
+#include "project_ws.cuh"
 #include "scan.cuh"
 #include "sort.cuh"
 #include "tables_host.hpp"
@@ -92,31 +93,53 @@ static int ensure_tables() {
   return MTN_OK;
 }
 
-// One instantiation of the projection kernel per (diagnostic counting, uniform kernel kind).
-template <bool COUNT, int KIND>
-static int launch_project_as(const ProjArgs& a, unsigned grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    MTN_CUDA(cudaFuncSetAttribute(project_kernel<COUNT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(ProjSmem)));
-    attr_set = true;
+// The projection kernel is project.cuh's; MTN_PROJECT=ws selects the warp-specialised variant
+// of project_ws.cuh instead (experimental: correct, but measured slower -- profiles/README.md).
+static bool use_classic_project() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTN_PROJECT");
+    v = (e && strcmp(e, "ws") == 0) ? 0 : 1;
   }
-  project_kernel<COUNT, KIND><<<grid, PROJ_THREADS, sizeof(ProjSmem), st>>>(a);
+  return v == 1;
+}
+
+// One instantiation per (diagnostic counting, uniform kernel kind).
+template <bool COUNT, int KIND>
+static int launch_project_as(const ProjArgs& a, int64_t max_items, cudaStream_t st) {
+  static bool attr_set[2] = {false, false};
+  const bool classic = use_classic_project();
+  if (!attr_set[classic]) {
+    if (classic)
+      MTN_CUDA(cudaFuncSetAttribute(project_kernel<COUNT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(ProjSmem)));
+    else
+      MTN_CUDA(cudaFuncSetAttribute(project_ws_kernel<COUNT, KIND>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSmem)));
+    attr_set[classic] = true;
+  }
+  if (classic) {
+    const unsigned grid = (unsigned)std::min<int64_t>(max_items, (int64_t)sm_count() * PROJ_CTAS_PER_SM);
+    project_kernel<COUNT, KIND><<<grid, PROJ_THREADS, sizeof(ProjSmem), st>>>(a);
+  } else {
+    const unsigned grid = (unsigned)std::min<int64_t>(max_items, (int64_t)sm_count() * WS_CTAS_PER_SM);
+    project_ws_kernel<COUNT, KIND><<<grid, WS_THREADS, sizeof(WsSmem), st>>>(a);
+  }
   return MTN_OK;
 }
 
 template <bool COUNT>
-static int launch_project_count(const ProjArgs& a, int uniform_kind, unsigned grid, cudaStream_t st) {
+static int launch_project_count(const ProjArgs& a, int uniform_kind, int64_t max_items, cudaStream_t st) {
   switch (uniform_kind) {
-    case MTN_KERNEL_WENDLANDC2: return launch_project_as<COUNT, MTN_KERNEL_WENDLANDC2>(a, grid, st);
-    case MTN_KERNEL_CUBICSPLINE: return launch_project_as<COUNT, MTN_KERNEL_CUBICSPLINE>(a, grid, st);
-    default: return launch_project_as<COUNT, -1>(a, grid, st);
+    case MTN_KERNEL_WENDLANDC2: return launch_project_as<COUNT, MTN_KERNEL_WENDLANDC2>(a, max_items, st);
+    case MTN_KERNEL_CUBICSPLINE: return launch_project_as<COUNT, MTN_KERNEL_CUBICSPLINE>(a, max_items, st);
+    default: return launch_project_as<COUNT, -1>(a, max_items, st);
   }
 }
 
-static int launch_project(const ProjArgs& a, int uniform_kind, bool count, unsigned grid, cudaStream_t st) {
-  return count ? launch_project_count<true>(a, uniform_kind, grid, st)
-               : launch_project_count<false>(a, uniform_kind, grid, st);
+static int launch_project(const ProjArgs& a, int uniform_kind, bool count, int64_t max_items, cudaStream_t st) {
+  return count ? launch_project_count<true>(a, uniform_kind, max_items, st)
+               : launch_project_count<false>(a, uniform_kind, max_items, st);
 }
 
 static int make_geo(const MtnCube* c, Geo* g, int edges_increasing) {
@@ -520,16 +543,15 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
     a.slab = cube->slab;
     a.partials = ws.partials;
     a.px_area = px_area;
+    a.inv_px_area = 1.0 / px_area;
     a.zeroed = zeroed;
     a.exec_counts = (unsigned long long*)(ws.scalars + 8);  // zeroed with the scalars
     // every particle on one tabulated SPH kernel: the specialised instantiation
     int uniform_kind = t.kind[0];
     for (int k = 1; k < t.n; ++k)
       if (t.kind[k] != uniform_kind) uniform_kind = -1;
-    const unsigned pgrid =
-        (unsigned)std::min<int64_t>(ws.max_items, (int64_t)sm_count() * PROJ_CTAS_PER_SM);
     mark(3, st);
-    if (int rc = launch_project(a, uniform_kind, g_count_exec != 0, pgrid, st)) return rc;
+    if (int rc = launch_project(a, uniform_kind, g_count_exec != 0, ws.max_items, st)) return rc;
     MTN_LAUNCH_CHECK();
     mark(4, st);
     reduce_partials_kernel<<<dim3((unsigned)ws.max_multi, SUB_PIX), PROJ_THREADS, 0, st>>>(

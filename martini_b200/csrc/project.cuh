@@ -161,6 +161,7 @@ struct ProjArgs {
   double* slab;
   double* partials;  // [slot][TILE_PIX][CB]
   double px_area;    // px_size_arcsec^2
+  double inv_px_area;  // RN(1 / px_area)
   int zeroed;        // MTN_CUBE_ZEROED
   unsigned long long* exec_counts;  // COUNT instantiation only: [updates, weights, erfs]
 };

@@ -50,7 +50,7 @@ def main():
     rows = list(csv.reader(io.StringIO(out)))
     hdr = next(r for r in rows if len(r) > 3 and r[1] == "Source")
     body = [dict(zip(hdr, r)) for r in rows[rows.index(hdr) + 1:] if len(r) == len(hdr)]
-    table = line_table(lib, "project_kernelILb0")
+    table = line_table(lib, sys.argv[4] if len(sys.argv) > 4 else "project_kernelILb0")
     assert len(table) == len(body), (len(table), len(body))
     agg = collections.OrderedDict()
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
