@@ -129,17 +129,17 @@ static int launch_project_as(const ProjArgs& a, int64_t max_items, cudaStream_t 
 }
 
 template <bool COUNT>
-static int launch_project_count(const ProjArgs& a, int uniform_kind, int64_t max_items, cudaStream_t st) {
-  switch (uniform_kind) {
+static int launch_project_count(const ProjArgs& a, int primary_kind, int64_t max_items, cudaStream_t st) {
+  switch (primary_kind) {
     case MTN_KERNEL_WENDLANDC2: return launch_project_as<COUNT, MTN_KERNEL_WENDLANDC2>(a, max_items, st);
     case MTN_KERNEL_CUBICSPLINE: return launch_project_as<COUNT, MTN_KERNEL_CUBICSPLINE>(a, max_items, st);
     default: return launch_project_as<COUNT, -1>(a, max_items, st);
   }
 }
 
-static int launch_project(const ProjArgs& a, int uniform_kind, bool count, int64_t max_items, cudaStream_t st) {
-  return count ? launch_project_count<true>(a, uniform_kind, max_items, st)
-               : launch_project_count<false>(a, uniform_kind, max_items, st);
+static int launch_project(const ProjArgs& a, int primary_kind, bool count, int64_t max_items, cudaStream_t st) {
+  return count ? launch_project_count<true>(a, primary_kind, max_items, st)
+               : launch_project_count<false>(a, primary_kind, max_items, st);
 }
 
 static int make_geo(const MtnCube* c, Geo* g, int edges_increasing) {
@@ -546,12 +546,9 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
     a.inv_px_area = 1.0 / px_area;
     a.zeroed = zeroed;
     a.exec_counts = (unsigned long long*)(ws.scalars + 8);  // zeroed with the scalars
-    // every particle on one tabulated SPH kernel: the specialised instantiation
-    int uniform_kind = t.kind[0];
-    for (int k = 1; k < t.n; ++k)
-      if (t.kind[k] != uniform_kind) uniform_kind = -1;
+    // the instantiation specialised on the kind of table entry 0 (if that kind is tabulated)
     mark(3, st);
-    if (int rc = launch_project(a, uniform_kind, g_count_exec != 0, ws.max_items, st)) return rc;
+    if (int rc = launch_project(a, t.kind[0], g_count_exec != 0, ws.max_items, st)) return rc;
     MTN_LAUNCH_CHECK();
     mark(4, st);
     reduce_partials_kernel<<<dim3((unsigned)ws.max_multi, SUB_PIX), PROJ_THREADS, 0, st>>>(

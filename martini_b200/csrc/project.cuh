@@ -226,9 +226,10 @@ __device__ __forceinline__ int owner_ordinal(uint32_t q0, uint32_t my_start, boo
 
 // COUNT = true is a diagnostic instantiation that additionally tallies the executed
 // algorithmic work (non-zero weight x non-zero spectrum terms, kernel integrals, edge erfs);
-// it is never the timed kernel.  KIND >= 0: every particle uses that (tabulated) SPH kernel, so
-// the weight evaluation is the bare table look-up with compile-time zone bounds; KIND = -1 is
-// the general case (adaptive kernel mixes, kernels evaluated through their closed forms).
+// it is never the timed kernel.  KIND >= 0: entry 0 of the kernel table -- the SPH kernel proper
+// of the reference's adaptive kernels; the other entries are its small-h fallbacks -- is that
+// tabulated kind, so the weight evaluation is the bare table look-up with compile-time zone
+// bounds and only the lanes on another entry take the closed forms; KIND = -1: general case.
 template <bool COUNT, int KIND>
 __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel(const ProjArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
           const int ord[2] = {owner_ordinal(q0, my_start, my_nonempty, lane),
                               owner_ordinal(q0 + 32, my_start, my_nonempty, lane)};
           bool ok[2];
-          int pp[2], pix[2], kind[2];
+          int pp[2], pix[2], kind[2], kid[2];
           double dx[2], dy[2], R2[2], ih2[2], tv[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -398,7 +399,8 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
             const Record& r = sm.rec[buf][p];
             pp[u] = p;
             pix[u] = tpx * TILE_Y + tpy;
-            kind[u] = KIND >= 0 ? KIND : a.table.kind[r.kid];
+            kid[u] = r.kid;
+            kind[u] = (KIND >= 0 && kid[u] == 0) ? KIND : a.table.kind[kid[u]];
             // dij = pixcoords - ij (martini.py:276)
             dx[u] = __dsub_rn(r.px, (double)(x0 + tpx));
             dy[u] = __dsub_rn(r.py, (double)(y0 + tpy));
@@ -407,12 +409,13 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u)  // straight-line, both chains in flight together
-            tv[u] = wtab_eval(KIND >= 0 || wtab_has(kind[u]) ? kind[u] : MTN_KERNEL_WENDLANDC2, R2[u]) * ih2[u];
+            tv[u] = wtab_eval(KIND >= 0 ? KIND : (wtab_has(kind[u]) ? kind[u] : MTN_KERNEL_WENDLANDC2), R2[u]) * ih2[u];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             if (ok[u]) {
               double w = tv[u];
-              if (KIND < 0 && !wtab_has(kind[u])) {  // kernels without a table: closed form
+              // closed form: kernels without a table; with KIND, every entry but the first
+              if (KIND >= 0 ? kid[u] != 0 : !wtab_has(kind[u])) {
                 const Record& r = sm.rec[buf][pp[u]];
                 w = kernel_weight_closed(kind[u], dx[u], dy[u], r.h, r.inv_h2, a.table.truncate[r.kid],
                                          a.table.norm[r.kid]);

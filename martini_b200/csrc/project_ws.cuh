@@ -287,7 +287,7 @@ __device__ __forceinline__ void ws_producer(const ProjArgs& a, WsSmem& sm, const
           const int ord[2] = {owner_ordinal(q0, my_start, my_nonempty, lane),
                               owner_ordinal(q0 + 32, my_start, my_nonempty, lane)};
           bool ok[2];
-          int pp[2], pix[2], kind[2];
+          int pp[2], pix[2], kind[2], kid[2];
           double dx[2], dy[2], R2[2], ih2[2], tv[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -301,7 +301,8 @@ __device__ __forceinline__ void ws_producer(const ProjArgs& a, WsSmem& sm, const
             const Record& r = sm.rec[buf][p];
             pp[u] = p;
             pix[u] = tpx * TILE_Y + tpy;
-            kind[u] = KIND >= 0 ? KIND : a.table.kind[r.kid];
+            kid[u] = r.kid;
+            kind[u] = (KIND >= 0 && kid[u] == 0) ? KIND : a.table.kind[kid[u]];
             // dij = pixcoords - ij (martini.py:276)
             dx[u] = __dsub_rn(r.px, (double)(x0 + tpx));
             dy[u] = __dsub_rn(r.py, (double)(y0 + tpy));
@@ -310,12 +311,13 @@ __device__ __forceinline__ void ws_producer(const ProjArgs& a, WsSmem& sm, const
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u)
-            tv[u] = wtab_eval(KIND >= 0 || wtab_has(kind[u]) ? kind[u] : MTN_KERNEL_WENDLANDC2, R2[u]) * ih2[u];
+            tv[u] = wtab_eval(KIND >= 0 ? KIND : (wtab_has(kind[u]) ? kind[u] : MTN_KERNEL_WENDLANDC2), R2[u]) * ih2[u];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             if (ok[u]) {
               double w = tv[u];
-              if (KIND < 0 && !wtab_has(kind[u])) {  // kernels without a table: closed form
+              // closed form: kernels without a table; with KIND, every entry but the first
+              if (KIND >= 0 ? kid[u] != 0 : !wtab_has(kind[u])) {
                 const Record& r = sm.rec[buf][pp[u]];
                 w = kernel_weight_closed(kind[u], dx[u], dy[u], r.h, r.inv_h2, a.table.truncate[r.kid],
                                          a.table.norm[r.kid]);
@@ -354,7 +356,7 @@ __device__ __forceinline__ void ws_producer(const ProjArgs& a, WsSmem& sm, const
             pp[u] = p;
             ee[u] = e;
             t[u] = (sm.edge[e] - r.v) * (sgn * r.inv_s);
-            scale[u] = r.amp * sm.inv_dv[e];
+            scale[u] = r.amp * sm.inv_dv[min(e, CB - 1)];
           }
           if (gaussian_line) {
 #pragma unroll
