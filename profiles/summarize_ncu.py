@@ -36,6 +36,11 @@ KEYS = (
     "launch__occupancy_limit_registers",
     "launch__occupancy_limit_shared_mem",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct",
     "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum",
     "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
     "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
