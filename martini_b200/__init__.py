@@ -12,10 +12,13 @@ pixel integrals, per-pixel accumulation) as hand-written sm_100a CUDA kernels be
 __version__ = "0.1.0"
 
 from . import sph_kernels, spectral_models  # noqa: F401
+from .beams import GaussianBeam  # noqa: F401
 from .datacube import DataCube  # noqa: F401
 from .engine import Engine, KernelTable  # noqa: F401
 from .martini import GlobalProfile, Martini, demo  # noqa: F401
+from .noise import GaussianNoise  # noqa: F401
 from .sources import L_coords, PixelSource, SPHSource, demo_source  # noqa: F401
 
 __all__ = ["Martini", "GlobalProfile", "DataCube", "SPHSource", "PixelSource", "L_coords",
-           "demo", "demo_source", "Engine", "KernelTable", "sph_kernels", "spectral_models"]
+           "demo", "demo_source", "Engine", "KernelTable", "sph_kernels", "spectral_models",
+           "GaussianBeam", "GaussianNoise"]

@@ -39,11 +39,49 @@ class DataCube:
         self.ra = float(_value(ra, "deg"))
         self.dec = float(_value(dec, "deg"))
         self.padx = self.pady = 0
-        self._array = np.zeros((self.n_px_x, self.n_px_y, self.n_channels))
+        self._dev = None  # device copy (torch, 3-D); authoritative while _host is None
+        self._host = np.zeros((self.n_px_x, self.n_px_y, self.n_channels))
         if stokes_axis:
-            self._array = self._array[..., np.newaxis]
+            self._host = self._host[..., np.newaxis]
         #: "Jy/pix2" until insert_source_in_cube converts to "Jy/arcsec2" (martini.py:364-366)
         self.array_unit = "Jy/pix2"
+
+    # ------------------------------------------------------------------ array residency
+    # Between insert_source_in_cube, add_noise and convolve_beam the cube stays on the GPU; the
+    # host array of the reference (`DataCube._array`) is materialised on first access.  A
+    # host access also drops the device copy, because the caller may modify the array in
+    # place (the reference's own tests do).
+    @property
+    def _array(self):
+        if self._host is None:
+            a = self._dev.cpu().numpy()
+            self._host = a[..., np.newaxis] if self.stokes_axis else a
+        self._dev = None
+        return self._host
+
+    @_array.setter
+    def _array(self, value):
+        self._host = value
+        self._dev = None
+
+    def _device_array(self, engine):
+        """The cube as a 3-D device tensor (uploaded from the host copy if needed)."""
+        if self._dev is None:
+            h = self._host
+            self._dev = engine.to_device(np.ascontiguousarray(h.reshape(h.shape[:3])))
+        return self._dev
+
+    def _set_device_array(self, tensor):
+        """Make ``tensor`` (3-D, on the device) the cube's contents; the host copy is stale."""
+        self._dev = tensor
+        self._host = None
+
+    @property
+    def _array_is_zero(self):
+        """True if the cube holds only zeros (checked where the data lives)."""
+        if self._host is None:
+            return not bool(self._dev.any())
+        return not self._host.any()
 
     # ------------------------------------------------------------------ channels
     @property

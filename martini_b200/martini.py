@@ -117,11 +117,12 @@ class _BaseMartini:
             raise RuntimeError("The data cube already holds an inserted source; call reset() first.")
         self.sph_kernel._confirm_validation(noraise=skip_validation, quiet=self.quiet)
         eng, d = self.engine, self._dev
-        arr = dc._array
-        shape3 = arr.shape[:3]
-        zero = not arr.any()
-        cube = (torch.zeros(shape3, dtype=torch.float64, device=eng.device) if zero
-                else eng.to_device(np.ascontiguousarray(arr.reshape(shape3))))
+        zero = dc._array_is_zero
+        if zero:
+            nx, ny = dc.n_px_x + 2 * dc.padx, dc.n_px_y + 2 * dc.pady
+            cube = torch.zeros((nx, ny, dc.n_channels), dtype=torch.float64, device=eng.device)
+        else:
+            cube = dc._device_array(eng)
         edges = eng.to_device(dc.velocity_channel_edges)
         gauss = self._spectrum == L.SPECTRUM_GAUSSIAN
         plan = eng.insert(px=d["px"], py=d["py"], h_eff=d["h_eff"], sm_range=d["sm_range"], v=d["v"],
@@ -129,7 +130,7 @@ class _BaseMartini:
                           mHI=d["mHI"], D=d["D"], accept=d["accept"], table=self._table,
                           spectrum=self._spectrum, edges=edges, cube=cube,
                           px_size_arcsec=dc.px_size, zeroed=zero)
-        dc._array = cube.cpu().numpy().reshape(arr.shape)
+        dc._set_device_array(cube)  # stays on the GPU until someone reads datacube._array
         dc.array_unit = "Jy/arcsec2"
         self.last_plan = plan
         if (quiet is None and not self.quiet) or (quiet is not None and not quiet):
@@ -180,6 +181,35 @@ class Martini(_BaseMartini):
         self._insert_source_in_cube(skip_validation=skip_validation, progressbar=progressbar, ncpu=ncpu)
 
 
+    def add_noise(self):
+        """Insert noise into the data cube (martini.py:903-937).  The realisation is the
+        reference's (``noise.generate``: numpy Generator, same seed -> same numbers); it is
+        converted from Jy/beam to the cube's current unit and added on the device."""
+        from warnings import warn
+
+        if self.noise is None:
+            warn("Skipping noise, no noise object provided to Martini.")
+            return
+        if self.beam is None:
+            warn("Skipping noise, no beam object (required to estimate post-convolution"
+                 " noise level) provided to Martini.")
+            return
+        dc, eng = self._datacube, self.engine
+        if dc.array_unit not in ("Jy/pix2", "Jy/arcsec2"):
+            raise RuntimeError("add_noise expects a cube in Jy/pix2 or Jy/arcsec2 (before convolve_beam).")
+        noise = self.noise.generate(dc, self.beam)  # Jy/beam, shape of datacube._array
+        # Jy/beam -> Jy/arcsec2 (beam_angular_area) -> the cube's unit (arcsec2_to_pix)
+        factor = 1.0 / self.beam.area * (dc.px_size**2 if dc.array_unit == "Jy/pix2" else 1.0)
+        cube = dc._device_array(eng)
+        noise_dev = eng.to_device(np.ascontiguousarray(noise.reshape(noise.shape[:3])))
+        cube.add_(noise_dev, alpha=factor)
+        dc._set_device_array(cube)
+        if not self.quiet:
+            print("Noise added.",
+                  f"  Noise cube RMS: {float(noise_dev.std(correction=0)) * factor:.2e} (before beam convolution).",
+                  "  Data cube RMS after noise addition (before beam convolution): "
+                  f"{float(cube.std(correction=0)):.2e}", sep="\n")
+
     def convolve_beam(self):
         """Convolve the cube with the beam, drop the pad, convert to Jy/beam
         (martini.py:863-901), on the GPU (``mtn_convolve_beam``)."""
@@ -198,11 +228,9 @@ class Martini(_BaseMartini):
         if dc.array_unit != "Jy/arcsec2":
             raise RuntimeError("convolve_beam expects a cube in Jy/arcsec2: insert the source first.")
         eng = self.engine
-        arr = dc._array
-        cube = eng.to_device(np.ascontiguousarray(arr.reshape(arr.shape[:3])))
-        out = eng.convolve_beam(cube, self.beam.kernel, scale=self.beam.area)  # x area: -> Jy/beam
-        dc._array = out.cpu().numpy().reshape(arr.shape)
-        dc.drop_pad()
+        out = eng.convolve_beam(dc._device_array(eng), self.beam.kernel, scale=self.beam.area)  # x area: -> Jy/beam
+        dc._set_device_array(out)  # the convolution returns the unpadded cube (drop_pad, :899)
+        dc.padx = dc.pady = 0
         dc.array_unit = "Jy/beam"
         if not self.quiet:
             nz = dc._array[dc._array > 0]

@@ -276,7 +276,9 @@ def gen_prune():
     np.savez_compressed(os.path.join(HERE, "prune.npz"), **out)
 
 
-def gen_insert():
+def gen_insert(dtype=np.float64, prefix="insert", only=None):
+    """``dtype`` is the spectral model's ``spec_dtype``; the float32 fixtures (prefix
+    "insertf32", two cases) pin what the reference produces in its float32 mode."""
     nx, ny, nc, pad = 9, 7, 12, 2
     X, Y = nx + 2 * pad, ny + 2 * pad
     px_size = 3.0
@@ -286,6 +288,8 @@ def gen_insert():
         for sname in ("gauss7", "gaussP", "dirac"):
             cases.append((name, kw, sname))
     for ic, (name, kw, sname) in enumerate(cases):
+        if only is not None and (name, sname) not in only:
+            continue
         rng = np.random.Generator(np.random.PCG64(1000 + ic))
         edges = 30.0 - 5.0 * np.arange(nc + 1)
         if ic % 4 == 3:
@@ -313,7 +317,7 @@ def gen_insert():
         k = ref_kernel(name, **kw)
         set_sm(k, sm)
         sm_ranges0 = np.asarray(k.sm_ranges).copy()
-        m = make_martini(src, dc, k, make_spectrum(kind, sigma))
+        m = make_martini(src, dc, k, make_spectrum(kind, sigma, dtype=dtype))
         tracer = {}
         orig_apply = src.apply_mask
         src.apply_mask = lambda mask, _t=tracer, _o=orig_apply: (_t.setdefault("mask", np.asarray(mask).copy()), _o(mask))
@@ -330,7 +334,7 @@ def gen_insert():
             "kernel": np.array(name), "truncate": np.float64(kw.get("truncate", 0.0)),
             "spectrum": np.array(sname),
         }
-        np.savez_compressed(os.path.join(HERE, f"insert_{tag(name, kw)}_{sname}.npz"), **out)
+        np.savez_compressed(os.path.join(HERE, f"{prefix}_{tag(name, kw)}_{sname}.npz"), **out)
 
 
 if __name__ == "__main__":
@@ -339,5 +343,7 @@ if __name__ == "__main__":
     gen_spectra()
     gen_prune()
     gen_insert()
+    gen_insert(dtype=np.float32, prefix="insertf32",
+               only={("WendlandC2Kernel", "gauss7"), ("CubicSplineKernel", "gaussP")})
     tot = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print("golden fixtures written:", tot // 1024, "KiB")

@@ -207,3 +207,82 @@ def test_convolve_beam_needs_pad_and_beam():
     m.insert_source_in_cube()
     with pytest.warns(UserWarning, match="no beam object"):
         m.convolve_beam()
+
+
+# ------------------------------------------------------------------ SURVEY row f4
+def _noisy_martini(seed=0, rms=1.0e-6, insert=True, N=300):
+    from martini_b200 import GaussianBeam, GaussianNoise
+
+    s = demo_source(N=N)
+    dc = DataCube(n_px_x=64, n_px_y=64, n_channels=16, px_size=10.0, channel_width=20.0, spectral_centre=s.vsys)
+    m = Martini(source=s, datacube=dc, beam=GaussianBeam(bmaj=30.0, bmin=30.0), noise=GaussianNoise(rms=rms, seed=seed),
+                spectral_model=GaussianSpectrum(sigma=7.0), sph_kernel=CubicSplineKernel(), quiet=True)
+    if insert:
+        m.insert_source_in_cube()
+    return m
+
+
+def test_noise_amplitude():
+    """reference tests/test_noise.py:28-36: zero the cube, add noise, convolve, measure the rms."""
+    m = _noisy_martini()
+    m.datacube._array[...] = 0.0
+    m.add_noise()
+    m.convolve_beam()
+    a = m.datacube._array
+    assert a.shape == (64, 64, 16) and m.datacube.array_unit == "Jy/beam"
+    assert np.isclose(np.sqrt(np.mean(a**2)), m.noise.target_rms, rtol=0.1)
+
+
+def test_add_noise_is_the_reference_arithmetic_and_order_independent():
+    """martini.py:916-928: the noise realisation (Jy/beam) / beam area, in the cube's unit,
+    added to the array -- before or after the source insertion."""
+    after = _noisy_martini(seed=4)
+    clean = after.datacube._array.copy()
+    after.add_noise()
+    gen = _noisy_martini(seed=4, insert=False).noise
+    want = clean + gen.generate(after.datacube, after.beam) / after.beam.area
+    assert np.abs(after.datacube._array - want).max() <= 1e-15 * np.abs(want).max()
+    before = _noisy_martini(seed=4, insert=False)
+    before.add_noise()  # cube still in Jy/pix^2
+    before.insert_source_in_cube()
+    assert np.abs(before.datacube._array - want).max() <= 1e-12 * np.abs(want).max()
+
+
+def test_add_noise_needs_noise_and_beam():
+    s = demo_source(N=50)
+    dc = DataCube(n_px_x=16, n_px_y=16, n_channels=4, px_size=10.0, channel_width=50.0, spectral_centre=s.vsys)
+    m = Martini(source=s, datacube=dc, spectral_model=GaussianSpectrum(), sph_kernel=CubicSplineKernel(), quiet=True)
+    with pytest.warns(UserWarning, match="no noise object"):
+        m.add_noise()
+    from martini_b200 import GaussianNoise
+
+    m.noise = GaussianNoise()
+    with pytest.warns(UserWarning, match="no beam object"):
+        m.add_noise()
+
+
+def test_cube_stays_on_the_device_between_steps():
+    m = _noisy_martini()
+    dc = m.datacube
+    assert dc._host is None and dc._dev is not None and dc._dev.is_cuda  # no download after insertion
+    m.add_noise()
+    m.convolve_beam()
+    assert dc._host is None and dc._dev.shape == (64, 64, 16)
+    a = dc._array  # first host access materialises the array ...
+    assert a.shape == (64, 64, 16) and dc._dev is None  # ... and makes the host copy authoritative
+
+
+def test_float32_spec_dtype_is_accepted():
+    """The reference's memory-saving mode; here spectra never exist as an array, the answer is
+    the float64 one (tests/test_gpu_parity.py pins the gap to the reference's float32 cube)."""
+    def run(dtype):
+        s = demo_source(N=200)
+        dc = DataCube(n_px_x=32, n_px_y=32, n_channels=16, px_size=10.0, channel_width=20.0, spectral_centre=s.vsys)
+        m = Martini(source=s, datacube=dc, spectral_model=GaussianSpectrum(sigma=7.0, spec_dtype=dtype),
+                    sph_kernel=CubicSplineKernel(), quiet=True)
+        m.insert_source_in_cube()
+        return m
+    m32, m64 = run(np.float32), run(np.float64)
+    assert np.array_equal(m32.datacube._array, m64.datacube._array)
+    m32.init_spectra()
+    assert m32.spectral_model.spectra.dtype == np.float32

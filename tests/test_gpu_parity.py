@@ -190,6 +190,22 @@ def test_insert_vs_reference_cube(eng, path):
     check_cube(out["cube"].cpu().numpy(), g["cube"])
 
 
+F32_FILES = sorted(glob.glob(os.path.join(GOLDEN, "insertf32_*.npz")))
+
+
+@pytest.mark.parametrize("path", F32_FILES, ids=lambda p: os.path.basename(p)[10:-4])
+def test_insert_vs_reference_float32_mode(eng, path):
+    """spec_dtype=float32 of the reference (spectral_models.py:43-61): the device evaluates
+    the spectra in float64 regardless, which is within the reference's own float32 rounding
+    of its float32-mode cube -- per-voxel tolerance 1e-6 x peak as everywhere, total flux to
+    1e-6 (the reference's float32 spectra move it by ~1e-8)."""
+    g = np.load(path)
+    out = run_hot_path(eng, case_from_golden(g))
+    assert np.array_equal(out["accept"].cpu().numpy().astype(bool), g["accept"])
+    err = check_cube(out["cube"].cpu().numpy(), g["cube"], rtol_flux=1e-6)
+    assert 1e-9 < err <= 1e-6  # genuinely the float32 cube, not the float64 one
+
+
 def small_cases():
     mk = synthetic.make_case
     cases = {

@@ -88,8 +88,9 @@ def test_thermal_sigma_kat():
     assert np.isclose(S.GaussianSpectrum(sigma="thermal").half_width(src)[0], 9.0853727258, rtol=1e-9)
     assert S.GaussianSpectrum(sigma=7.0).half_width(src) == 7.0
     assert S.DiracDeltaSpectrum().half_width(src) == 0.0
+    assert S.GaussianSpectrum(spec_dtype=np.float32).spec_dtype == np.float32  # accepted, see class
     with pytest.raises(NotImplementedError, match="float64"):
-        S.GaussianSpectrum(spec_dtype=np.float32)
+        S.GaussianSpectrum(spec_dtype=np.float16)
 
 
 def test_kernel_constants_and_fwhm():
@@ -105,3 +106,60 @@ def test_kernel_constants_and_fwhm():
         K.AdaptiveKernel()
     t = K.kernel_table(K.WendlandC2Kernel())
     assert [e["kind"] for e in t.entries] == [0, 4, 3] and t.adaptive
+
+
+# ------------------------------------------------------------------ noise
+def _noise_setup(seed=0, rms=1.0):
+    from martini_b200 import GaussianBeam, GaussianNoise
+
+    dc = DataCube(n_px_x=64, n_px_y=48, n_channels=8, px_size=15.0, channel_width=4.0)
+    beam = GaussianBeam()
+    beam.init_kernel(dc)
+    dc.add_pad(beam.needs_pad())
+    return dc, beam, GaussianNoise(rms=rms, seed=seed)
+
+
+def test_noise_shape_seed_noseed_reset():
+    """reference tests/test_noise.py:13-94 on the mirror class."""
+    dc, beam, gen = _noise_setup()
+    n1 = gen.generate(dc, beam)
+    assert n1.shape == dc._array.shape
+    _, _, gen2 = _noise_setup()
+    assert np.array_equal(n1, gen2.generate(dc, beam))  # same seed, same stream
+    _, _, a = _noise_setup(seed=None)
+    _, _, b = _noise_setup(seed=None)
+    assert not np.allclose(a.generate(dc, beam), b.generate(dc, beam))
+    gen.reset_rng()
+    assert gen.seed is not None and np.array_equal(gen.generate(dc, beam), n1)
+
+
+def test_noise_is_the_reference_formula():
+    """noise.py:140-155 restated: default_rng(seed).normal(scale=rms*2.19568*sqrt(pi s_maj s_min))."""
+    dc, beam, gen = _noise_setup(seed=7, rms=3.0e-3)
+    s_maj = beam.bmaj / 2 / np.sqrt(2 * np.log(2)) / dc.px_size
+    s_min = beam.bmin / 2 / np.sqrt(2 * np.log(2)) / dc.px_size
+    scale = 3.0e-3 * 2.19568 * np.sqrt(np.pi * s_maj * s_min)
+    want = np.random.default_rng(seed=7).normal(scale=scale, size=dc._array.shape)
+    assert np.array_equal(gen.generate(dc, beam), want)
+
+
+def test_datacube_array_residency():
+    """The host array is materialised on access and a host access drops the device copy."""
+    import torch
+
+    class FakeEngine:
+        def to_device(self, a):
+            return torch.from_numpy(np.array(a, dtype=np.float64))
+
+    dc = DataCube(n_px_x=4, n_px_y=3, n_channels=2, px_size=10.0, channel_width=4.0, stokes_axis=True)
+    assert dc._array.shape == (4, 3, 2, 1) and dc._array_is_zero
+    dc._array[1, 2, 0, 0] = 5.0  # in-place edits of the host array are seen by the next device step
+    dev = dc._device_array(FakeEngine())
+    assert dev.shape == (4, 3, 2) and float(dev[1, 2, 0]) == 5.0 and not dc._array_is_zero
+    dev *= 2.0
+    dc._set_device_array(dev)
+    assert dc._host is None and not dc._array_is_zero
+    assert dc._array.shape == (4, 3, 2, 1) and dc._array[1, 2, 0, 0] == 10.0
+    assert dc._dev is None  # the host copy is authoritative again
+    dc.add_pad((1, 2))
+    assert dc._array.shape == (6, 7, 2, 1) and dc._array[2, 4, 0, 0] == 10.0

@@ -100,7 +100,7 @@ def test_prune_mask_bit_exact(golden_dir, sname, flags):
 INSERT_FILES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "insert_*.npz")))
 
 
-def run_oracle_case(g, fast=False):
+def run_oracle_case(g, fast=False, dtype=np.float64):
     """Prune + insert a golden case with the oracle; returns the final cube."""
     nx, ny, nc, pad = g["shape"]
     name, trunc, sname = str(g["kernel"]), float(g["truncate"]), str(g["spectrum"])
@@ -119,7 +119,7 @@ def run_oracle_case(g, fast=False):
         cube = O.insert_fast(cube0, pix[:, acc], k, kind, g["edges"], g["v"][acc], sig,
                              g["mHI"][acc], g["D"][acc], float(g["px_size"]))
     else:
-        spectra = O.init_spectra(kind, g["edges"], g["v"][acc], sig, g["mHI"][acc], g["D"][acc])
+        spectra = O.init_spectra(kind, g["edges"], g["v"][acc], sig, g["mHI"][acc], g["D"][acc], dtype=dtype)
         cube = O.insert_source_in_cube(cube0, pix[:, acc], k, spectra, float(g["px_size"]),
                                        skip_validation=True)
     return acc, cube
@@ -137,5 +137,21 @@ def test_insert_bit_exact(path):
     assert np.array_equal(cube_fast, g["cube"])
 
 
+F32_FILES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "insertf32_*.npz")))
+
+
+@pytest.mark.parametrize("path", F32_FILES, ids=lambda p: os.path.basename(p)[10:-4])
+def test_insert_float32_mode_bit_exact(path):
+    """The reference's spec_dtype=float32 mode (spectral_models.py:43-61, 297-300)."""
+    g = np.load(path)
+    acc, cube = run_oracle_case(g, dtype=np.float32)
+    assert np.array_equal(acc, g["accept"])
+    assert np.array_equal(cube, g["cube"])
+    # ... and it is the float64 mode to float32 rounding: the gap the GPU path is allowed
+    g64 = np.load(path.replace("insertf32_", "insert_"))
+    assert 0 < np.abs(g["cube"] - g64["cube"]).max() <= 1e-6 * np.abs(g64["cube"]).max()
+
+
 def test_insert_fixture_count():
+    assert len(F32_FILES) == 2
     assert len(INSERT_FILES) == 42  # (8 primitive + 6 adaptive) kernels x 3 spectra
