@@ -229,7 +229,9 @@ class Martini(_BaseMartini):
             raise RuntimeError("convolve_beam expects a cube in Jy/arcsec2: insert the source first.")
         eng = self.engine
         out = eng.convolve_beam(dc._device_array(eng), self.beam.kernel, scale=self.beam.area)  # x area: -> Jy/beam
-        dc._set_device_array(out)  # the convolution returns the unpadded cube (drop_pad, :899)
+        # drop_pad (martini.py:899, datacube.py:710-729) on the device
+        out = out[dc.padx:dc.padx + dc.n_px_x, dc.pady:dc.pady + dc.n_px_y, :].contiguous()
+        dc._set_device_array(out)
         dc.padx = dc.pady = 0
         dc.array_unit = "Jy/beam"
         if not self.quiet:
