@@ -16,7 +16,8 @@ metric  = particle-channel updates / s, with one update = one (particle, pixel o
           U_dense = C * sum_p n_x(p) n_y(p), counted on the device by mtn_plan.
 value   = U_dense * steps / device time, inputs resident in HBM.
 e2e     = same, but every step also copies the particle arrays from pinned host memory and
-          reads the finished cube back to the host.
+          reads the finished cube back to the host (N > 1: every rank reads its slab back over
+          its own PCIe link into one host cube shared by the ranks, martini_b200.dist.HostCube).
 
 `--impl reference` times the CPU restatement of the reference algorithm (oracle/, the
 reference itself needs astropy, which cannot be installed here) with all host threads on a
@@ -244,25 +245,29 @@ def run_b200(args):
             peer = None
     slab = peer.rows if peer is not None else torch.zeros((x_hi - x_lo, ny, nc), dtype=torch.float64, device=dev_t)
     full = torch.empty((nx, ny, nc), dtype=torch.float64, device=dev_t) if (world > 1 and rank == 0 and peer is None) else None
-    host_cube = torch.empty((nx, ny, nc), dtype=torch.float64).pin_memory() if rank == 0 else None
+    # end-to-end leg: the result is read back into one host cube shared by the ranks; every
+    # rank copies its own slab over its own PCIe link (martini_b200.dist.HostCube)
+    host_cube = mdist.HostCube((nx, ny, nc), bounds)
+    slab_e2e = slab if peer is None else torch.zeros((x_hi - x_lo, ny, nc), dtype=torch.float64, device=dev_t)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev_t)
 
     def step(e2e=False):
         if e2e:
+            # host buffers in, host cube out: upload, project into the local slab, read it back
             pipeline.upload(eng, case, pinned, out=dev)
+            slab_e2e.zero_()
+            out = pipeline.run_hot_path(eng, case, dev=dev, cube=slab_e2e, x_lo=x_lo, x_hi=x_hi, zeroed=True, ctx=ctx)
+            host_cube.store(slab_e2e)
+            return out
         if peer is not None:
             peer.begin()  # rank 0 zeroes the cube, barrier
         else:
             slab.zero_()
         out = pipeline.run_hot_path(eng, case, dev=dev, cube=slab, x_lo=x_lo, x_hi=x_hi, zeroed=True, ctx=ctx)
         if peer is not None:
-            res = peer.end()  # barrier: every rank's stores have landed in rank 0's cube
-        elif world == 1:
-            res = slab
-        else:
-            res = mdist.gather_slabs(slab, bounds, full, dst=0)
-        if e2e and rank == 0:
-            host_cube.copy_(res, non_blocking=True)
+            peer.end()  # barrier: every rank's stores have landed in rank 0's cube
+        elif world > 1:
+            mdist.gather_slabs(slab, bounds, full, dst=0)
         return out
 
     def timed(n_steps, e2e=False, stage_times=None):
@@ -349,7 +354,9 @@ def run_b200(args):
             "data": "synthetic", "config": workload_config(case, args.workload, n_gpus),
             "updates_per_step": u_dense, "insertion_wall_ms": ms_step,
             "e2e": {"value": u_dense / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "result": "host cube shared by the ranks (POSIX shared memory, page-locked), "
+                              "each rank copies its own slab" if n_gpus > 1 else "pinned host cube"},
             "gpu_launches": int(out["launches"]) * args.steps,
             "gpu_launches_per_step": int(out["launches"]),
             "clocks": clocks, "roofline": roofline,
@@ -377,6 +384,7 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": ncpu, "kind": "port",
                                     "sample": desc, "full_insertion_s": t_full}
         print(json.dumps(line))
+    host_cube.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

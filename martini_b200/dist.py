@@ -135,6 +135,53 @@ class PeerCube:
         return self.buf if self.rank == self.dst else None
 
 
+class HostCube:
+    """The assembled cube in host memory, for callers that want the result on the host: every
+    rank copies its slab device -> host over its own PCIe link into its rows of one array
+    shared by the ranks of the node (POSIX shared memory, page-locked with cudaHostRegister so
+    the copies are asynchronous DMA).  No rank ever holds the whole cube on a device and the
+    read-back time does not grow with the number of GPUs.  ``array`` is the numpy view."""
+
+    def __init__(self, shape, bounds, pin=True):
+        from multiprocessing import resource_tracker, shared_memory
+
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        nbytes = int(np.prod(shape)) * 8
+        name = [None]
+        if self.rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name[0] = self.shm.name
+        if world > 1:
+            dist.broadcast_object_list(name, src=0)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            # the creator unlinks it; keep this process's resource tracker out of it
+            resource_tracker.unregister(self.shm._name, "shared_memory")
+        self.array = np.ndarray(shape, dtype=np.float64, buffer=self.shm.buf)
+        self.tensor = torch.from_numpy(self.array)
+        self.pinned = False
+        if pin and torch.cuda.is_available():
+            self.pinned = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 0) in (0, None) or \
+                self.tensor.is_pinned()
+        self.rows = self.tensor[bounds[self.rank]:bounds[self.rank + 1]]
+
+    def store(self, slab: torch.Tensor):
+        """Enqueue the copy of this rank's slab into its rows (asynchronous if page-locked)."""
+        self.rows.copy_(slab, non_blocking=True)
+
+    def close(self):
+        if self.pinned:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self.pinned = False
+        del self.rows, self.tensor, self.array
+        self.shm.close()
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.barrier()
+        if self.rank == 0:
+            self.shm.unlink()
+
+
 def insert_sharded(engine, case, dev=None, ctx=None, bounds=None, gather=True, full=None):
     """Run the hot path for this rank's slab and (optionally) gather the cube on rank 0.
 

@@ -90,3 +90,39 @@ def test_single_process_gather_is_identity():
     slab = torch.ones(4, 2, 2, dtype=torch.float64)
     full = torch.zeros(4, 2, 2, dtype=torch.float64)
     assert torch.equal(mdist.gather_slabs(slab, [0, 4], full), slab)
+
+
+def _host_cube_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from martini_b200 import dist as mdist
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    shape, bounds = (12, 5, 4), [0, 8, 12]
+    hc = mdist.HostCube(shape, bounds, pin=False)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    slab = torch.arange(lo * 20, hi * 20, dtype=torch.float64).reshape(hi - lo, 5, 4)
+    hc.store(slab)
+    dist.barrier()
+    if rank == 0:  # rank 0 sees the rows written by the other process
+        q.put(bool(np.array_equal(hc.array, np.arange(12 * 20, dtype=np.float64).reshape(shape))))
+    dist.barrier()
+    hc.close()
+    dist.destroy_process_group()
+
+
+def test_host_cube_is_shared_between_ranks():
+    """dist.HostCube: every rank writes its slab rows into one host array (world size 2, gloo)."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_host_cube_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok
