@@ -139,8 +139,10 @@ class HostCube:
     """The assembled cube in host memory, for callers that want the result on the host: every
     rank copies its slab device -> host over its own PCIe link into its rows of one array
     shared by the ranks of the node (POSIX shared memory, page-locked with cudaHostRegister so
-    the copies are asynchronous DMA).  No rank ever holds the whole cube on a device and the
-    read-back time does not grow with the number of GPUs.  ``array`` is the numpy view."""
+    the copies are asynchronous DMA).  No rank ever holds the whole cube on a device and no
+    single link carries all of it (measured on this pool's 8-GPU boxes: 29 ms instead of 46 ms
+    for the 537 MB weak-scaled cube; the boxes' host side saturates at about 43 GB/s aggregate).
+    ``array`` is the numpy view."""
 
     def __init__(self, shape, bounds, pin=True):
         from multiprocessing import resource_tracker, shared_memory
