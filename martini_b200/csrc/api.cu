@@ -7,7 +7,10 @@
 #include "kernel_integrals.cuh"
 #include "plan.cuh"
 #include "project.cuh"
-#include "project_ws.cuh"
+#if MTN_TILE == 8
+#define MTN_HAVE_WS 1
+#include "project_ws.cuh"  // the warp-specialised variant is written for 8 x 8 tiles
+#endif
 #include "scan.cuh"
 #include "sort.cuh"
 #include "tables_host.hpp"
@@ -108,23 +111,32 @@ static bool use_classic_project() {
 template <bool COUNT, int KIND>
 static int launch_project_as(const ProjArgs& a, int64_t max_items, cudaStream_t st) {
   static bool attr_set[2] = {false, false};
+#ifdef MTN_HAVE_WS
   const bool classic = use_classic_project();
+#else
+  const bool classic = true;
+#endif
   if (!attr_set[classic]) {
     if (classic)
       MTN_CUDA(cudaFuncSetAttribute(project_kernel<COUNT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(ProjSmem)));
+#ifdef MTN_HAVE_WS
     else
       MTN_CUDA(cudaFuncSetAttribute(project_ws_kernel<COUNT, KIND>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSmem)));
+#endif
     attr_set[classic] = true;
   }
   if (classic) {
     const unsigned grid = (unsigned)std::min<int64_t>(max_items, (int64_t)sm_count() * PROJ_CTAS_PER_SM);
     project_kernel<COUNT, KIND><<<grid, PROJ_THREADS, sizeof(ProjSmem), st>>>(a);
-  } else {
+  }
+#ifdef MTN_HAVE_WS
+  else {
     const unsigned grid = (unsigned)std::min<int64_t>(max_items, (int64_t)sm_count() * WS_CTAS_PER_SM);
     project_ws_kernel<COUNT, KIND><<<grid, WS_THREADS, sizeof(WsSmem), st>>>(a);
   }
+#endif
   return MTN_OK;
 }
 
