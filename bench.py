@@ -331,10 +331,26 @@ def run_b200(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         plan = out["plan"]
         bytes_alg = 72.0 * plan.n_pairs + 8.0 * (x_hi - x_lo) * ny * nc
+        # DRAM bytes of one launch from the committed ncu --set full capture of this workload
+        # (profiles/r1_final_project_kernel.md); only meaningful for the default config at N = 1
+        traffic = None
+        if n_gpus == 1 and args.workload == "cfg2" and args.particles is None:
+            try:
+                import re
+
+                txt = open(os.path.join(ROOT, "profiles", "r1_final_project_kernel.md")).read()
+                rd = re.search(r"dram__bytes_read\.sum` = ([0-9.]+) Mbyte", txt)
+                wr = re.search(r"dram__bytes_write\.sum` = ([0-9.]+) Mbyte", txt)
+                if rd and wr:
+                    traffic = (float(rd.group(1)) + float(wr.group(1))) * 1e6
+            except OSError:
+                pass
         roofline = {
             "kernel": "project_kernel", "bound": "fp64",
             "achieved": flops_fma / t_proj / 1e12, "peak": p64, "unit": "TFLOP/s",
-            "frac": flops_fma / t_proj / 1e12 / p64, "traffic": None,
+            "frac": flops_fma / t_proj / 1e12 / p64, "traffic": traffic,
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, bytes, ncu capture "
+                            "profiles/r1_final_project_kernel.md; algorithmic bytes are in hbm.achieved",
             "peak_source": "FP64 FMA microbenchmark run on this GPU in this process "
                            "(mtn_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
             "algorithmic": {"fma_updates": ex["updates"], "kernel_integrals": ex["weights"],
