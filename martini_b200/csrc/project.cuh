@@ -478,37 +478,66 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
       uint32_t rel = __ballot_sync(0xffffffffu, mymask != 0);
 
       // ---- phase C: acc[pixel][2 channels] += W * S for the masked pixels -----------------
-      while (rel) {
-        const int p = __ffs(rel) - 1;
-        rel &= rel - 1;
-        const uint32_t m = __shfl_sync(0xffffffffu, mymask, p);
-        // this lane's two channels of the particle's line spectrum, from the shared edge erfs
-        // (adjacent channels share an edge):  S = 0.5 [erf(hi) - erf(lo)] A / dv / 2.36e5,
-        // the 0.5 and 2.36e5 live in amp; channels outside the live range are exactly zero
-        const int c = half * CH_HALF + 2 * lane;
-        const uint32_t cs = sm.chan[p][0], span = sm.chan[p][1] - cs;
+      // Software-pipelined: the next particle's mask shuffle, shared-memory loads and spectrum
+      // arithmetic are issued before the current particle's FMAs, so their ~110-cycle chain
+      // (bit scan, shuffle, load) overlaps the FMA stream instead of preceding it.
+      const int c = half * CH_HALF + 2 * lane;
+      const double2 idv = *reinterpret_cast<const double2*>(&sm.inv_dv[c]);
+      // this lane's two channels of particle p's line spectrum, from the shared edge erfs
+      // (adjacent channels share an edge):  S = 0.5 [erf(hi) - erf(lo)] A / dv / 2.36e5, the
+      // 0.5 and 2.36e5 live in amp; channels outside the live range are exactly zero
+      struct RawSpec {  // what spectrum_of needs from shared memory, loaded ahead of time
+        uint32_t chan;
+        double amp, ec;
+        double2 eab;
+      };
+      auto load_spec = [&](int p) {
+        RawSpec r;
+        r.chan = *reinterpret_cast<const uint16_t*>(sm.chan[p]);
+        r.amp = sm.rec[buf][p].amp;
+        r.eab = *reinterpret_cast<const double2*>(&sm.ES[p][c]);
+        r.ec = sm.ES[p][c + 2];
+        return r;
+      };
+      auto spectrum_of = [&](const RawSpec& r) {
+        const uint32_t cs = r.chan & 0xffu, span = (r.chan >> 8) - cs;
         const bool in0 = (uint32_t)c - cs < span, in1 = (uint32_t)c + 1u - cs < span;
-        const double amp = sm.rec[buf][p].amp;
-        const double2 idv = *reinterpret_cast<const double2*>(&sm.inv_dv[c]);
         double2 s2;
         if (gaussian_line) {
-          const double2 eab = *reinterpret_cast<const double2*>(&sm.ES[p][c]);
-          const double ec = sm.ES[p][c + 2];
-          s2.x = in0 ? (eab.y - eab.x) * (amp * idv.x) : 0.0;
-          s2.y = in1 ? (ec - eab.y) * (amp * idv.y) : 0.0;
+          s2.x = in0 ? (r.eab.y - r.eab.x) * (r.amp * idv.x) : 0.0;
+          s2.y = in1 ? (r.ec - r.eab.y) * (r.amp * idv.y) : 0.0;
         } else {  // Dirac line: the live channels are exactly those with lo <= v <= hi
-          s2.x = in0 ? amp * idv.x : 0.0;
-          s2.y = in1 ? amp * idv.y : 0.0;
+          s2.x = in0 ? r.amp * idv.x : 0.0;
+          s2.y = in1 ? r.amp * idv.y : 0.0;
         }
-        const double* Wp = sm.W[p];
+        return s2;
+      };
+      if (rel) {
+        int p = __ffs(rel) - 1;
+        rel &= rel - 1;
+        uint32_t m = __shfl_sync(0xffffffffu, mymask, p);
+        double2 s2 = spectrum_of(load_spec(p));
+        for (;;) {
+          const bool more = rel != 0;
+          const int pn = more ? __ffs(rel) - 1 : p;
+          rel &= rel - 1;
+          // loads for the next particle go out now, their arithmetic comes after the FMAs
+          const uint32_t mn = __shfl_sync(0xffffffffu, mymask, pn);
+          const RawSpec rn = load_spec(pn);
+          const double* Wp = sm.W[p];
 #pragma unroll
-        for (int j = 0; j < SUB_PIX; ++j) {
-          if (m & (1u << j)) {
-            const double w = Wp[sub_x(sub, j) * TILE_Y + sub_y(sub, j)];
-            acc[j][0] = fma(w, s2.x, acc[j][0]);
-            acc[j][1] = fma(w, s2.y, acc[j][1]);
-            if (COUNT) n_upd += (s2.x != 0.0) + (s2.y != 0.0);
+          for (int j = 0; j < SUB_PIX; ++j) {
+            if (m & (1u << j)) {
+              const double w = Wp[sub_x(sub, j) * TILE_Y + sub_y(sub, j)];
+              acc[j][0] = fma(w, s2.x, acc[j][0]);
+              acc[j][1] = fma(w, s2.y, acc[j][1]);
+              if (COUNT) n_upd += (s2.x != 0.0) + (s2.y != 0.0);
+            }
           }
+          if (!more) break;
+          p = pn;
+          m = mn;
+          s2 = spectrum_of(rn);
         }
       }
       __syncthreads();  // W, ES, boxes and rec[buf] are free again
