@@ -19,7 +19,8 @@
 //   C      each warp builds, with one ballot, the list of particles that touch its sub-block
 //          and their pixel masks, then walks it: the lane forms its two spectrum values
 //          S = (E[c+1] - E[c]) amp / dv from the shared edge erfs and does acc[pixel] += W * S
-//          for the masked pixels (W is a shared-memory broadcast).
+//          for the masked pixels (W is a shared-memory broadcast); the next particle's mask
+//          shuffle and spectrum loads are issued ahead of the current FMAs.
 //
 // No atomics on the data path; every voxel is stored exactly once, as a 16-byte vector store
 // (a warp writes 512 contiguous bytes per pixel).
