@@ -389,3 +389,32 @@ def test_cfg4_wide_footprints_midsize(eng):
     case["sm_length"] = case["sm_length"] * 2.0  # keep 8..40 px smoothing lengths at this cube size
     out = sampled_pixel_check(eng, case, 24, seed=404, bright_box=(64, 192))
     assert out["plan"].n_pairs > 50 * out["plan"].n_kept
+
+
+@pytest.mark.parametrize("name", ("cfg2_small", "cfg3_thermal", "dirac_edges"))
+def test_warp_specialised_variant_matches(eng, name, tmp_path):
+    """The opt-in MTN_PROJECT=ws kernel (csrc/project_ws.cuh) against the oracle and the default
+    kernel.  The switch is read once per process, so the variant runs in a child process."""
+    import pickle
+    import subprocess
+    import sys
+
+    case = SMALL[name]
+    case_file, out_file = tmp_path / "case.pkl", tmp_path / "cube.npy"
+    case_file.write_bytes(pickle.dumps(case))
+    code = (
+        "import pickle, sys, numpy as np\n"
+        "from martini_b200.engine import Engine\n"
+        "from martini_b200.pipeline import run_hot_path\n"
+        "case = pickle.load(open(sys.argv[1], 'rb'))\n"
+        "out = run_hot_path(Engine('cuda:0'), case)\n"
+        "np.save(sys.argv[2], out['cube'].cpu().numpy())\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MTN_PROJECT="ws", PYTHONPATH=root)
+    subprocess.run([sys.executable, "-c", code, str(case_file), str(out_file)], check=True, env=env,
+                   cwd=root, timeout=300)
+    ws = np.load(out_file)
+    check_cube(ws, oracle_hot_path(case)["cube"])
+    default = run_hot_path(eng, case)["cube"].cpu().numpy()
+    assert np.abs(ws - default).max() <= 1e-13 * np.abs(default).max()
