@@ -45,8 +45,15 @@ static_assert(PBATCH == 32, "the batch is indexed by lane in several places");
 
 // erf table: Taylor coefficients of erf at the centres of ERF_NINT intervals of width
 // 1/ERF_INV_W covering [0, ERF_SAT]; degree ERF_DEG.  Truncation error < 5e-18.
-constexpr int ERF_INV_W = 16;
-constexpr int ERF_DEG = 9;
+#ifndef MTN_ERF_INV_W
+#define MTN_ERF_INV_W 16
+#endif
+#ifndef MTN_ERF_DEG
+#define MTN_ERF_DEG 9
+#endif
+constexpr int ERF_INV_W = MTN_ERF_INV_W;
+constexpr int ERF_DEG = MTN_ERF_DEG;
+static_assert(ERF_DEG % 2 == 1, "rows are read as pairs of coefficients");
 constexpr int ERF_NCOEF = ERF_DEG + 1;  // 10 doubles = 80 B per interval (16-B aligned rows)
 constexpr int ERF_NINT = 6 * ERF_INV_W + 1;
 constexpr int REC_DOUBLES = 8;        // 64-byte particle record

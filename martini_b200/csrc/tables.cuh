@@ -26,17 +26,16 @@ __device__ __forceinline__ double erf_tab(double t) {
   const int i = (int)(a * ERF_INV_W);  // a = ERF_SAT lands in the last (saturated) interval
   const double u = a - ((double)i + 0.5) * (1.0 / ERF_INV_W);
   const double2* row = reinterpret_cast<const double2*>(g_erf_table + i * ERF_NCOEF);
-  const double2 c89 = __ldg(row + 4), c67 = __ldg(row + 3), c45 = __ldg(row + 2),
-                c23 = __ldg(row + 1), c01 = __ldg(row);
-  double r = fma(c89.y, u, c89.x);
-  r = fma(r, u, c67.y);
-  r = fma(r, u, c67.x);
-  r = fma(r, u, c45.y);
-  r = fma(r, u, c45.x);
-  r = fma(r, u, c23.y);
-  r = fma(r, u, c23.x);
-  r = fma(r, u, c01.y);
-  r = fmin(fma(r, u, c01.x), 1.0);
+  double2 c[ERF_NCOEF / 2];
+#pragma unroll
+  for (int k = ERF_NCOEF / 2 - 1; k >= 0; --k) c[k] = __ldg(row + k);
+  double r = fma(c[ERF_NCOEF / 2 - 1].y, u, c[ERF_NCOEF / 2 - 1].x);
+#pragma unroll
+  for (int k = ERF_NCOEF / 2 - 2; k >= 0; --k) {
+    r = fma(r, u, c[k].y);
+    r = fma(r, u, c[k].x);
+  }
+  r = fmin(r, 1.0);
   r = fabs(t) >= ERF_SAT ? 1.0 : r;
   return copysign(r, t);
 }
@@ -50,8 +49,9 @@ __device__ __forceinline__ double erf_tab(double t) {
 // of u is split into 8 equal intervals, so (interval width) / (distance to the anchor) <=
 // 1/8 everywhere and a degree-9 interpolant converges like 33^-10; u < 2^-kmin is one "core"
 // interval, where the non-analytic term itself is below 1e-16 of W(0).  The interval index
-// is read off the exponent and top 3 mantissa bits of u, and the polynomial's variable is
-// u - (interval centre): u = |s - anchor| is exact in float64 for every zone below.
+// is read off the exponent and top 3 mantissa bits of u, and so is the interval's centre;
+// the polynomial's variable is u - centre (u = |s - anchor| is exact in float64 for every
+// zone below), so only the ten coefficients are loaded.
 constexpr int WT_DEG = 9;
 constexpr int WT_ROW = 12;          // c0..c9 (in t = u - centre), interval centre, unused
 constexpr int WT_MAX_ZONES = 4;
@@ -62,6 +62,7 @@ constexpr int WT_SUB_BITS = 3;      // 8 intervals per octave
 struct WZone {
   double s_lo;    // the zone holds s_lo <= s < (next zone).s_lo; +inf for unused zones
   double anchor;  // u = |s - anchor|
+  double core_centre;  // centre of the core interval: 2^-(kmin+1)
   int off;        // row = clamp((hi32(u) >> 17) + off, row0, last)
   int row0;       // the zone's core interval
   int last;       // the zone's last row
@@ -88,9 +89,15 @@ __device__ __forceinline__ double wtab_eval(int kind, double R2) {
   const double u = fabs(s - zn.anchor);
   const int idx = min(max((__double2hiint(u) >> (20 - WT_SUB_BITS)) + zn.off, zn.row0), zn.last);
   const double2* row = reinterpret_cast<const double2*>(g_wtab_rows + idx * WT_ROW);
-  const double2 cw = __ldg(row + 5), c89 = __ldg(row + 4), c67 = __ldg(row + 3), c45 = __ldg(row + 2),
-                c23 = __ldg(row + 1), c01 = __ldg(row);
-  const double t = u - cw.x;
+  const double2 c89 = __ldg(row + 4), c67 = __ldg(row + 3), c45 = __ldg(row + 2), c23 = __ldg(row + 1),
+                c01 = __ldg(row);
+  // the interval's centre (also stored in the row, for the host replica) from its own index:
+  // start of the interval = key << 17 as a high word, plus half its width = the next mantissa bit
+  const int key = idx - zn.off;
+  const double centre = idx == zn.row0
+                            ? zn.core_centre
+                            : __hiloint2double((key << (20 - WT_SUB_BITS)) | (1 << (19 - WT_SUB_BITS)), 0);
+  const double t = u - centre;
   double v = fma(c89.y, t, c89.x);
   v = fma(v, t, c67.y);
   v = fma(v, t, c67.x);

@@ -129,7 +129,14 @@ static double host_wtab_eval(const HostTables& T, int kind, double R2) {
   const double u = std::fabs(s - zn.anchor);
   const int idx = std::min(std::max((hi32(u) >> (20 - WT_SUB_BITS)) + zn.off, zn.row0), zn.last);
   const double* row = T.rows.data() + (size_t)idx * WT_ROW;
-  const double t = u - row[10];
+  // the centre from the interval's own index, as on the device; row[10] holds the same number
+  const int key = idx - zn.off;
+  const long long cbits = (long long)((key << (20 - WT_SUB_BITS)) | (1 << (19 - WT_SUB_BITS))) << 32;
+  double centre;
+  memcpy(&centre, &cbits, sizeof(centre));
+  if (idx == zn.row0) centre = zn.core_centre;
+  if (centre != row[10]) return NAN;  // a layout bug would poison max_err
+  const double t = u - centre;
   double v = row[9];
   for (int k = 8; k >= 0; --k) v = std::fma(v, t, row[k]);
   return v;
@@ -148,6 +155,7 @@ static void build_kind(HostTables& T, int kind, double scale, F f, const std::ve
     const ld u_max = up ? sp.s_hi - sp.anchor : sp.anchor - sp.s_lo;
     zn.s_lo = (double)sp.s_lo;
     zn.anchor = (double)sp.anchor;
+    zn.core_centre = (double)ldexpl(1.0L, -sp.kmin - 1);
     zn.row0 = (int)(T.rows.size() / WT_ROW);
     zn.off = zn.row0 + 1 - ((1023 - sp.kmin) << WT_SUB_BITS);
     zn.pad = 0;
@@ -168,7 +176,7 @@ static void build_kind(HostTables& T, int kind, double scale, F f, const std::ve
     zn.last = (int)(T.rows.size() / WT_ROW) - 1;
   }
   for (size_t z = specs.size(); z < (size_t)WT_MAX_ZONES; ++z)
-    T.zone[kind][z] = WZone{HUGE_VAL, 0.0, 0, 0, 0, 0};
+    T.zone[kind][z] = WZone{HUGE_VAL, 0.0, 0.0, 0, 0, 0, 0};
   // verify on a dense sample of s: uniform over the support, and geometrically approaching
   // every zone anchor from inside the zone
   const ld f0 = f(0.0L, 0.0L);
@@ -178,7 +186,7 @@ static void build_kind(HostTables& T, int kind, double scale, F f, const std::ve
     const double sd = R2 * scale;
     const double got = host_wtab_eval(T, kind, R2);
     const double err = (double)(fabsl((ld)got - f(anchor, (ld)sd - anchor)) / f0);
-    if (err > worst) worst = err;
+    if (!(err <= worst)) worst = err;  // NaN (a layout bug flagged by the replica) sticks
   };
   const ld s_end = specs.back().s_hi;
   for (int i = 0; i <= 40000; ++i) check(0.0L, (ld)i / 40000.0L * s_end * (1.0L - 1e-12L));
@@ -200,7 +208,7 @@ static HostTables build_kernel_tables() {
     T.scale[k] = 1.0;
     T.end[k] = 0.0;
     T.max_err[k] = 0.0;
-    for (int z = 0; z < WT_MAX_ZONES; ++z) T.zone[k][z] = WZone{HUGE_VAL, 0.0, 0, 0, 0, 0};
+    for (int z = 0; z < WT_MAX_ZONES; ++z) T.zone[k][z] = WZone{HUGE_VAL, 0.0, 0.0, 0, 0, 0, 0};
   }
   // Wendland C2: s^2 log s at 0, (1 - s)^(9/2) at the edge
   build_kind(T, MTN_KERNEL_WENDLANDC2, 1.0, F_wendland_c2,
