@@ -52,6 +52,10 @@ def parse():
     ap.add_argument("--particles", type=int, default=None, help="override particles per GPU")
     ap.add_argument("--sample-pixels", type=int, default=512, help="CPU baseline pixel sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-slabs", type=int, default=1,
+                    help="x-sub-slabs of the end-to-end leg (each one's read-back overlaps the next one's "
+                         "projection); measured on config 2: 7.16 / 7.51 / 7.70 ms for 1 / 2 / 3 -- the extra "
+                         "planning passes cost more than the overlap hides, so the default is 1")
     return ap.parse_args()
 
 
@@ -249,16 +253,15 @@ def run_b200(args):
     # rank copies its own slab over its own PCIe link (martini_b200.dist.HostCube)
     host_cube = mdist.HostCube((nx, ny, nc), bounds)
     slab_e2e = slab if peer is None else torch.zeros((x_hi - x_lo, ny, nc), dtype=torch.float64, device=dev_t)
+    copy_stream = torch.cuda.Stream(device=dev_t)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev_t)
 
     def step(e2e=False):
         if e2e:
             # host buffers in, host cube out: upload, project into the local slab, read it back
             pipeline.upload(eng, case, pinned, out=dev)
-            slab_e2e.zero_()
-            out = pipeline.run_hot_path(eng, case, dev=dev, cube=slab_e2e, x_lo=x_lo, x_hi=x_hi, zeroed=True, ctx=ctx)
-            host_cube.store(slab_e2e)
-            return out
+            return pipeline.run_hot_path_to_host(eng, case, host_cube.rows, dev, ctx, slab_e2e, x_lo=x_lo,
+                                                 x_hi=x_hi, n_slabs=args.e2e_slabs, copy_stream=copy_stream)
         if peer is not None:
             peer.begin()  # rank 0 zeroes the cube, barrier
         else:
@@ -371,8 +374,9 @@ def run_b200(args):
             "updates_per_step": u_dense, "insertion_wall_ms": ms_step,
             "e2e": {"value": u_dense / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "result": "host cube shared by the ranks (POSIX shared memory, page-locked), "
-                              "each rank copies its own slab" if n_gpus > 1 else "pinned host cube"},
+                    "result": ("host cube shared by the ranks (POSIX shared memory, page-locked), "
+                               "each rank copies its own slab" if n_gpus > 1 else "pinned host cube")
+                              + f"; pipeline.run_hot_path_to_host with {args.e2e_slabs} x-sub-slab(s) per rank"},
             "gpu_launches": int(out["launches"]) * args.steps,
             "gpu_launches_per_step": int(out["launches"]),
             "clocks": clocks, "roofline": roofline,

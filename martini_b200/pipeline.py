@@ -109,3 +109,49 @@ def run_hot_path(engine, case, dev=None, cube=None, x_lo=0, x_hi=None, prune=(Tr
     return {"cube": cube, "accept": accept, "n_accept": n_accept, "plan": plan, "kernel_id": kid,
             "valid": valid, "sm_range": sm_range, "h_eff": h_eff,
             "launches": engine.last_launches + 2}  # + smoothing_setup + prune
+
+
+def run_hot_path_to_host(engine, case, host_rows, dev, ctx: CaseContext, slab, x_lo=0, x_hi=None,
+                         n_slabs=1, copy_stream=None, prune=(True, True, True)):
+    """The hot path with the result delivered to host memory: K0 -> K1 once, then plan + project
+    in ``n_slabs`` x-sub-slabs of rows [x_lo, x_hi); each finished sub-slab is copied device ->
+    host on ``copy_stream`` while the next one is being projected.  (On BASELINE config 2 the
+    extra planning passes cost more than the overlap hides -- 7.2 ms with one sub-slab, 7.5 with
+    two -- so the default is one; larger cubes per GPU shift the balance.)
+
+    ``slab``       float64 device tensor (x_hi - x_lo, ny, C), used as the staging cube;
+    ``host_rows``  page-locked host tensor of the same shape (e.g. ``dist.HostCube.rows``).
+    Returns dict(plans, accept, n_accept, launches); on return the current stream waits for the
+    copies, so an event recorded next covers them.
+    """
+    from . import dist as mdist
+
+    nx, ny, nc = ctx.shape
+    x_hi = nx if x_hi is None else x_hi
+    gauss = ctx.spectrum == L.SPECTRUM_GAUSSIAN
+    kid, valid, sm_range, h_eff = engine.smoothing_setup(dev["sm_length"], ctx.table)
+    accept, n_accept = engine.prune(dev["px"], dev["py"], dev["pz"], sm_range, dev["mHI"],
+                                    dev["sigma"] if gauss else 0.0, ctx.max_abs_dv, nx, ny, nc, *prune)
+    copy_stream = copy_stream or torch.cuda.Stream(device=engine.device)
+    main = torch.cuda.current_stream(engine.device)
+    bounds = mdist.slab_bounds(x_hi - x_lo, n_slabs)
+    plans, launches = [], 2
+    slab.zero_()
+    for k in range(n_slabs):
+        a, b = bounds[k], bounds[k + 1]
+        if b == a:
+            continue
+        part = slab[a:b]
+        plans.append(engine.insert(
+            px=dev["px"], py=dev["py"], h_eff=h_eff, sm_range=sm_range, v=dev["v"], kernel_id=kid,
+            sigma=dev["sigma"] if gauss else 1.0, mHI=dev["mHI"], D=dev["D"], accept=accept,
+            table=ctx.table, spectrum=ctx.spectrum, edges=dev["edges"], cube=part,
+            px_size_arcsec=ctx.px_size, x_lo=x_lo + a, x_hi=x_lo + b, nx_full=nx, zeroed=True))
+        launches += engine.last_launches
+        done = torch.cuda.Event()
+        done.record(main)
+        copy_stream.wait_event(done)
+        with torch.cuda.stream(copy_stream):
+            host_rows[a:b].copy_(part, non_blocking=True)
+    main.wait_stream(copy_stream)
+    return {"plans": plans, "accept": accept, "n_accept": n_accept, "launches": launches}

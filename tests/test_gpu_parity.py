@@ -418,3 +418,25 @@ def test_warp_specialised_variant_matches(eng, name, tmp_path):
     check_cube(ws, oracle_hot_path(case)["cube"])
     default = run_hot_path(eng, case)["cube"].cpu().numpy()
     assert np.abs(ws - default).max() <= 1e-13 * np.abs(default).max()
+
+
+@pytest.mark.parametrize("n_slabs", (1, 2, 3))
+def test_hot_path_to_host_matches(eng, n_slabs):
+    """pipeline.run_hot_path_to_host: sub-slab projection with overlapped read-back gives the
+    cube of the one-shot path (a voxel's terms are summed in the same order either way)."""
+    import torch
+
+    from martini_b200 import pipeline
+
+    case = SMALL["cfg2_small"]
+    ctx = pipeline.prepare(case)
+    dev = pipeline.upload(eng, case)
+    nx, ny, nc = ctx.shape
+    want = run_hot_path(eng, case, dev=dev, ctx=ctx)
+    host = torch.empty((nx, ny, nc), dtype=torch.float64).pin_memory()
+    slab = torch.empty((nx, ny, nc), dtype=torch.float64, device=eng.device)
+    out = pipeline.run_hot_path_to_host(eng, case, host, dev, ctx, slab, n_slabs=n_slabs)
+    torch.cuda.synchronize()
+    assert sum(p.updates_dense for p in out["plans"]) == want["plan"].updates_dense
+    ref = want["cube"].cpu().numpy()
+    assert np.abs(host.numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
