@@ -7,7 +7,7 @@
 namespace mtn {
 
 constexpr int PLAN_THREADS = 1024;
-constexpr int TILE_STAT_STRIDE = 16;
+constexpr int TILE_STAT_STRIDE = 32;
 
 // ---------------------------------------------------------------------------------------
 // K0: per-particle kernel choice, sm_range, h_eff.

@@ -1,7 +1,7 @@
 // Device-wide exclusive prefix sum (hand-written; no CUB/thrust).
 //
 // Three launches: per-block sums -> one CTA scans the block sums -> per-block rescan
-// with the block's base.  Blocks cover SCAN_ITEMS elements; the middle step loops, so any
+// with the block's base (short in-place scans take a single-CTA shortcut).  Blocks cover SCAN_ITEMS elements; the middle step loops, so any
 // length works.  HBM-bound: reads the input twice, writes it once.
 #pragma once
 
@@ -12,6 +12,7 @@ namespace mtn {
 constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_PER_THREAD = 8;
 constexpr int SCAN_ITEMS = SCAN_THREADS * SCAN_PER_THREAD;
+constexpr int64_t SCAN_SMALL = 16384;  // up to here a single CTA scans in place
 
 template <typename T>
 __device__ __forceinline__ T warp_incl_scan(T x) {
@@ -107,6 +108,12 @@ template <typename TIn, typename T>
 int exclusive_scan(const TIn* in, T* out, int64_t n, void* temp, T* total_dev, cudaStream_t st) {
   if (n <= 0) {
     if (total_dev) MTN_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(T), st));
+    return MTN_OK;
+  }
+  // short in-place scans (brick tables of ordinary cubes): one CTA, one launch
+  if (sizeof(TIn) == sizeof(T) && (const void*)in == (const void*)out && n <= SCAN_SMALL) {
+    scan_sums_inplace<T><<<1, 1024, 0, st>>>(out, n, total_dev);
+    MTN_LAUNCH_CHECK();
     return MTN_OK;
   }
   const int64_t nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
