@@ -7,7 +7,7 @@
 #include "kernel_integrals.cuh"
 #include "plan.cuh"
 #include "project.cuh"
-#if MTN_TILE == 8
+#if MTN_TILE == 8 && !defined(MTN_HOST_EMU)  // (inline PTX throughout: not run by the test emulator)
 #define MTN_HAVE_WS 1
 #include "project_ws.cuh"  // the warp-specialised variant is written for 8 x 8 tiles
 #endif
@@ -129,12 +129,14 @@ static int launch_project_as(const ProjArgs& a, int64_t max_items, cudaStream_t 
   }
   if (classic) {
     const unsigned grid = (unsigned)std::min<int64_t>(max_items, (int64_t)sm_count() * PROJ_CTAS_PER_SM);
-    project_kernel<COUNT, KIND><<<grid, PROJ_THREADS, sizeof(ProjSmem), st>>>(a);
+    auto kfn = project_kernel<COUNT, KIND>;
+    MTN_LAUNCH(kfn, grid, PROJ_THREADS, sizeof(ProjSmem), st, a);
   }
 #ifdef MTN_HAVE_WS
   else {
     const unsigned grid = (unsigned)std::min<int64_t>(max_items, (int64_t)sm_count() * WS_CTAS_PER_SM);
-    project_ws_kernel<COUNT, KIND><<<grid, WS_THREADS, sizeof(WsSmem), st>>>(a);
+    auto kfn = project_ws_kernel<COUNT, KIND>;
+    MTN_LAUNCH(kfn, grid, WS_THREADS, sizeof(WsSmem), st, a);
   }
 #endif
   return MTN_OK;
@@ -375,8 +377,8 @@ int mtn_smoothing_setup(int64_t n, const double* sm_length, const MtnKernelTable
   if (int rc = to_dev_table(table, &t)) return rc;
   if (n < 0 || (n > 0 && !sm_length)) return fail(MTN_ERR_INVALID, "smoothing_setup: bad input%s", "");
   if (n == 0) return MTN_OK;
-  smoothing_setup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      n, sm_length, t, kernel_id_out, valid_out, sm_range_out, h_eff_out);
+  MTN_LAUNCH(smoothing_setup_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, n,
+             sm_length, t, kernel_id_out, valid_out, sm_range_out, h_eff_out);
   MTN_LAUNCH_CHECK();
   return MTN_OK;
 }
@@ -394,10 +396,9 @@ int mtn_prune(int64_t n0, const double* px, const double* py, const double* pz,
     return fail(MTN_ERR_INVALID, "prune: spatial pruning needs px, py, sm_range%s", "");
   if ((flags & MTN_PRUNE_SPECTRAL) && !pz)
     return fail(MTN_ERR_INVALID, "prune: spectral pruning needs pz%s", "");
-  prune_kernel<<<(unsigned)((n0 + 255) / 256), 256, 0, st>>>(
-      n0, px, py, pz, sm_range, mHI, mHI_scalar, half_width, half_width_scalar, max_abs_dv,
-      (double)nx_tot, (double)ny_tot, (double)n_channels, flags, accept_out,
-      (unsigned long long*)n_accept_out);
+  MTN_LAUNCH(prune_kernel, (unsigned)((n0 + 255) / 256), 256, 0, st, n0, px, py, pz, sm_range, mHI,
+             mHI_scalar, half_width, half_width_scalar, max_abs_dv, (double)nx_tot, (double)ny_tot,
+             (double)n_channels, flags, accept_out, (unsigned long long*)n_accept_out);
   MTN_LAUNCH_CHECK();
   return MTN_OK;
 }
@@ -441,20 +442,20 @@ int mtn_plan(const MtnParticles* p, const MtnCube* cube, void* scratch, size_t s
   MTN_CUDA(cudaMemsetAsync(ps.tile_sum, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
   MTN_CUDA(cudaMemsetAsync(ps.tile_cnt, 0, (size_t)n_tiles * sizeof(unsigned int), st));
   if (p->n > 0) {
-    tile_stats_kernel<<<(unsigned)((ps.nblk + TILE_STAT_STRIDE - 1) / TILE_STAT_STRIDE), PLAN_THREADS, 0,
-                        st>>>(make_plan_in(p, cube), g, ps.tile_sum, ps.tile_cnt);
+    MTN_LAUNCH(tile_stats_kernel, (unsigned)((ps.nblk + TILE_STAT_STRIDE - 1) / TILE_STAT_STRIDE),
+               PLAN_THREADS, 0, st, make_plan_in(p, cube), g, ps.tile_sum, ps.tile_cnt);
     MTN_LAUNCH_CHECK();
   }
-  tile_phase_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>(n_tiles, ps.tile_sum, ps.tile_cnt,
-                                                                      ps.tile_phase);
+  MTN_LAUNCH(tile_phase_kernel, (unsigned)((n_tiles + 255) / 256), 256, 0, st, n_tiles, ps.tile_sum,
+             ps.tile_cnt, ps.tile_phase);
   MTN_LAUNCH_CHECK();
   if (p->n > 0) {
-    plan_count_kernel<<<(unsigned)ps.nblk, PLAN_THREADS, 0, st>>>(make_plan_in(p, cube), g, ps.blk_kept,
-                                                                 ps.blk_pairs, ps.totals + 2);
+    MTN_LAUNCH(plan_count_kernel, (unsigned)ps.nblk, PLAN_THREADS, 0, st, make_plan_in(p, cube), g,
+               ps.blk_kept, ps.blk_pairs, ps.totals + 2);
     MTN_LAUNCH_CHECK();
-    scan_sums_inplace<int64_t><<<1, 1024, 0, st>>>(ps.blk_kept, ps.nblk, (int64_t*)ps.totals);
+    MTN_LAUNCH(scan_sums_inplace<int64_t>, 1, 1024, 0, st, ps.blk_kept, ps.nblk, (int64_t*)ps.totals);
     MTN_LAUNCH_CHECK();
-    scan_sums_inplace<int64_t><<<1, 1024, 0, st>>>(ps.blk_pairs, ps.nblk, (int64_t*)ps.totals + 1);
+    MTN_LAUNCH(scan_sums_inplace<int64_t>, 1, 1024, 0, st, ps.blk_pairs, ps.nblk, (int64_t*)ps.totals + 1);
     MTN_LAUNCH_CHECK();
   }
   unsigned long long tot[3];
@@ -509,8 +510,8 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
   for (int k = 1; k <= N_STAGES; ++k) mark(k, st);  // stages skipped below read as 0 ms
 
   if (plan->n_pairs > 0) {
-    plan_emit_kernel<<<(unsigned)ps.nblk, PLAN_THREADS, 0, st>>>(
-        make_plan_in(p, cube), g, ps.blk_kept, ps.blk_pairs, ws.records, ws.pairs_a);
+    MTN_LAUNCH(plan_emit_kernel, (unsigned)ps.nblk, PLAN_THREADS, 0, st, make_plan_in(p, cube), g,
+               ps.blk_kept, ps.blk_pairs, ws.records, ws.pairs_a);
     MTN_LAUNCH_CHECK();
 
     mark(1, st);
@@ -522,12 +523,12 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
       return rc;
 
     mark(2, st);
-    brick_bounds_kernel<<<(unsigned)((plan->n_pairs + 255) / 256), 256, 0, st>>>(
-        sorted, plan->n_pairs, ws.brick_start, ws.brick_count);
+    MTN_LAUNCH(brick_bounds_kernel, (unsigned)((plan->n_pairs + 255) / 256), 256, 0, st, sorted,
+               plan->n_pairs, ws.brick_start, ws.brick_count);
     MTN_LAUNCH_CHECK();
     const unsigned bgrid = (unsigned)((g.n_bricks + 255) / 256);
-    item_count_kernel<<<bgrid, 256, 0, st>>>(ws.brick_count, ws.brick_start, g.n_bricks,
-                                             (uint32_t)plan->chunk, ws.counts, ws.multi, ws.ismulti);
+    MTN_LAUNCH(item_count_kernel, bgrid, 256, 0, st, ws.brick_count, ws.brick_start, g.n_bricks,
+               (uint32_t)plan->chunk, ws.counts, ws.multi, ws.ismulti);
     MTN_LAUNCH_CHECK();
     if (int rc = exclusive_scan<uint32_t, uint32_t>(ws.counts, ws.counts, g.n_bricks, ws.scan_temp,
                                                     ws.scalars + 0, st))
@@ -538,9 +539,8 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
     if (int rc = exclusive_scan<uint32_t, uint32_t>(ws.ismulti, ws.ismulti, g.n_bricks, ws.scan_temp,
                                                     ws.scalars + 2, st))
       return rc;
-    item_fill_kernel<<<bgrid, 256, 0, st>>>(ws.brick_count, ws.brick_start, g.n_bricks,
-                                            (uint32_t)plan->chunk, ws.counts, ws.multi, ws.ismulti,
-                                            ws.items, ws.multis);
+    MTN_LAUNCH(item_fill_kernel, bgrid, 256, 0, st, ws.brick_count, ws.brick_start, g.n_bricks,
+               (uint32_t)plan->chunk, ws.counts, ws.multi, ws.ismulti, ws.items, ws.multis);
     MTN_LAUNCH_CHECK();
 
     ProjArgs a;
@@ -563,8 +563,8 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
     if (int rc = launch_project(a, t.kind[0], g_count_exec != 0, ws.max_items, st)) return rc;
     MTN_LAUNCH_CHECK();
     mark(4, st);
-    reduce_partials_kernel<<<dim3((unsigned)ws.max_multi, SUB_PIX), PROJ_THREADS, 0, st>>>(
-        g, ws.multis, ws.scalars + 2, ws.partials, cube->slab, px_area, zeroed);
+    MTN_LAUNCH(reduce_partials_kernel, dim3((unsigned)ws.max_multi, SUB_PIX), PROJ_THREADS, 0, st, g,
+               ws.multis, ws.scalars + 2, ws.partials, cube->slab, px_area, zeroed);
     MTN_LAUNCH_CHECK();
     if (g_count_exec) {
       MTN_CUDA(cudaMemcpyAsync(g_exec_counts, a.exec_counts, sizeof(g_exec_counts),
@@ -574,8 +574,8 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
   }
   mark(5, st);
   if (!zeroed) {
-    empty_brick_kernel<<<(unsigned)g.n_bricks, PROJ_THREADS, 0, st>>>(g, ws.brick_count, cube->slab,
-                                                                     px_area);
+    MTN_LAUNCH(empty_brick_kernel, (unsigned)g.n_bricks, PROJ_THREADS, 0, st, g, ws.brick_count, cube->slab,
+               px_area);
     MTN_LAUNCH_CHECK();
   }
   mark(6, st);
@@ -618,7 +618,7 @@ int mtn_fp64_peak(double* tflops_out, double* ms_out, void* stream) {
   float best = 1e30f;
   for (int rep = 0; rep < 4; ++rep) {
     MTN_CUDA(cudaEventRecord(e0, st));
-    fp64_peak_kernel<<<blocks, 256, 0, st>>>(d, iters, 0.999999, 1e-7);
+    MTN_LAUNCH(fp64_peak_kernel, blocks, 256, 0, st, d, iters, 0.999999, 1e-7);
     MTN_CUDA(cudaEventRecord(e1, st));
     MTN_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
@@ -650,8 +650,8 @@ int mtn_convolve_beam(const double* cube_in, double* cube_out, int32_t nx, int32
     attr_set = true;
   }
   const dim3 grid((nc + 31) / 32, (ny + 4 * CONV_TY - 1) / (4 * CONV_TY), nx);
-  convolve_beam_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(cube_in, cube_out, nx, ny, nc, kernel,
-                                                                   ka, kb, scale);
+  MTN_LAUNCH(convolve_beam_kernel, grid, 128, smem, (cudaStream_t)stream, cube_in, cube_out, nx, ny, nc,
+             kernel, ka, kb, scale);
   MTN_LAUNCH_CHECK();
   return MTN_OK;
 }
@@ -669,8 +669,8 @@ int mtn_probe_kernel_integral(const MtnKernelEntry* entry, int32_t closed_form, 
   if (!entry || n < 0) return fail(MTN_ERR_INVALID, "probe: bad arguments%s", "");
   if (int rc = ensure_tables()) return rc;
   if (n == 0) return MTN_OK;
-  probe_kernel_integral_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      entry->kind, entry->truncate, entry->norm, closed_form, n, dx, dy, h, w_out);
+  MTN_LAUNCH(probe_kernel_integral_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream,
+             entry->kind, entry->truncate, entry->norm, closed_form, n, dx, dy, h, w_out);
   MTN_LAUNCH_CHECK();
   return MTN_OK;
 }
@@ -682,8 +682,8 @@ int mtn_probe_spectra(int32_t spectrum, int64_t n, const double* v, const double
   if (n == 0) return MTN_OK;
   if (int rc = ensure_tables()) return rc;
   const int64_t tot = n * n_channels;
-  probe_spectra_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      spectrum, n, v, sigma, sigma_scalar, amp, n_channels, edges, s_out);
+  MTN_LAUNCH(probe_spectra_kernel, (unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream, spectrum, n,
+             v, sigma, sigma_scalar, amp, n_channels, edges, s_out);
   MTN_LAUNCH_CHECK();
   return MTN_OK;
 }

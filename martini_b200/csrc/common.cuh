@@ -134,6 +134,18 @@ inline int fail(int code, const char* fmt, const char* a = "", long long b = 0) 
     MTN_CUDA(cudaGetLastError());         \
   } while (0)
 
+// Kernel launch and dynamic shared memory.  MTN_HOST_EMU is defined only by the CPU test
+// suite's SIMT emulator (tests/emu/, never built into libmartini_b200.so), which runs these
+// same kernels as host code to check their logic against the oracle without a GPU.
+#ifdef MTN_HOST_EMU
+#define MTN_LAUNCH MTN_EMU_LAUNCH
+#define MTN_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(mtn_emu::dyn_smem())
+#else
+#define MTN_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define MTN_DYN_SMEM(type, name) extern __shared__ __align__(128) type name[]
+#endif
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 }  // namespace mtn

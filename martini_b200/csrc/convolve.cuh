@@ -19,7 +19,7 @@ constexpr int CONV_MAX_TAPS = 96 * 96;
 __global__ void __launch_bounds__(128) convolve_beam_kernel(
     const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int nc,
     const double* __restrict__ K, int ka, int kb, double scale) {
-  extern __shared__ double sK[];
+  MTN_DYN_SMEM(double, sK);
   for (int i = threadIdx.x; i < ka * kb; i += blockDim.x) sK[i] = K[i];
   __syncthreads();
   // block = 32 channels x 4 y-strips; grid = (channel blocks, y strips of 4*CONV_TY, x)

@@ -33,6 +33,7 @@
 namespace mtn {
 
 // ----------------------------------------------------------------------------- PTX helpers
+#ifndef MTN_HOST_EMU  // (the CPU test suite's emulator, tests/emu/cuda_emu.h, supplies its own)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -58,13 +59,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // bounded spin: a lost transaction traps instead of hanging the GPU
-#pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 26); ++it)
-    if (mbar_try_wait(bar, parity)) return;
-  __trap();
-}
 // global -> shared bulk copy (TMA engine, SASS UBLKCP), completion bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
                                          uint64_t* bar) {
@@ -73,6 +67,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
           "r"(smem_u32(dst_smem)),
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+#endif  // MTN_HOST_EMU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // bounded spin: a lost transaction traps instead of hanging the GPU
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 26); ++it)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
 }
 
 __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t x, int lane) {
@@ -233,7 +235,7 @@ __device__ __forceinline__ int owner_ordinal(uint32_t q0, uint32_t my_start, boo
 // bounds and only the lanes on another entry take the closed forms; KIND = -1: general case.
 template <bool COUNT, int KIND>
 __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel(const ProjArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  MTN_DYN_SMEM(unsigned char, smem_raw);
   ProjSmem& sm = *reinterpret_cast<ProjSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp / N_SUB, sub = warp % N_SUB;  // this warp's channel half and sub-block

@@ -521,7 +521,7 @@ __device__ __forceinline__ void ws_consumer(const ProjArgs& a, WsSmem& sm, const
 // KIND >= 0: every particle uses that tabulated SPH kernel; KIND = -1: the general case.
 template <bool COUNT, int KIND>
 __global__ void __launch_bounds__(WS_THREADS, WS_CTAS_PER_SM) project_ws_kernel(const ProjArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  MTN_DYN_SMEM(unsigned char, smem_raw);
   WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {

@@ -112,17 +112,19 @@ int exclusive_scan(const TIn* in, T* out, int64_t n, void* temp, T* total_dev, c
   }
   // short in-place scans (brick tables of ordinary cubes): one CTA, one launch
   if (sizeof(TIn) == sizeof(T) && (const void*)in == (const void*)out && n <= SCAN_SMALL) {
-    scan_sums_inplace<T><<<1, 1024, 0, st>>>(out, n, total_dev);
+    MTN_LAUNCH(scan_sums_inplace<T>, 1, 1024, 0, st, out, n, total_dev);
     MTN_LAUNCH_CHECK();
     return MTN_OK;
   }
   const int64_t nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
   T* sums = reinterpret_cast<T*>(temp);
-  scan_block_sums<TIn, T><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, sums);
+  auto k_sums = scan_block_sums<TIn, T>;
+  MTN_LAUNCH(k_sums, (unsigned)nb, SCAN_THREADS, 0, st, in, n, sums);
   MTN_LAUNCH_CHECK();
-  scan_sums_inplace<T><<<1, 1024, 0, st>>>(sums, nb, total_dev);
+  MTN_LAUNCH(scan_sums_inplace<T>, 1, 1024, 0, st, sums, nb, total_dev);
   MTN_LAUNCH_CHECK();
-  scan_apply<TIn, T><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, sums, out);
+  auto k_apply = scan_apply<TIn, T>;
+  MTN_LAUNCH(k_apply, (unsigned)nb, SCAN_THREADS, 0, st, in, n, sums, out);
   MTN_LAUNCH_CHECK();
   return MTN_OK;
 }

@@ -85,11 +85,11 @@ inline int radix_sort_pairs(uint64_t* a, uint64_t* b, int64_t n, int key_bits, u
   uint64_t* dst = b;
   for (int bit = 0; bit < key_bits; bit += RADIX_BITS) {
     const int shift = 32 + bit;
-    radix_count_kernel<<<grid, SORT_THREADS, 0, st>>>(src, n, shift, n_chunks, hist);
+    MTN_LAUNCH(radix_count_kernel, grid, SORT_THREADS, 0, st, src, n, shift, n_chunks, hist);
     MTN_LAUNCH_CHECK();
     int rc = exclusive_scan<uint32_t, uint32_t>(hist, hist, n_chunks * RADIX, scan_temp, nullptr, st);
     if (rc) return rc;
-    radix_scatter_kernel<<<grid, SORT_THREADS, 0, st>>>(src, dst, n, shift, n_chunks, hist);
+    MTN_LAUNCH(radix_scatter_kernel, grid, SORT_THREADS, 0, st, src, dst, n, shift, n_chunks, hist);
     MTN_LAUNCH_CHECK();
     uint64_t* t = src;
     src = dst;

@@ -75,14 +75,21 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
         L.load()
 
 
-def test_product_never_imports_oracle():
-    """The product package must not reference oracle/ (a CPU fallback would void parity)."""
+def test_product_never_imports_oracle_or_emulator():
+    """The product package must not reference oracle/ or the CPU test suite's SIMT emulator
+    (tests/emu/): a CPU fallback would void parity.  The only trace of the emulator in the
+    product sources is the MTN_HOST_EMU switch of the launch macro, defined by tests/emu alone."""
     pkg = os.path.join(ROOT, "martini_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 text = open(os.path.join(dirpath, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert not re.search(r"^\s*(from|import)\s+(oracle|tests)\b", text, flags=re.M), f
+                assert "libmartini_emu" not in text and "cuda_emu" not in text.replace("tests/emu/cuda_emu.h", ""), f
+                assert not re.search(r"#\s*define\s+MTN_HOST_EMU", text), f
+    # and the build recipe of the product library never defines the switch
+    entry = open(os.path.join(ROOT, "__graft_entry__.py")).read()
+    assert "MTN_HOST_EMU" not in entry
 
 
 def test_unsupported_plugins_raise():

@@ -1,0 +1,152 @@
+"""The CUDA kernels under the SIMT emulator (tests/emu/), on the CPU: the parity tests of
+tests/test_gpu_parity.py re-run with ``EmuEngine`` -- the same csrc/ sources compiled as host
+code, driven through the same C ABI and the same host classes -- against the golden fixtures
+and the oracle.
+
+This is a logic check that runs where there is no GPU (indexing, predicates, barrier
+placement, arithmetic of every kernel on the hot path); the ``-m gpu`` suite on a B200 remains
+the parity proof.  The emulated library is test infrastructure: the product never loads it.
+"""
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from martini_b200 import synthetic  # noqa: E402
+from martini_b200.pipeline import run_hot_path  # noqa: E402
+from tests import test_gpu_parity as G  # noqa: E402
+from tests.emu import EmuEngine  # noqa: E402
+from tests.parity import check_cube, oracle_hot_path  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = EmuEngine()
+    e.set_schedule("forward")
+    yield e
+    # no kernel may enter a warp collective naming a lane that has already returned
+    assert e.violations() == 0
+
+
+# --- the device functions and the O(N) kernels against the reference's own outputs -----------
+test_kernel_integral_vs_reference = G.test_kernel_integral_vs_reference
+test_tabulated_kernels_match_their_closed_form = G.test_tabulated_kernels_match_their_closed_form
+test_spectra_vs_reference = G.test_spectra_vs_reference
+test_smoothing_setup_bit_exact = G.test_smoothing_setup_bit_exact
+test_prune_bit_exact = G.test_prune_bit_exact
+
+# --- the whole hot path against cubes made by the reference's _insert_source_in_cube ---------
+test_insert_vs_reference_cube = G.test_insert_vs_reference_cube
+test_insert_vs_reference_float32_mode = G.test_insert_vs_reference_float32_mode
+test_empty_and_fully_pruned = G.test_empty_and_fully_pruned
+
+
+def emu_cases():
+    """The seeded cases of the GPU suite at sizes the emulator finishes in seconds."""
+    mk = synthetic.make_case
+    cases = {
+        "cfg2_small": mk("cfg2", n=6000, nx=40, ny=48, nc=64),
+        "cfg2_odd_shape": mk("cfg2", n=3000, nx=37, ny=21, nc=45),
+        "cfg2_one_channel_block_partial": mk("cfg2", n=2000, nx=16, ny=48, nc=7),
+        "cfg2_three_channel_blocks": mk("cfg2", n=3000, nx=24, ny=24, nc=150),
+        "cfg3_thermal": mk("cfg3", n=6000, nx=48, ny=40, nc=64),
+        "cfg4_wide_dirac": mk("cfg4", n=600, nx=48, ny=48, nc=32),
+        "demo": G.SMALL["demo"],
+        "increasing_edges": G.SMALL["increasing_edges"],
+        "dirac_edges": G.SMALL["dirac_edges"],
+    }
+    for name in ("adaptive_wc6", "adaptive_quartic", "adaptive_gauss"):
+        c = dict(G.SMALL[name])
+        for k in ("px", "py", "pz", "sm_length", "v", "mHI", "D"):
+            c[k] = c[k][:2500]
+        cases[name] = c
+    # a crowded brick: more pairs in one brick than a work item holds (multi-chunk bricks,
+    # partial sums reduced in chunk order)
+    crowd = mk("cfg2", n=4000, nx=16, ny=16, nc=32, seed=21)
+    crowd["px"] = 8.0 + 0.2 * (crowd["px"] - crowd["px"].mean())
+    crowd["py"] = 8.0 + 0.2 * (crowd["py"] - crowd["py"].mean())
+    cases["crowded_bricks"] = crowd
+    return cases
+
+
+CASES = emu_cases()
+
+
+def run_and_check(eng, case):
+    out = run_hot_path(eng, case)
+    ref = oracle_hot_path(case)
+    assert np.array_equal(out["accept"].numpy().astype(bool), ref["accept"])
+    assert np.array_equal(out["sm_range"].numpy(), ref["sm_ranges"])
+    if ref["kernel_indices"] is not None:
+        assert np.array_equal(out["kernel_id"].numpy().astype(int), np.maximum(ref["kernel_indices"], 0))
+    assert out["plan"].updates_dense == ref["updates"]
+    assert np.abs(ref["cube"]).max() > 0
+    check_cube(out["cube"].numpy(), ref["cube"])
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_hot_path_vs_oracle(eng, name):
+    run_and_check(eng, CASES[name])
+
+
+def test_crowded_bricks_use_partial_sums(eng):
+    out = run_hot_path(eng, CASES["crowded_bricks"])
+    assert out["plan"].n_pairs > 4 * out["plan"].chunk  # several work items per brick
+
+
+def test_accumulate_into_existing_cube(eng):
+    case = CASES["cfg2_odd_shape"]
+    rng = np.random.Generator(np.random.PCG64(99))
+    cube0 = rng.normal(0.0, 1e-6, case["shape"])
+    out = run_hot_path(eng, case, cube=eng.to_device(cube0.copy()))
+    check_cube(out["cube"].numpy(), oracle_hot_path(case, cube0=cube0)["cube"])
+
+
+def test_slabs_concatenate(eng):
+    case = CASES["cfg2_small"]
+    full = run_hot_path(eng, case)["cube"]
+    nx = case["shape"][0]
+    for bounds in ((0, 13, 29, nx), (0, 1, nx)):
+        parts = [run_hot_path(eng, case, x_lo=a, x_hi=b)["cube"] for a, b in zip(bounds[:-1], bounds[1:])]
+        G.assert_same_cube(torch.cat(parts, dim=0), full)
+
+
+def test_linearity_in_mass(eng):
+    case = dict(CASES["cfg2_odd_shape"])
+    a = run_hot_path(eng, case)["cube"]
+    case["mHI"] = case["mHI"] * 2.0
+    assert torch.equal(run_hot_path(eng, case)["cube"], 2.0 * a)
+
+
+@pytest.mark.parametrize("mode", ("reverse", "shuffle"))
+@pytest.mark.parametrize("name", ("cfg2_odd_shape", "cfg3_thermal", "dirac_edges", "crowded_bricks"))
+def test_result_does_not_depend_on_thread_schedule(eng, name, mode):
+    """The order in which a block's runnable threads take their turns must not change a bit
+    of the result: a missing barrier or a shared-memory race between phases shows up here."""
+    case = CASES[name]
+    eng.set_schedule("forward")
+    want = run_hot_path(eng, case)
+    try:
+        eng.set_schedule(mode, seed=20260117)
+        got = run_hot_path(eng, case)
+    finally:
+        eng.set_schedule("forward")
+    assert torch.equal(got["cube"], want["cube"])
+    assert torch.equal(got["accept"], want["accept"])
+    assert got["plan"].n_pairs == want["plan"].n_pairs
+
+
+def test_beam_convolution_matches_scipy(eng):
+    """mtn_convolve_beam against scipy.signal.fftconvolve, as Martini.convolve_beam
+    uses it per channel (martini.py:863-901)."""
+    from scipy.signal import fftconvolve
+
+    rng = np.random.Generator(np.random.PCG64(5))
+    cube = rng.normal(size=(21, 30, 5))
+    yy, xx = np.meshgrid(np.arange(-4, 5), np.arange(-3, 4))
+    beam = np.exp(-0.5 * ((xx / 1.7) ** 2 + (yy / 2.3) ** 2))
+    out = eng.convolve_beam(eng.to_device(cube), eng.to_device(beam), scale=1.25).numpy()
+    ref = np.stack([fftconvolve(cube[..., c], beam, mode="same") for c in range(cube.shape[2])], axis=-1) * 1.25
+    assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
