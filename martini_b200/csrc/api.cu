@@ -7,7 +7,8 @@
 #include "kernel_integrals.cuh"
 #include "plan.cuh"
 #include "project.cuh"
-#if MTN_TILE == 8 && !defined(MTN_HOST_EMU)  // (inline PTX throughout: not run by the test emulator)
+// (inline PTX throughout: not run by the test emulator; written for the 64-byte record)
+#if MTN_TILE == 8 && !defined(MTN_HOST_EMU) && !MTN_FOOTREC
 #define MTN_HAVE_WS 1
 #include "project_ws.cuh"  // the warp-specialised variant is written for 8 x 8 tiles
 #endif
@@ -465,6 +466,10 @@ int mtn_plan(const MtnParticles* p, const MtnCube* cube, void* scratch, size_t s
   plan->n_pairs = (int64_t)tot[1];
   plan->updates_dense = (int64_t)tot[2];
   plan->n_bricks = g.n_bricks;
+#if MTN_FOOTREC
+  if (cube->n_channels > 65535)
+    return fail(MTN_ERR_LIMIT, "plan: more than 65535 channels%s", "");
+#endif
   if (plan->n_pairs >= (1ll << 32) - 1 || plan->n_kept >= (1ll << 32) - 1)
     return fail(MTN_ERR_LIMIT, "plan: %s%lld pairs exceed the 32-bit sort index; split the slab", "",
                 (long long)plan->n_pairs);

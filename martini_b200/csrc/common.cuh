@@ -56,7 +56,15 @@ constexpr int ERF_DEG = MTN_ERF_DEG;
 static_assert(ERF_DEG % 2 == 1, "rows are read as pairs of coefficients");
 constexpr int ERF_NCOEF = ERF_DEG + 1;  // 10 doubles = 80 B per interval (16-B aligned rows)
 constexpr int ERF_NINT = 6 * ERF_INV_W + 1;
-constexpr int REC_DOUBLES = 8;        // 64-byte particle record
+// MTN_FOOTREC (experimental, default off -- queued for measurement, profiles/README.md): the
+// particle's footprint (candidate box in the slab, live channel window) is computed once, by
+// the plan kernels that need it anyway, and travels in an 80-byte record; the projection
+// kernel's per-batch set-up is then integer clipping -- no candidate-box predicate and no
+// edge search per (particle, brick), one block barrier fewer per batch.
+#ifndef MTN_FOOTREC
+#define MTN_FOOTREC 0
+#endif
+constexpr int REC_DOUBLES = MTN_FOOTREC ? 10 : 8;  // 64-byte (80-byte) particle record
 constexpr int REC_BYTES = REC_DOUBLES * 8;
 
 // erf(x) == 1.0 exactly for x >= ~5.93 (1 - erf(x) < 2^-54); channels whose edges are
@@ -83,10 +91,18 @@ struct __align__(16) Record {
   double v;          // line centre [km/s]
   double inv_s;      // 1 / (sqrt(2) * sigma)   (Gaussian spectrum)
   double amp;        // mHI * D^-2 / 2.36e5  [Jy km/s]
+#if MTN_FOOTREC
+  int32_t i0, i1, j0, j1;     // candidate box clipped to the slab, inclusive (plan.cuh: Foot)
+  uint16_t c_first, c_last;   // live channel window, inclusive (plan.cuh: channel_window)
+  uint8_t kid;                // kernel table index
+  uint8_t pad[3];
+#else
   float r;           // sm_range (integer valued or +inf)
   int32_t kid;       // kernel table index
+#endif
 };
-static_assert(sizeof(Record) == REC_BYTES, "record must be 64 bytes");
+static_assert(sizeof(Record) == REC_BYTES, "record size");
+static_assert(REC_BYTES % 16 == 0, "cp.async.bulk moves multiples of 16 bytes");
 
 // A unit of work for the projection kernel: a contiguous run of one brick's sorted pairs.
 struct __align__(16) Item {

@@ -171,12 +171,8 @@ struct ProjArgs {
 
 constexpr int W_STRIDE = TILE_PIX + 1;  // odd row stride: lane-per-particle reads hit 32 banks
 
-struct ProjSmem {
-  Record rec[2][PBATCH];
-  double W[PBATCH][W_STRIDE];   // kernel integrals, valid inside the particle's box only
-  double ES[PBATCH][CB + 2];    // edge erfs of the live channels (up to CB+1 per particle)
-  double inv_dv[CB];            // (16-byte aligned: read as double2)
-  double edge[CB + 1];
+// What the per-batch set-up leaves for the evaluation and accumulation phases.
+struct SetupBuf {
   uint32_t wprefix[PBATCH + 1];  // exclusive prefix of box areas
   uint32_t eprefix[PBATCH + 1];  // exclusive prefix of edge-run lengths
   float rny[PBATCH];             // 1 / (box height)
@@ -187,6 +183,15 @@ struct ProjSmem {
   uint8_t erun[PBATCH][2];       // first edge to evaluate, number of edges
   uint8_t chan[PBATCH][2];       // live channels of the brick: [cs, ce)
   uint8_t hlive[PBATCH];         // bit h: channel half h of the brick holds a non-zero
+};
+
+struct ProjSmem {
+  Record rec[2][PBATCH];
+  double W[PBATCH][W_STRIDE];   // kernel integrals, valid inside the particle's box only
+  double ES[PBATCH][CB + 2];    // edge erfs of the live channels (up to CB+1 per particle)
+  double inv_dv[CB];            // (16-byte aligned: read as double2)
+  double edge[CB + 1];
+  SetupBuf sb[MTN_FOOTREC >= 2 ? 2 : 1];  // (two: batch b+1 is set up while batch b is evaluated)
   uint64_t bar[2];
   uint32_t item;
 };
@@ -288,15 +293,105 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
       if (tid == 0) mbar_arrive_expect_tx(&sm.bar[buf], nb * REC_BYTES);
     };
 
+#if MTN_FOOTREC
+    // ---- setup, lane = particle: the record carries the particle's footprint (candidate
+    // box in the slab, live channel window; computed once by the plan kernels with the exact
+    // predicates of martini.py:272-274), so the brick's share of it is integer clipping.
+    // Warp 0 turns the box areas into the enumeration prefix / owner list of the kernel
+    // integrals, warp 1 does the same for the edge runs; one barrier.
+    auto setup_from_records = [&](uint32_t bb) {
+      const int nbb = (int)min((uint32_t)PBATCH, n_part - bb * PBATCH);
+      SetupBuf& S = sm.sb[MTN_FOOTREC >= 2 ? (bb & 1u) : 0u];
+      if (warp < 2) {
+        int bx0 = 0, bnx = 0, by0 = 0, bny = 0, cs = 0, ce = 0;
+        if (lane < nbb) {
+          const Record& r = sm.rec[bb & 1u][lane];
+          const int xa = max(r.i0, x0), xb = min(r.i1, x_last);
+          const int ya = max(r.j0, y0), yb = min(r.j1, y_last);
+          if (xa <= xb && ya <= yb) {
+            bx0 = xa - x0;
+            bnx = xb - xa + 1;
+            by0 = ya - y0;
+            bny = yb - ya + 1;
+          }
+          // live channels of the brick [cs, ce): the particle's window cut to the brick
+          cs = max((int)r.c_first - c0, clo);
+          ce = min((int)r.c_last + 1 - c0, nch);
+          if (cs >= ce) cs = ce = 0;
+        }
+        const uint32_t area = (ce > cs) ? (uint32_t)(bnx * bny) : 0u;
+        const uint32_t ne = (area && gaussian_line) ? (uint32_t)(ce - cs + 1) : 0u;
+        const uint32_t lt = (1u << lane) - 1u;
+        if (warp == 0) {
+          S.box[lane][0] = (uint8_t)bx0;
+          S.box[lane][1] = (uint8_t)bnx;
+          S.box[lane][2] = (uint8_t)by0;
+          S.box[lane][3] = (uint8_t)bny;
+          S.rny[lane] = bny ? 1.0f / (float)bny : 0.0f;
+          S.chan[lane][0] = (uint8_t)cs;
+          S.chan[lane][1] = (uint8_t)ce;
+          uint32_t hl = 0;
+#pragma unroll
+          for (int hh = 0; hh < N_HALF; ++hh)
+            if (cs < (hh + 1) * CH_HALF && ce > hh * CH_HALF) hl |= 1u << hh;
+          S.hlive[lane] = (uint8_t)(area ? hl : 0u);
+          const uint32_t wi = warp_incl_scan_u32(area, lane);
+          S.wprefix[lane] = wi - area;
+          if (lane == 31) S.wprefix[32] = wi;
+          const uint32_t wm = __ballot_sync(0xffffffffu, area != 0);
+          if (area != 0) S.wowner[__popc(wm & lt)] = (uint8_t)lane;
+        }
+        if (warp == PROJ_WARPS - 1 || warp == 1) {  // warp 1, or warp 0 again in a 1-warp CTA
+          S.erun[lane][0] = (uint8_t)cs;
+          S.erun[lane][1] = (uint8_t)ne;
+          const uint32_t ei = warp_incl_scan_u32(ne, lane);
+          S.eprefix[lane] = ei - ne;
+          if (lane == 31) S.eprefix[32] = ei;
+          const uint32_t em = __ballot_sync(0xffffffffu, ne != 0);
+          if (ne != 0) S.eowner[__popc(em & lt)] = (uint8_t)lane;
+        }
+      }
+    };
+#endif
+
+#if MTN_FOOTREC >= 2
+    // Two barriers per batch: batch b+1 is set up (by warps 0 and 1, from the records that
+    // landed while batch b-1 was processed) during batch b's evaluation phase, into the other
+    // set-up buffer; the bulk copies of batch b+2 are issued once batch b has released rec[buf].
+    issue(0);
+    if (n_batch > 1) issue(1);
+    __syncthreads();  // edge table visible before the first setup step reads it
+    mbar_wait(&sm.bar[0], phase & 1u);
+    phase ^= 1u;
+    setup_from_records(0);
+    __syncthreads();
+#else
     issue(0);
     __syncthreads();  // edge table visible before the first setup step reads it
+#endif
     for (uint32_t b = 0; b < n_batch; ++b) {
       const uint32_t buf = b & 1u;
       const int nb = (int)min((uint32_t)PBATCH, n_part - b * PBATCH);
+#if MTN_FOOTREC >= 2
+      SetupBuf& S = sm.sb[buf];
+      if (b > 0) {  // every thread observes the completion itself (visibility of rec[buf])
+        mbar_wait(&sm.bar[buf], (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+      }
+      if (warp < 2 && b + 1 < n_batch) {
+        mbar_wait(&sm.bar[buf ^ 1u], (phase >> (buf ^ 1u)) & 1u);  // (parity toggled next iteration)
+        setup_from_records(b + 1);
+      }
+#else
+      SetupBuf& S = sm.sb[0];
       if (b + 1 < n_batch) issue(b + 1);
       mbar_wait(&sm.bar[buf], (phase >> buf) & 1u);
       phase ^= 1u << buf;
 
+#if MTN_FOOTREC
+      setup_from_records(b);
+      __syncthreads();
+#else
       // ---- setup, lane = particle.  Stage 1: the four independent searches (x box, y box,
       // first / last live edge) run on different warps; stage 2: warps 0 and 1 combine them
       // into the live-channel range, the enumeration prefixes and the owner lists. -----------
@@ -329,11 +424,11 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
           }
         }
         if (task < 2) {
-          sm.box[lane][2 * task] = (uint8_t)v0;
-          sm.box[lane][2 * task + 1] = (uint8_t)v1;
-          if (task == 1) sm.rny[lane] = v1 ? 1.0f / (float)v1 : 0.0f;
+          S.box[lane][2 * task] = (uint8_t)v0;
+          S.box[lane][2 * task + 1] = (uint8_t)v1;
+          if (task == 1) S.rny[lane] = v1 ? 1.0f / (float)v1 : 0.0f;
         } else {
-          sm.e01[lane][task - 2] = (uint8_t)v0;
+          S.e01[lane][task - 2] = (uint8_t)v0;
         }
       }
       __syncthreads();
@@ -341,39 +436,42 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         // channel c can be non-zero only if edge c+1 >= e0 and edge c < e1:
         //   Gaussian: some edge of the channel is unsaturated, or the saturation flips in it
         //   Dirac   : lo <= v <= hi, both closed (spectral_models.py:564-569)
-        const int e0 = sm.e01[lane][0], e1 = sm.e01[lane][1];
+        const int e0 = S.e01[lane][0], e1 = S.e01[lane][1];
         int cs = max(e0 - 1, clo), ce = min(e1, nch);
         if (cs >= ce || lane >= nb) cs = ce = 0;
-        const int bnx = sm.box[lane][1], bny = sm.box[lane][3];
+        const int bnx = S.box[lane][1], bny = S.box[lane][3];
         const uint32_t area = (ce > cs && bnx && bny) ? (uint32_t)(bnx * bny) : 0u;
         // edges to evaluate: those of the live channels; none if no pixel is reached
         const uint32_t ne = (area && gaussian_line) ? (uint32_t)(ce - cs + 1) : 0u;
         const uint32_t lt = (1u << lane) - 1u;
         if (warp == 0) {
-          sm.chan[lane][0] = (uint8_t)cs;
-          sm.chan[lane][1] = (uint8_t)ce;
+          S.chan[lane][0] = (uint8_t)cs;
+          S.chan[lane][1] = (uint8_t)ce;
           uint32_t hl = 0;
 #pragma unroll
           for (int hh = 0; hh < N_HALF; ++hh)
             if (cs < (hh + 1) * CH_HALF && ce > hh * CH_HALF) hl |= 1u << hh;
-          sm.hlive[lane] = (uint8_t)(area ? hl : 0u);
+          S.hlive[lane] = (uint8_t)(area ? hl : 0u);
           const uint32_t wi = warp_incl_scan_u32(area, lane);
-          sm.wprefix[lane] = wi - area;
-          if (lane == 31) sm.wprefix[32] = wi;
+          S.wprefix[lane] = wi - area;
+          if (lane == 31) S.wprefix[32] = wi;
           const uint32_t wm = __ballot_sync(0xffffffffu, area != 0);
-          if (area != 0) sm.wowner[__popc(wm & lt)] = (uint8_t)lane;
+          if (area != 0) S.wowner[__popc(wm & lt)] = (uint8_t)lane;
         }
         if (warp == PROJ_WARPS - 1 || warp == 1) {  // warp 1, or warp 0 again in a 1-warp CTA
-          sm.erun[lane][0] = (uint8_t)cs;
-          sm.erun[lane][1] = (uint8_t)ne;
+          S.erun[lane][0] = (uint8_t)cs;
+          S.erun[lane][1] = (uint8_t)ne;
           const uint32_t ei = warp_incl_scan_u32(ne, lane);
-          sm.eprefix[lane] = ei - ne;
-          if (lane == 31) sm.eprefix[32] = ei;
+          S.eprefix[lane] = ei - ne;
+          if (lane == 31) S.eprefix[32] = ei;
           const uint32_t em = __ballot_sync(0xffffffffu, ne != 0);
-          if (ne != 0) sm.eowner[__popc(em & lt)] = (uint8_t)lane;
+          if (ne != 0) S.eowner[__popc(em & lt)] = (uint8_t)lane;
         }
       }
       __syncthreads();
+
+#endif  // MTN_FOOTREC == 1
+#endif  // MTN_FOOTREC >= 2
 
       // ---- phase A: kernel integrals (once per pair) and edge erfs (once per live edge) ---
       // Items are enumerated through the prefix sums; a warp takes 2 x 32 consecutive items
@@ -381,9 +479,9 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
       // rows) and every lane carries two independent dependency chains (the tabulated
       // evaluators are straight-line code, so the two interleave).
       {
-        const uint32_t total = sm.wprefix[PBATCH];
-        const uint32_t my_start = sm.wprefix[lane];
-        const bool my_nonempty = sm.wprefix[lane + 1] > my_start;
+        const uint32_t total = S.wprefix[PBATCH];
+        const uint32_t my_start = S.wprefix[lane];
+        const bool my_nonempty = S.wprefix[lane + 1] > my_start;
 #ifndef MTN_W_CHAINS
 #define MTN_W_CHAINS 2
 #endif
@@ -399,11 +497,11 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
           for (int u = 0; u < NW; ++u) {
             const uint32_t q = q0 + 32 * u + lane;
             ok[u] = q < total;
-            const int p = ok[u] ? sm.wowner[ord[u]] : sm.wowner[0];
-            const uint32_t local = ok[u] ? q - sm.wprefix[p] : 0u;
-            const int ix = (int)(((float)local + 0.5f) * sm.rny[p]);
-            const int iy = (int)local - ix * sm.box[p][3];
-            const int tpx = sm.box[p][0] + ix, tpy = sm.box[p][2] + iy;
+            const int p = ok[u] ? S.wowner[ord[u]] : S.wowner[0];
+            const uint32_t local = ok[u] ? q - S.wprefix[p] : 0u;
+            const int ix = (int)(((float)local + 0.5f) * S.rny[p]);
+            const int iy = (int)local - ix * S.box[p][3];
+            const int tpx = S.box[p][0] + ix, tpy = S.box[p][2] + iy;
             const Record& r = sm.rec[buf][p];
             pp[u] = p;
             pix[u] = tpx * TILE_Y + tpy;
@@ -435,9 +533,9 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         }
       }
       if (gaussian_line) {
-        const uint32_t total = sm.eprefix[PBATCH];
-        const uint32_t my_start = sm.eprefix[lane];
-        const bool my_nonempty = sm.eprefix[lane + 1] > my_start;
+        const uint32_t total = S.eprefix[PBATCH];
+        const uint32_t my_start = S.eprefix[lane];
+        const bool my_nonempty = S.eprefix[lane + 1] > my_start;
         for (uint32_t q0 = warp * 64; q0 < total; q0 += PROJ_WARPS * 64) {
           const int ord[2] = {owner_ordinal(q0, my_start, my_nonempty, lane),
                               owner_ordinal(q0 + 32, my_start, my_nonempty, lane)};
@@ -448,8 +546,8 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
           for (int u = 0; u < 2; ++u) {
             const uint32_t q = q0 + 32 * u + lane;
             ok[u] = q < total;
-            const int p = ok[u] ? sm.eowner[ord[u]] : sm.eowner[0];
-            const int e = ok[u] ? sm.erun[p][0] + (int)(q - sm.eprefix[p]) : 0;
+            const int p = ok[u] ? S.eowner[ord[u]] : S.eowner[0];
+            const int e = ok[u] ? S.erun[p][0] + (int)(q - S.eprefix[p]) : 0;
             const Record& r = sm.rec[buf][p];
             pp[u] = p;
             ee[u] = e;
@@ -472,9 +570,9 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
 
       // ---- warp-private list: which particles touch my sub-block, and on which pixels -----
       uint32_t mymask = 0;
-      if (lane < nb && ((sm.hlive[lane] >> half) & 1u)) {
-        const int bx0 = sm.box[lane][0], bx1 = bx0 + sm.box[lane][1];
-        const int by0 = sm.box[lane][2], by1 = by0 + sm.box[lane][3];
+      if (lane < nb && ((S.hlive[lane] >> half) & 1u)) {
+        const int bx0 = S.box[lane][0], bx1 = bx0 + S.box[lane][1];
+        const int by0 = S.box[lane][2], by1 = by0 + S.box[lane][3];
 #pragma unroll
         for (int j = 0; j < SUB_PIX; ++j) {
           const int tpx = sub_x(sub, j), tpy = sub_y(sub, j);
@@ -503,7 +601,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
       };
       auto load_spec = [&](int p) {
         RawSpec r;
-        r.chan = *reinterpret_cast<const uint16_t*>(sm.chan[p]);
+        r.chan = *reinterpret_cast<const uint16_t*>(S.chan[p]);
         r.amp = sm.rec[buf][p].amp;
         r.eab = *reinterpret_cast<const double2*>(&sm.ES[p][c]);
         r.ec = sm.ES[p][c + 2];
@@ -551,6 +649,9 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         }
       }
       __syncthreads();  // W, ES, boxes and rec[buf] are free again
+#if MTN_FOOTREC >= 2
+      if (b + 2 < n_batch) issue(b + 2);
+#endif
     }
 
     // ---- one store per voxel -------------------------------------------------------------

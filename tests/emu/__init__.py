@@ -29,15 +29,24 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "martini_b200", "csrc")
 LIB = os.path.join(HERE, "libmartini_emu.so")
+
+
+def lib_path(defines=()) -> str:
+    """One emulated library per set of -D switches (experimental kernel variants)."""
+    if not defines:
+        return LIB
+    tag = "_".join(d.replace("=", "").replace("MTN_", "").lower() for d in sorted(defines))
+    return os.path.join(HERE, f"libmartini_emu_{tag}.so")
+
 CUDA_INCLUDE = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
 
-_lib = None
+_libs = {}
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
+def _stale(lib) -> bool:
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     srcs += [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp")]
     srcs.append(os.path.join(ROOT, "include", "martini_b200.h"))
@@ -47,23 +56,24 @@ def _stale() -> bool:
 def build(force: bool = False, defines=()) -> str:
     """g++ build of the emulated library; -ffp-contract=off keeps the explicitly rounded
     predicates (``__dsub_rn`` ...) honest."""
-    if force or _stale():
+    lib = lib_path(defines)
+    if force or _stale(lib):
         cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off",
                "-Wl,-Bsymbolic",  # our cuda* stand-ins, not the libcudart torch has loaded
                *[f"-D{d}" for d in defines],
                "-include", os.path.join(HERE, "cuda_emu.h"), f"-I{CUDA_INCLUDE}", f"-I{HERE}",
                "-x", "c++", os.path.join(CSRC, "api.cu"), os.path.join(HERE, "cuda_emu.cpp"),
-               "-o", LIB]
+               "-o", lib]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("emulator build failed:\n" + res.stdout + res.stderr)
-    return LIB
+    return lib
 
 
-def load():
-    global _lib
-    if _lib is None:
-        lib = C.CDLL(build())
+def load(defines=()):
+    key = tuple(sorted(defines))
+    if key not in _libs:
+        lib = C.CDLL(build(defines=key))
         for name, (restype, argtypes) in L.SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype = restype
@@ -71,15 +81,15 @@ def load():
         lib.mtn_emu_violations.restype = C.c_int
         lib.mtn_emu_set_schedule.argtypes = [C.c_int, C.c_ulonglong]
         lib.mtn_emu_set_schedule.restype = None
-        _lib = lib
-    return _lib
+        _libs[key] = lib
+    return _libs[key]
 
 
 class EmuEngine(Engine):
     """``Engine`` over the emulated library: same host code, CPU tensors, no stream."""
 
-    def __init__(self):  # noqa: D107  (deliberately does not call Engine.__init__: no CUDA here)
-        self.lib = load()
+    def __init__(self, defines=()):  # (deliberately does not call Engine.__init__: no CUDA here)
+        self.lib = load(defines)
         self.device = torch.device("cpu")
         self._scratch = None
         self._workspace = None
