@@ -189,6 +189,10 @@ struct ProjSmem {
   Record rec[2][PBATCH];
   double W[PBATCH][W_STRIDE];   // kernel integrals, valid inside the particle's box only
   double ES[PBATCH][CB + 2];    // edge erfs of the live channels (up to CB+1 per particle)
+#if MTN_GAUSS_SEP
+  double GX[PBATCH][TILE_X];    // Gaussian SPH kernel: erf factor of every box column ...
+  double GY[PBATCH][TILE_Y];    // ... and of every box row
+#endif
   double inv_dv[CB];            // (16-byte aligned: read as double2)
   double edge[CB + 1];
   SetupBuf sb[MTN_FOOTREC >= 2 ? 2 : 1];  // (two: batch b+1 is set up while batch b is evaluated)
@@ -473,6 +477,29 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
 #endif  // MTN_FOOTREC == 1
 #endif  // MTN_FOOTREC >= 2
 
+#if MTN_GAUSS_SEP
+      if (KIND == MTN_KERNEL_GAUSSIAN) {
+        // ---- Gaussian SPH kernel: the separable erf factors of the box columns and rows,
+        // (TILE_X + TILE_Y) per particle, spread statically over the CTA ------------------------
+        for (int idx = tid; idx < PBATCH * (TILE_X + TILE_Y); idx += PROJ_THREADS) {
+          const int p = idx / (TILE_X + TILE_Y), f = idx % (TILE_X + TILE_Y);
+          if (p < nb && S.wprefix[p + 1] > S.wprefix[p]) {
+            const Record& r = sm.rec[buf][p];
+            if (a.table.kind[r.kid] == MTN_KERNEL_GAUSSIAN) {
+              if (f < TILE_X) {
+                if (f >= S.box[p][0] && f < S.box[p][0] + S.box[p][1])
+                  sm.GX[p][f] = gaussian_axis_factor(__dsub_rn(r.px, (double)(x0 + f)), r.h);
+              } else {
+                const int j = f - TILE_X;
+                if (j >= S.box[p][2] && j < S.box[p][2] + S.box[p][3])
+                  sm.GY[p][j] = gaussian_axis_factor(__dsub_rn(r.py, (double)(y0 + j)), r.h);
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+#endif
       // ---- phase A: kernel integrals (once per pair) and edge erfs (once per live edge) ---
       // Items are enumerated through the prefix sums; a warp takes 2 x 32 consecutive items
       // per step, so its lanes mostly share a particle (coherent branches, conflict-free
@@ -513,6 +540,25 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
             ih2[u] = r.inv_h2;
             R2[u] = sq_dist(dx[u], dy[u]) * ih2[u];
           }
+#if MTN_GAUSS_SEP
+          if (KIND == MTN_KERNEL_GAUSSIAN) {
+#pragma unroll
+            for (int u = 0; u < NW; ++u) {
+              if (ok[u]) {
+                const Record& r = sm.rec[buf][pp[u]];
+                const double w =
+                    kind[u] == MTN_KERNEL_GAUSSIAN
+                        ? w_gaussian_sep(dx[u], dy[u], r.h, a.table.truncate[r.kid], a.table.norm[r.kid],
+                                         sm.GX[pp[u]][pix[u] / TILE_Y], sm.GY[pp[u]][pix[u] % TILE_Y])
+                        : kernel_weight_closed(kind[u], dx[u], dy[u], r.h, r.inv_h2,
+                                               a.table.truncate[r.kid], a.table.norm[r.kid]);
+                sm.W[pp[u]][pix[u]] = w;
+                if (COUNT) ++n_w;
+              }
+            }
+            continue;
+          }
+#endif
 #pragma unroll
           for (int u = 0; u < NW; ++u)  // straight-line, both chains in flight together
             tv[u] = wtab_eval(KIND >= 0 ? KIND : (wtab_has(kind[u]) ? kind[u] : MTN_KERNEL_WENDLANDC2), R2[u]) * ih2[u];

@@ -11,6 +11,7 @@ if [ ${#variants[@]} -eq 0 ]; then
     "base="
     "footrec=-DMTN_FOOTREC=1"
     "footrec2=-DMTN_FOOTREC=2"
+    "gauss_sep=-DMTN_GAUSS_SEP=1"
   )
 fi
 for v in "${variants[@]}"; do

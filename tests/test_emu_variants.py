@@ -17,6 +17,8 @@ from tests.emu import EmuEngine  # noqa: E402
 VARIANTS = {
     "footrec": (("MTN_FOOTREC=1",), True),
     "footrec2": (("MTN_FOOTREC=2",), True),
+    "gauss_sep": (("MTN_GAUSS_SEP=1",), True),
+    "footrec2_gauss_sep": (("MTN_FOOTREC=2", "MTN_GAUSS_SEP=1"), True),
 }
 FAST_CASES = ("cfg2_odd_shape", "cfg2_one_channel_block_partial", "cfg3_thermal", "cfg4_wide_dirac",
               "adaptive_gauss", "increasing_edges", "dirac_edges", "crowded_bricks")
