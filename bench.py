@@ -333,7 +333,7 @@ def run_b200(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         plan = out["plan"]
-        bytes_alg = 72.0 * plan.n_pairs + 8.0 * (x_hi - x_lo) * ny * nc
+        bytes_alg = 88.0 * plan.n_pairs + 8.0 * (x_hi - x_lo) * ny * nc
         # DRAM bytes of one launch from the committed ncu --set full capture of this workload
         # (profiles/r1_final_project_kernel.md); only meaningful for the default config at N = 1
         traffic = None

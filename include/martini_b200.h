@@ -172,7 +172,8 @@ size_t mtn_plan_scratch_bytes(int64_t n, const MtnCube* cube);
  * Plan the projection of `p` into `cube`: footprints, live channel windows, brick
  * overlap counts.  Synchronises the stream and fills *plan_host.  Replaces the
  * O(n_pix * N) candidate scan of _evaluate_pixel_spectrum (martini.py:272-274) by an
- * O(N) footprint pass.
+ * O(N) footprint pass.  Limits (MTN_ERR_LIMIT): fewer than 2^32 - 1 (particle, brick)
+ * pairs and kept particles per slab, at most 65535 channels.
  */
 int mtn_plan(const MtnParticles* p, const MtnCube* cube, void* scratch, size_t scratch_bytes,
              MtnPlan* plan_host, void* stream);

@@ -11,7 +11,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmartini_b200.so")
+# MTN_B200_LIB: developer switch -- another build of the same C ABI (an A/B variant from
+# scripts/build_variants.sh); it must export every symbol, or load() raises
+LIB_PATH = os.environ.get("MTN_B200_LIB") or os.path.join(_HERE, "libmartini_b200.so")
 
 MTN_MAX_KERNELS = 8
 

@@ -7,7 +7,7 @@
 #include "kernel_integrals.cuh"
 #include "plan.cuh"
 #include "project.cuh"
-// (inline PTX throughout: not run by the test emulator; written for the 64-byte record)
+// (inline PTX throughout: not run by the test emulator; written for the 64-byte record of MTN_FOOTREC=0)
 #if MTN_TILE == 8 && !defined(MTN_HOST_EMU) && !MTN_FOOTREC
 #define MTN_HAVE_WS 1
 #include "project_ws.cuh"  // the warp-specialised variant is written for 8 x 8 tiles
@@ -97,8 +97,9 @@ static int ensure_tables() {
   return MTN_OK;
 }
 
-// The projection kernel is project.cuh's; MTN_PROJECT=ws selects the warp-specialised variant
-// of project_ws.cuh instead (experimental: correct, but measured slower -- profiles/README.md).
+// The projection kernel is project.cuh's; in a -DMTN_FOOTREC=0 build MTN_PROJECT=ws selects the
+// warp-specialised variant of project_ws.cuh instead (experimental: correct, but measured
+// slower -- profiles/README.md).
 static bool use_classic_project() {
   static int v = -1;
   if (v < 0) {
@@ -115,6 +116,9 @@ static int launch_project_as(const ProjArgs& a, int64_t max_items, cudaStream_t 
 #ifdef MTN_HAVE_WS
   const bool classic = use_classic_project();
 #else
+  if (!use_classic_project())  // asked for, not built: say so instead of running something else
+    return fail(MTN_ERR_INVALID, "MTN_PROJECT=ws: this library was built without the warp-specialised "
+                "kernel (it needs -DMTN_FOOTREC=0, scripts/build_variants.sh)%s", "");
   const bool classic = true;
 #endif
   if (!attr_set[classic]) {

@@ -56,13 +56,18 @@ constexpr int ERF_DEG = MTN_ERF_DEG;
 static_assert(ERF_DEG % 2 == 1, "rows are read as pairs of coefficients");
 constexpr int ERF_NCOEF = ERF_DEG + 1;  // 10 doubles = 80 B per interval (16-B aligned rows)
 constexpr int ERF_NINT = 6 * ERF_INV_W + 1;
-// MTN_FOOTREC (experimental, default off -- queued for measurement, profiles/README.md): the
-// particle's footprint (candidate box in the slab, live channel window) is computed once, by
-// the plan kernels that need it anyway, and travels in an 80-byte record; the projection
-// kernel's per-batch set-up is then integer clipping -- no candidate-box predicate and no
-// edge search per (particle, brick), one block barrier fewer per batch.
+// MTN_FOOTREC: the particle's footprint (candidate box in the slab, live channel window) is
+// computed once, by the plan kernels that need it anyway, and travels in an 80-byte record;
+// the projection kernel's per-batch set-up is then integer clipping -- no candidate-box
+// predicate and no edge search per (particle, brick).
+//   2 (default): batch b+1 is set up by warps 0 / 1 while batch b is evaluated, two block
+//      barriers per batch.  B200, config 2: projection kernel 4.21 -> 4.04 ms, step 4.94 ->
+//      4.78 ms; 115 GPU parity tests green (profiles/README.md, r1_variants.log).
+//   1: set-up in line from the record, three barriers per batch (4.08 ms).
+//   0: 64-byte record, footprint searched per (particle, brick) in the kernel, four barriers
+//      (4.21 ms); the build that also carries the warp-specialised kernel (project_ws.cuh).
 #ifndef MTN_FOOTREC
-#define MTN_FOOTREC 0
+#define MTN_FOOTREC 2
 #endif
 // MTN_GAUSS_SEP (experimental, default off): a projection-kernel instantiation for Gaussian
 // SPH kernels (BASELINE config 4) that evaluates the kernel integral's two separable erf

@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(
   }
 }
 
-// Pass 3 (after the block sums were scanned): write one 64-byte record per kept particle
+// Pass 3 (after the block sums were scanned): write one record (REC_BYTES = 80) per kept particle
 // and one (brick key << 32 | record index) pair per brick it overlaps, in particle order.
 __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
     PlanIn in, Geo g, const int64_t* __restrict__ blk_kept, const int64_t* __restrict__ blk_pairs,

@@ -5,13 +5,15 @@
 // (2l, 2l+1) of the brick, i.e. 16 pixels x 2 channels = 32 float64 accumulators per thread.
 // With the default 8 x 8 tile a CTA is 4 warps and four CTAs share an SM, so one CTA's
 // barrier waits are covered by the others.  The particle records of the brick are gathered
-// into shared memory with cp.async.bulk (one 64-byte bulk copy per record, completion on an
+// into shared memory with cp.async.bulk (one 80-byte bulk copy per record, completion on an
 // mbarrier, double buffered).  Per batch of 32 staged particles:
 //
-//   setup  one lane per particle; the four independent searches (candidate box along x and
-//          y -- martini.py:272-274, exact predicate -- first and last live channel edge)
-//          run on different warps, then warps 0/1 turn them into prefix sums of box areas
-//          and edge-run lengths;
+//   setup  one lane per particle: the record carries the particle's footprint (candidate box
+//          of martini.py:272-274 in the slab, live channel window -- computed once by the
+//          plan kernels with the exact predicates), so warps 0/1 clip it to the brick with
+//          integer arithmetic and turn it into prefix sums of box areas and edge-run lengths,
+//          for batch b+1 while batch b is in phase A (MTN_FOOTREC=2, the default; =0 is the
+//          older set-up that searches box and edges per (particle, brick) on four warps);
 //   A      every (particle, box pixel) pair and every (particle, live edge) pair is handed to
 //          one thread through those prefix sums -- all lanes hold real work, two items per
 //          lane so two dependency chains are in flight -- which evaluates the SPH-kernel

@@ -9,8 +9,8 @@ variants=("$@")
 if [ ${#variants[@]} -eq 0 ]; then
   variants=(
     "base="
-    "footrec=-DMTN_FOOTREC=1"
-    "footrec2=-DMTN_FOOTREC=2"
+    "ws=-DMTN_FOOTREC=0"
+    "footrec1=-DMTN_FOOTREC=1"
     "gauss_sep=-DMTN_GAUSS_SEP=1"
   )
 fi

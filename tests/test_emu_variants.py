@@ -1,7 +1,8 @@
-"""Experimental kernel variants (compile-time switches of csrc/, default off, queued for GPU
-measurement in profiles/README.md) under the SIMT emulator: each must reproduce the oracle and
--- where the variant only moves work around -- the default kernel's cube bit for bit, under
-every thread schedule.  Test infrastructure; see tests/emu/__init__.py.
+"""Kernel variants (compile-time switches of csrc/: the two older footprint set-ups of the
+projection kernel, MTN_FOOTREC=0 / 1, and the experimental MTN_GAUSS_SEP, measurements in
+profiles/README.md) under the SIMT emulator: each must reproduce the oracle and -- where the
+variant only moves work around -- the default kernel's cube bit for bit, under every thread
+schedule.  Test infrastructure; see tests/emu/__init__.py.
 """
 
 import numpy as np
@@ -15,10 +16,10 @@ from tests.emu import EmuEngine  # noqa: E402
 
 #: name -> (switches, bit-identical to the default kernel?)
 VARIANTS = {
-    "footrec": (("MTN_FOOTREC=1",), True),
-    "footrec2": (("MTN_FOOTREC=2",), True),
+    "footrec0": (("MTN_FOOTREC=0",), True),
+    "footrec1": (("MTN_FOOTREC=1",), True),
     "gauss_sep": (("MTN_GAUSS_SEP=1",), True),
-    "footrec2_gauss_sep": (("MTN_FOOTREC=2", "MTN_GAUSS_SEP=1"), True),
+    "footrec0_gauss_sep": (("MTN_FOOTREC=0", "MTN_GAUSS_SEP=1"), True),
 }
 FAST_CASES = ("cfg2_odd_shape", "cfg2_one_channel_block_partial", "cfg3_thermal", "cfg4_wide_dirac",
               "adaptive_gauss", "increasing_edges", "dirac_edges", "crowded_bricks")

@@ -394,11 +394,21 @@ def test_cfg4_wide_footprints_midsize(eng):
 @pytest.mark.parametrize("name", ("cfg2_small", "cfg3_thermal", "dirac_edges"))
 def test_warp_specialised_variant_matches(eng, name, tmp_path):
     """The opt-in MTN_PROJECT=ws kernel (csrc/project_ws.cuh) against the oracle and the default
-    kernel.  The switch is read once per process, so the variant runs in a child process."""
+    kernel.  It is written for the 64-byte record, i.e. lives in the -DMTN_FOOTREC=0 build
+    (martini_b200/lib_var_ws.so, scripts/build_variants.sh; built here if nvcc is at hand).
+    The switch is read once per process, so the variant runs in a child process."""
     import pickle
+    import shutil
     import subprocess
     import sys
 
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ws_lib = os.path.join(root, "martini_b200", "lib_var_ws.so")
+    if not os.path.exists(ws_lib):
+        if shutil.which("nvcc") is None:
+            pytest.skip("lib_var_ws.so not built and no nvcc here (scripts/build_variants.sh ws=-DMTN_FOOTREC=0)")
+        subprocess.run(["bash", os.path.join(root, "scripts", "build_variants.sh"), "ws=-DMTN_FOOTREC=0"],
+                       check=True, cwd=root, timeout=600)
     case = SMALL[name]
     case_file, out_file = tmp_path / "case.pkl", tmp_path / "cube.npy"
     case_file.write_bytes(pickle.dumps(case))
@@ -410,8 +420,7 @@ def test_warp_specialised_variant_matches(eng, name, tmp_path):
         "out = run_hot_path(Engine('cuda:0'), case)\n"
         "np.save(sys.argv[2], out['cube'].cpu().numpy())\n"
     )
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, MTN_PROJECT="ws", PYTHONPATH=root)
+    env = dict(os.environ, MTN_PROJECT="ws", MTN_B200_LIB=ws_lib, PYTHONPATH=root)
     subprocess.run([sys.executable, "-c", code, str(case_file), str(out_file)], check=True, env=env,
                    cwd=root, timeout=300)
     ws = np.load(out_file)
