@@ -1,6 +1,7 @@
 // C ABI of libmartini_b200.so -- see include/martini_b200.h for the contract.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 #include "convolve.cuh"
@@ -58,24 +59,35 @@ static int to_dev_table(const MtnKernelTable* t, KernelTableDev* d) {
   return MTN_OK;
 }
 
+// Per-device one-time state (a process may drive several GPUs, one host thread each):
+// function attributes and __device__ / __constant__ tables belong to the device that was
+// current when they were set.
+constexpr int MAX_DEVICES = 64;
+static std::mutex g_once_mutex;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
+}
+
 static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[MAX_DEVICES] = {0};
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(g_once_mutex);
+  if (!n[dev]) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 // Fill the device tables (erf, kernel integrals) once per device; see tables_host.hpp.
 static double g_table_err[WT_KINDS] = {0};
 static int ensure_tables() {
-  static bool done[64] = {false};
-  int dev = 0;
-  MTN_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && done[dev]) return MTN_OK;
+  static bool done[MAX_DEVICES] = {false};
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(g_once_mutex);
+  if (done[dev]) return MTN_OK;
   static double erf_tab_host[ERF_NINT * ERF_NCOEF];
   static HostTables T;
   static bool built = false;
@@ -93,7 +105,7 @@ static int ensure_tables() {
   MTN_CUDA(cudaMemcpyToSymbol(c_wscale, T.scale, sizeof(T.scale)));
   MTN_CUDA(cudaMemcpyToSymbol(c_wend, T.end, sizeof(T.end)));
   MTN_CUDA(cudaMemcpyToSymbol(g_wtab_rows, T.rows.data(), T.rows.size() * sizeof(double)));
-  if (dev >= 0 && dev < 64) done[dev] = true;
+  done[dev] = true;
   return MTN_OK;
 }
 
@@ -112,7 +124,8 @@ static bool use_classic_project() {
 // One instantiation per (diagnostic counting, uniform kernel kind).
 template <bool COUNT, int KIND>
 static int launch_project_as(const ProjArgs& a, int64_t max_items, cudaStream_t st) {
-  static bool attr_set[2] = {false, false};
+  static bool attr_set_dev[MAX_DEVICES][2] = {{false, false}};
+  bool* attr_set = attr_set_dev[current_device()];
 #ifdef MTN_HAVE_WS
   const bool classic = use_classic_project();
 #else
@@ -121,16 +134,19 @@ static int launch_project_as(const ProjArgs& a, int64_t max_items, cudaStream_t 
                 "kernel (it needs -DMTN_FOOTREC=0, scripts/build_variants.sh)%s", "");
   const bool classic = true;
 #endif
-  if (!attr_set[classic]) {
-    if (classic)
-      MTN_CUDA(cudaFuncSetAttribute(project_kernel<COUNT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sizeof(ProjSmem)));
+  {
+    std::lock_guard<std::mutex> lock(g_once_mutex);
+    if (!attr_set[classic]) {
+      if (classic)
+        MTN_CUDA(cudaFuncSetAttribute(project_kernel<COUNT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(ProjSmem)));
 #ifdef MTN_HAVE_WS
-    else
-      MTN_CUDA(cudaFuncSetAttribute(project_ws_kernel<COUNT, KIND>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSmem)));
+      else
+        MTN_CUDA(cudaFuncSetAttribute(project_ws_kernel<COUNT, KIND>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSmem)));
 #endif
-    attr_set[classic] = true;
+      attr_set[classic] = true;
+    }
   }
   if (classic) {
     const unsigned grid = (unsigned)std::min<int64_t>(max_items, (int64_t)sm_count() * PROJ_CTAS_PER_SM);
@@ -655,11 +671,15 @@ int mtn_convolve_beam(const double* cube_in, double* cube_out, int32_t nx, int32
       (int64_t)ka * kb > CONV_MAX_TAPS)
     return fail(MTN_ERR_INVALID, "convolve_beam: bad shape (beam image must be odd x odd, <= 96 x 96)%s", "");
   const size_t smem = (size_t)ka * kb * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MTN_CUDA(cudaFuncSetAttribute(convolve_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(CONV_MAX_TAPS * sizeof(double))));
-    attr_set = true;
+  static bool attr_set[MAX_DEVICES] = {false};
+  {
+    std::lock_guard<std::mutex> lock(g_once_mutex);
+    const int dev = current_device();
+    if (!attr_set[dev]) {
+      MTN_CUDA(cudaFuncSetAttribute(convolve_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(CONV_MAX_TAPS * sizeof(double))));
+      attr_set[dev] = true;
+    }
   }
   const dim3 grid((nc + 31) / 32, (ny + 4 * CONV_TY - 1) / (4 * CONV_TY), nx);
   MTN_LAUNCH(convolve_beam_kernel, grid, 128, smem, (cudaStream_t)stream, cube_in, cube_out, nx, ny, nc,
