@@ -168,6 +168,10 @@ static int launch_project_count(const ProjArgs& a, int primary_kind, int64_t max
   switch (primary_kind) {
     case MTN_KERNEL_WENDLANDC2: return launch_project_as<COUNT, MTN_KERNEL_WENDLANDC2>(a, max_items, st);
     case MTN_KERNEL_CUBICSPLINE: return launch_project_as<COUNT, MTN_KERNEL_CUBICSPLINE>(a, max_items, st);
+#if MTN_WTAB_MORE
+    case MTN_KERNEL_WENDLANDC6: return launch_project_as<COUNT, MTN_KERNEL_WENDLANDC6>(a, max_items, st);
+    case MTN_KERNEL_QUARTICSPLINE: return launch_project_as<COUNT, MTN_KERNEL_QUARTICSPLINE>(a, max_items, st);
+#endif
 #if MTN_GAUSS_SEP
     case MTN_KERNEL_GAUSSIAN: return launch_project_as<COUNT, MTN_KERNEL_GAUSSIAN>(a, max_items, st);
 #endif

@@ -4,8 +4,9 @@
 // (csrc/tables_host.hpp) and accurate to a few 1e-16 -- the level of libm itself:
 //
 //  * erf: Taylor coefficients about the centres of 1/16-wide intervals on [0, 6);
-//  * pixel-integrated SPH kernels W(R^2) for the kernels whose closed form costs a log and
-//    two square roots (Wendland C2, cubic spline): piecewise degree-9 polynomials in R^2 on
+//  * pixel-integrated SPH kernels W(R^2) for the kernels whose closed form costs logs and
+//    square roots (Wendland C2, cubic spline; with MTN_WTAB_MORE also Wendland C6 and the
+//    quartic spline): piecewise degree-9 polynomials in R^2 on
 //    intervals refined towards the points where the closed form is not analytic (below).
 //    ~35 straight-line instructions instead of ~145 branchy ones, and two evaluations
 //    interleave (the projection kernel evaluates two pixels per lane).
@@ -54,9 +55,21 @@ __device__ __forceinline__ double erf_tab(double t) {
 // zone below), so only the ten coefficients are loaded.
 constexpr int WT_DEG = 9;
 constexpr int WT_ROW = 12;          // c0..c9 (in t = u - centre), interval centre, unused
-constexpr int WT_MAX_ZONES = 4;
+// MTN_WTAB_MORE: tables for Wendland C6 and the quartic spline too (their closed forms cost
+// ~350 instructions: 40-term polynomials, a log or up to three asinh, up to four square
+// roots); 0 restores the closed forms on the device for an A/B.
+#ifndef MTN_WTAB_MORE
+#define MTN_WTAB_MORE 1
+#endif
+constexpr int WT_MAX_ZONES = MTN_WTAB_MORE ? 6 : 4;
 constexpr int WT_KINDS = 6;         // indexed by MTN_KERNEL_*
-constexpr int WT_MAX_ROWS = 2048;
+constexpr int WT_MAX_ROWS = MTN_WTAB_MORE ? 4096 : 2048;
+// zones of a kind (compile-time kinds fold the zone search to the compares they need)
+__host__ __device__ constexpr int wtab_zones_of(int kind) {
+  return kind == MTN_KERNEL_WENDLANDC2 || kind == MTN_KERNEL_WENDLANDC6 ? 2
+         : kind == MTN_KERNEL_CUBICSPLINE                                ? 4
+                                                                         : WT_MAX_ZONES;
+}
 constexpr int WT_SUB_BITS = 3;      // 8 intervals per octave
 
 struct WZone {
@@ -84,7 +97,8 @@ __device__ __forceinline__ double wtab_eval(int kind, double R2) {
   const double s = R2 * c_wscale[kind];
   int z = 0;
 #pragma unroll
-  for (int k = 1; k < WT_MAX_ZONES; ++k) z += s >= c_wzone[kind][k].s_lo ? 1 : 0;
+  for (int k = 1; k < WT_MAX_ZONES; ++k)
+    if (k < wtab_zones_of(kind)) z += s >= c_wzone[kind][k].s_lo ? 1 : 0;
   const WZone& zn = c_wzone[kind][z];
   const double u = fabs(s - zn.anchor);
   const int idx = min(max((__double2hiint(u) >> (20 - WT_SUB_BITS)) + zn.off, zn.row0), zn.last);

@@ -57,6 +57,60 @@ static ld F_cubic_spline(ld anchor, ld ds) {
   return scale * 0.25L * I2;
 }
 
+// _WendlandC6Kernel._kernel_integral * h^2 (sph_kernels.py:575-685), s = R^2.  The reference's
+// antiderivative regrouped as P(z) + q Q(z) + L (7.21875 R^12 + 173.25 R^10 + 288.75 R^8), P and
+// Q odd polynomials in z with polynomial coefficients in R^2 (the same regrouping as the
+// device's c6_indef, kernel_integrals.cuh).  Its decimal coefficients are the reference's
+// float64 literals (24.7813, 128 + 1/3, ...: rounded in float64 first, as Python does).
+static ld F_wendland_c6(ld anchor, ld ds) {
+  const ld s = anchor + ds, om = (1.0L - anchor) - ds;  // R^2, 1 - R^2
+  if (om <= 0.0L) return 0.0L;
+  const ld norm = (ld)(1365.0 / 64.0) / PI_L;
+  if (s <= 0.0L) return norm * 2.0L * (ld)(4.0 / 15.0);
+  const ld z = sqrtl(om), z2 = z * z, q = sqrtl(s + z2), L = logl(q + z);
+  const ld R2 = s, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4, R10 = R8 * R2, R12 = R8 * R4;
+  const ld p1 = 1.0L - 11.0L * R2 + 66.0L * R4 - 462.0L * R6 - 1155.0L * R8 - 231.0L * R10;
+  const ld p3 = -(ld)(11.0 / 3.0) + 44.0L * R2 - 462.0L * R4 - 1540.0L * R6 - 385.0L * R8;
+  const ld p5 = (ld)13.2 - (ld)277.2 * R2 - 1386.0L * R4 - 462.0L * R6;
+  const ld p7 = -66.0L - 660.0L * R2 - 330.0L * R4;
+  const ld p9 = -(ld)(128.0 + 1.0 / 3.0) * (1.0L + R2);
+  const ld p11 = -21.0L;
+  const ld P = z * (p1 + z2 * (p3 + z2 * (p5 + z2 * (p7 + z2 * (p9 + z2 * p11)))));
+  const ld q1 = (ld)24.7813 * R10 + (ld)530.75 * R8 + (ld)767.25 * R6;
+  const ld q3 = (ld)47.4792 * R8 + (ld)819.5 * R6 + (ld)896.5 * R4;
+  const ld q5 = (ld)58.0167 * R6 + (ld)752.4 * R4 + 550.0L * R2;
+  const ld q7 = (ld)41.7 * R4 + (ld)360.8 * R2 + 132.0L;
+  const ld q9 = (ld)(16.0 + 4.0 / 15.0) * R2 + (ld)70.4;
+  const ld q11 = (ld)(8.0 / 3.0);
+  const ld Q = z * (q1 + z2 * (q3 + z2 * (q5 + z2 * (q7 + z2 * (q9 + z2 * q11)))));
+  const ld logs = (ld)7.21875 * R12 + (ld)173.25 * R10 + (ld)288.75 * R8;
+  const ld up = P + q * Q + L * logs;      // indef(R, zmax)
+  const ld lo = 0.5L * logl(s) * logs;     // indef(R, 0): q = R, L = log R, every z power gone
+  return norm * 2.0L * (up - lo);
+}
+
+// _QuarticSplineKernel._kernel_integral * h^2 (sph_kernels.py:1516-1564), s = R^2.  The three
+// IA pieces end at R = A = 0.2, 0.6, 1 (float64 values, as are the reference's A**2 under
+// the square roots); `piece` = how many of them are switched on is fixed per zone by the
+// caller through the zone's bounds, here it follows from the sign of A^2 - s.
+static ld F_quartic_spline(ld anchor, ld ds) {
+  const ld s = anchor + ds;
+  if ((1.0L - anchor) - ds <= 0.0L) return 0.0L;
+  const ld pref = 2.0L * (ld)(15625.0 / 512.0) / PI_L;
+  if (s <= 0.0L) return pref * (ld)(384.0 / 3125.0);
+  const ld R = sqrtl(s);
+  auto IA = [&](double Ad, double A2d) -> ld {
+    const ld A = (ld)Ad, z2 = ((ld)A2d - anchor) - ds;  // A^2 - R^2 with the zone's precision
+    if (z2 <= 0.0L) return 0.0L;                      // piece switched off (R >= A)
+    const ld z = sqrtl(z2), q = sqrtl(z2 + s), A2 = A * A;
+    return A2 * A2 * z - 2.0L * A2 * A * z * q + 2.0L * A2 * z * (3.0L * s + z2) -
+           A * s * (4.0L * A2 + 3.0L * s) * asinhl(z / R) / 2.0L -
+           A * z * q * (5.0L * s + 2.0L * z2) / 2.0L + s * s * z + 2.0L * s * z2 * z / 3.0L +
+           z2 * z2 * z / 5.0L;
+  };
+  return pref * (10.0L * IA(0.2, 0.2 * 0.2) - 5.0L * IA(0.6, 0.6 * 0.6) + IA(1.0, 1.0));
+}
+
 // --------------------------------------------------------------------------------- fitting
 // Degree-WT_DEG Chebyshev interpolant of g(u) = f(anchor, dir * u) on u in [a, b], returned as
 // monomial coefficients in t = u - centre (unscaled: the half-widths are powers of two, so
@@ -103,6 +157,15 @@ struct ZoneSpec {
   ld s_lo, s_hi, anchor;
   int kmin;
 };
+
+// core-interval exponents of the Wendland C6 / quartic spline zones (u < 2^-k is one interval)
+#ifndef WTAB_C6_K0
+#define WTAB_C6_K0 20
+#define WTAB_C6_K1 54
+#define WTAB_Q_K0 10
+#define WTAB_Q_KNOT 12
+#define WTAB_Q_UP 8
+#endif
 
 struct HostTables {
   WZone zone[WT_KINDS][WT_MAX_ZONES];
@@ -220,6 +283,20 @@ static HostTables build_kernel_tables() {
   // (4 - s)^(7/2) at the edge
   build_kind(T, MTN_KERNEL_CUBICSPLINE, 4.0, F_cubic_spline,
              {{0.0L, 0.5L, 0.0L, 28}, {0.5L, 1.0L, 1.0L, 54}, {1.0L, 2.5L, 1.0L, 6}, {2.5L, 4.0L, 4.0L, 16}});
+#if MTN_WTAB_MORE
+  // Wendland C6: s^4 log s at 0, (1 - s)^(17/2) at the edge
+  build_kind(T, MTN_KERNEL_WENDLANDC6, 1.0, F_wendland_c6,
+             {{0.0L, 0.5L, 0.0L, WTAB_C6_K0}, {0.5L, 1.0L, 1.0L, WTAB_C6_K1}});
+  // quartic spline: analytic at 0 (the s log s terms of its three pieces cancel) and between
+  // its knots; (A^2 - s)^(9/2) below each of s = A^2 = 0.04, 0.36, 1, nothing of that piece
+  // above -- one zone on either side of the two inner knots
+  {
+    const ld k1 = (ld)(0.2 * 0.2), k2 = (ld)(0.6 * 0.6);
+    build_kind(T, MTN_KERNEL_QUARTICSPLINE, 1.0, F_quartic_spline,
+               {{0.0L, 0.02L, 0.0L, WTAB_Q_K0}, {0.02L, k1, k1, WTAB_Q_KNOT}, {k1, 0.2L, k1, WTAB_Q_UP},
+                {0.2L, k2, k2, WTAB_Q_KNOT}, {k2, 0.68L, k2, WTAB_Q_UP}, {0.68L, 1.0L, 1.0L, WTAB_Q_KNOT}});
+  }
+#endif
   return T;
 }
 

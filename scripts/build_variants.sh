@@ -12,6 +12,7 @@ if [ ${#variants[@]} -eq 0 ]; then
     "ws=-DMTN_FOOTREC=0"
     "footrec1=-DMTN_FOOTREC=1"
     "gauss_sep=-DMTN_GAUSS_SEP=1"
+    "wtab_more0=-DMTN_WTAB_MORE=0"
   )
 fi
 for v in "${variants[@]}"; do

@@ -20,6 +20,9 @@ VARIANTS = {
     "footrec1": (("MTN_FOOTREC=1",), True),
     "gauss_sep": (("MTN_GAUSS_SEP=1",), True),
     "footrec0_gauss_sep": (("MTN_FOOTREC=0", "MTN_GAUSS_SEP=1"), True),
+    # closed forms instead of tables for Wendland C6 / quartic spline (none of FAST_CASES uses
+    # them as primary kernel, so the cubes are bit-identical; the switch must keep building)
+    "wtab_more0": (("MTN_WTAB_MORE=0",), True),
 }
 FAST_CASES = ("cfg2_odd_shape", "cfg2_one_channel_block_partial", "cfg3_thermal", "cfg4_wide_dirac",
               "adaptive_gauss", "increasing_edges", "dirac_edges", "crowded_bricks")

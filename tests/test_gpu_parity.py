@@ -83,14 +83,21 @@ def test_kernel_integral_vs_reference(eng, tag):
     assert np.abs(w[big] / ref[big] - 1).max() < 1e-9
 
 
-@pytest.mark.parametrize("tag", ("_WendlandC2Kernel", "_CubicSplineKernel"))
+@pytest.mark.parametrize("tag", ("_WendlandC2Kernel", "_CubicSplineKernel", "_WendlandC6Kernel",
+                                 "_QuarticSplineKernel"))
 def test_tabulated_kernels_match_their_closed_form(eng, tag):
-    """Wendland C2 and the cubic spline are evaluated from piecewise-polynomial tables built
-    from the reference's closed forms in extended precision (csrc/tables_host.hpp); the table
-    must agree with the closed form evaluated on the device to 1e-13 of the kernel peak."""
+    """Wendland C2 / C6, the cubic and the quartic spline are evaluated from piecewise-polynomial
+    tables built from the reference's closed forms in extended precision
+    (csrc/tables_host.hpp); the table must agree with the closed form evaluated on the device
+    to 1e-13 of the kernel peak (Wendland C6: 5e-12 -- its 40-term closed form cancels from
+    terms of ~1e3 down to the result, so the float64 evaluation the table is compared with
+    carries ~1e-12 of rounding noise itself; against the reference's own output the table is
+    as close as the device's closed form, test_kernel_integral_vs_reference)."""
     name, kw = PRIMS[tag]
     k = getattr(K, name)(**kw)
-    assert 0 < eng.table_error(k._kind) < 2e-14  # worst fit error found when the table was built
+    # worst fit error found when the table was built; Wendland C6: 1.7e-14 at R = 0 exactly,
+    # where the reference returns a special value that its own formula's limit misses by that
+    assert 0 < eng.table_error(k._kind) < {"_WendlandC6Kernel": 5e-14}.get(tag, 2e-14)
     rng = np.random.Generator(np.random.PCG64(77))
     n = 200000
     h = rng.uniform(0.5, 20.0, n)
@@ -100,7 +107,7 @@ def test_tabulated_kernels_match_their_closed_form(eng, tag):
     tab = eng.probe_kernel_integral(k._entry(), dx, dy, h).cpu().numpy()
     closed = eng.probe_kernel_integral(k._entry(), dx, dy, h, closed_form=True).cpu().numpy()
     scale = (closed * h * h).max()
-    assert np.abs((tab - closed) * h * h).max() <= 1e-13 * scale
+    assert np.abs((tab - closed) * h * h).max() <= (5e-12 if tag == "_WendlandC6Kernel" else 1e-13) * scale
     assert np.array_equal(tab != 0, closed != 0)
     assert eng.table_error(K.DiracDeltaKernel._kind) == 0.0  # no table: closed form is used
 
