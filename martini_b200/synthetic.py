@@ -48,8 +48,10 @@ def disc(rng, n, r_d, incl_deg, centre):
 
 def make_case(name, n=None, nx=None, ny=None, nc=None, seed=None):
     """Build a named workload (optionally rescaled through n / nx / ny / nc)."""
-    if name in ("cfg2", "smoke"):
+    if name in ("cfg2", "smoke", "cfg2c6", "cfg2q"):
         # config 2: 1e6 particles, 256x256x128, WendlandC2Kernel + GaussianSpectrum(7 km/s)
+        # (cfg2c6 / cfg2q: the same source with WendlandC6Kernel / QuarticSplineKernel, for
+        # timing the kernels BASELINE.json names no config for)
         n = n or 1_000_000
         nx, ny, nc = nx or 256, ny or 256, nc or 128
         seed = 20260002 if seed is None else seed
@@ -64,7 +66,8 @@ def make_case(name, n=None, nx=None, ny=None, nc=None, seed=None):
             "name": name, "px": x, "py": y, "sm_length": h, "v": v, "sigma": 7.0,
             "mHI": (1.0e9 / n) * (1.0 + 0.01 * rng.uniform(-0.5, 0.5, n)),
             "D": np.full(n, 10.0), "edges": channel_edges(nc, 4.0), "shape": (nx, ny, nc),
-            "kernel": ("WendlandC2Kernel", {}), "spectrum": "gaussian",
+            "kernel": ({"cfg2c6": "WendlandC6Kernel", "cfg2q": "QuarticSplineKernel"}.get(name, "WendlandC2Kernel"), {}),
+            "spectrum": "gaussian",
         }
         return _finish(case, rng)
     if name == "cfg3":
