@@ -175,7 +175,9 @@ def load():
     return lib
 
 
-def check(rc: int, what: str) -> None:
+def check(rc: int, what: str, lib=None) -> None:
+    """Raise with the message of the library that made the call (``lib``; default: the one
+    ``load()`` returns)."""
     if rc != 0:
-        msg = load().mtn_last_error().decode(errors="replace")
+        msg = (lib or load()).mtn_last_error().decode(errors="replace")
         raise MartiniB200Error(f"{what} failed (code {rc}): {msg}")

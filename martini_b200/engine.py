@@ -74,6 +74,9 @@ class Engine:
         self.last_launches = 0
 
     # ------------------------------------------------------------------ helpers
+    def _check(self, rc, what):
+        L.check(rc, what, self.lib)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -97,7 +100,7 @@ class Engine:
 
     def device_info(self):
         sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
-        L.check(self.lib.mtn_device_info(C.byref(sm), C.byref(ma), C.byref(mi)), "mtn_device_info")
+        self._check(self.lib.mtn_device_info(C.byref(sm), C.byref(ma), C.byref(mi)), "mtn_device_info")
         return {"sm_count": sm.value, "cc": (ma.value, mi.value)}
 
     # ------------------------------------------------------------------ K0 / K1
@@ -109,7 +112,7 @@ class Engine:
         rng = torch.empty(n, dtype=torch.float64, device=self.device)
         heff = torch.empty(n, dtype=torch.float64, device=self.device)
         tc = table.to_c()
-        L.check(
+        self._check(
             self.lib.mtn_smoothing_setup(n, _ptr(sm_length), C.byref(tc), _ptr(kid), _ptr(valid),
                                          _ptr(rng), _ptr(heff), self._stream()),
             "mtn_smoothing_setup",
@@ -126,7 +129,7 @@ class Engine:
         count = torch.zeros((), dtype=torch.int64, device=self.device)
         flags = (L.PRUNE_SPATIAL if spatial else 0) | (L.PRUNE_SPECTRAL if spectral else 0) | (
             L.PRUNE_MASS if mass else 0)
-        L.check(
+        self._check(
             self.lib.mtn_prune(n, _ptr(px), _ptr(py), _ptr(pz), _ptr(sm_range), _ptr(mt), ms,
                                _ptr(ht), hs, float(max_abs_dv), int(nx_tot), int(ny_tot),
                                int(n_channels), flags, _ptr(accept), _ptr(count), self._stream()),
@@ -176,10 +179,10 @@ class Engine:
         sbytes = self.lib.mtn_plan_scratch_bytes(n, C.byref(c))
         scratch = self._grow("_scratch", sbytes)
         plan = L.MtnPlan()
-        L.check(self.lib.mtn_plan(C.byref(p), C.byref(c), _ptr(scratch), scratch.numel(),
+        self._check(self.lib.mtn_plan(C.byref(p), C.byref(c), _ptr(scratch), scratch.numel(),
                                   C.byref(plan), stream), "mtn_plan")
         ws = self._grow("_workspace", plan.workspace_bytes)
-        L.check(self.lib.mtn_project(C.byref(p), C.byref(tc), C.byref(c), C.byref(plan),
+        self._check(self.lib.mtn_project(C.byref(p), C.byref(tc), C.byref(c), C.byref(plan),
                                      _ptr(scratch), scratch.numel(), _ptr(ws), ws.numel(), stream),
                 "mtn_project")
         self.last_plan = plan
@@ -193,7 +196,7 @@ class Engine:
         assert cube.ndim == 3 and cube.dtype == torch.float64 and cube.is_contiguous()
         kernel = self.to_device(kernel)
         out = torch.empty_like(cube)
-        L.check(self.lib.mtn_convolve_beam(_ptr(cube), _ptr(out), cube.shape[0], cube.shape[1],
+        self._check(self.lib.mtn_convolve_beam(_ptr(cube), _ptr(out), cube.shape[0], cube.shape[1],
                                            cube.shape[2], _ptr(kernel), kernel.shape[0], kernel.shape[1],
                                            float(scale), self._stream()), "mtn_convolve_beam")
         return out
@@ -202,39 +205,39 @@ class Engine:
     STAGES = ("emit", "sort", "items", "project", "reduce", "finalize")
 
     def set_timing(self, enable: bool):
-        L.check(self.lib.mtn_set_timing(int(enable)), "mtn_set_timing")
+        self._check(self.lib.mtn_set_timing(int(enable)), "mtn_set_timing")
 
     def last_timing_ms(self):
         """Stage durations [ms] of the last insert() (needs set_timing(True)); synchronises."""
         arr = (C.c_float * 6)()
-        L.check(self.lib.mtn_last_timing(arr, 6), "mtn_last_timing")
+        self._check(self.lib.mtn_last_timing(arr, 6), "mtn_last_timing")
         return dict(zip(self.STAGES, (float(x) for x in arr)))
 
     def set_count_exec(self, enable: bool):
-        L.check(self.lib.mtn_set_count_exec(int(enable)), "mtn_set_count_exec")
+        self._check(self.lib.mtn_set_count_exec(int(enable)), "mtn_set_count_exec")
 
     def last_exec_counts(self):
         arr = (C.c_int64 * 3)()
-        L.check(self.lib.mtn_last_exec_counts(arr), "mtn_last_exec_counts")
+        self._check(self.lib.mtn_last_exec_counts(arr), "mtn_last_exec_counts")
         return {"updates": int(arr[0]), "weights": int(arr[1]), "erfs": int(arr[2])}
 
     def fp64_peak_tflops(self):
         t, ms = C.c_double(), C.c_double()
-        L.check(self.lib.mtn_fp64_peak(C.byref(t), C.byref(ms), self._stream()), "mtn_fp64_peak")
+        self._check(self.lib.mtn_fp64_peak(C.byref(t), C.byref(ms), self._stream()), "mtn_fp64_peak")
         return t.value
 
     def probe_kernel_integral(self, entry: dict, dx, dy, h, closed_form=False):
         e = KernelTable([entry]).to_c().k[0]
         dx, dy, h = (self.to_device(a) for a in (dx, dy, h))
         out = torch.empty_like(dx)
-        L.check(self.lib.mtn_probe_kernel_integral(C.byref(e), int(closed_form), dx.numel(), _ptr(dx),
+        self._check(self.lib.mtn_probe_kernel_integral(C.byref(e), int(closed_form), dx.numel(), _ptr(dx),
                                                    _ptr(dy), _ptr(h), _ptr(out), self._stream()),
                 "mtn_probe_kernel_integral")
         return out
 
     def table_error(self, kind: int) -> float:
         err = C.c_double()
-        L.check(self.lib.mtn_table_error(int(kind), C.byref(err)), "mtn_table_error")
+        self._check(self.lib.mtn_table_error(int(kind), C.byref(err)), "mtn_table_error")
         return err.value
 
     def probe_spectra(self, spectrum, v, sigma, amp, edges):
@@ -242,7 +245,7 @@ class Engine:
         st, ss = _scalar_or_tensor(sigma, self.device)
         nchan = edges.numel() - 1
         out = torch.empty((v.numel(), nchan), dtype=torch.float64, device=self.device)
-        L.check(self.lib.mtn_probe_spectra(int(spectrum), v.numel(), _ptr(v), _ptr(st), ss,
+        self._check(self.lib.mtn_probe_spectra(int(spectrum), v.numel(), _ptr(v), _ptr(st), ss,
                                            _ptr(amp), nchan, _ptr(edges), _ptr(out), self._stream()),
                 "mtn_probe_spectra")
         return out

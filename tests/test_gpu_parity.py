@@ -284,6 +284,18 @@ def test_empty_and_fully_pruned(eng):
     assert out["plan"].n_kept == 0 and torch.count_nonzero(out["cube"]) == 0
 
 
+def test_channel_limit_is_reported(eng):
+    """The footprint record holds a particle's live channel window as two uint16: mtn_plan
+    refuses cubes with more than 65535 channels with MTN_ERR_LIMIT instead of wrapping."""
+    from martini_b200._lib import MartiniB200Error
+
+    ok = synthetic.make_case("cfg2", n=50, nx=8, ny=8, nc=65535)
+    assert run_hot_path(eng, ok)["plan"].n_kept > 0
+    too_many = synthetic.make_case("cfg2", n=50, nx=8, ny=8, nc=65536)
+    with pytest.raises(MartiniB200Error, match="65535 channels"):
+        run_hot_path(eng, too_many)
+
+
 def assert_same_cube(a, b, rtol=1e-13):
     """Two decompositions of the same sum differ only by re-association of the additions."""
     peak = float(b.abs().max())
