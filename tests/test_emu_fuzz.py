@@ -1,0 +1,56 @@
+"""Seeded random cases through the SIMT emulator against the oracle: every kernel (primitive
+and adaptive), both spectra, scalar and per-particle line widths, either channel direction,
+odd cube shapes (fewer pixels than a tile, more channels than a brick), slabs, pre-filled
+cubes, particles on pixel centres / pixel edges / channel edges, NaN coordinates, zero masses,
+sub-pixel and cube-sized smoothing lengths.  Same C ABI and host code as on the GPU; test
+infrastructure (tests/emu/__init__.py) -- the ``-m gpu`` suite remains the parity proof.
+"""
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from martini_b200.pipeline import run_hot_path  # noqa: E402
+from tests.emu import EmuEngine  # noqa: E402
+from tests.parity import oracle_hot_path  # noqa: E402
+
+from tests.fuzz_cases import random_case  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = EmuEngine()
+    yield e
+    assert e.violations() == 0
+
+
+@pytest.mark.parametrize("seed", range(280))
+def test_random_case_vs_oracle(eng, seed):
+    case, extras = random_case(seed)
+    nx = case["shape"][0]
+    ref = oracle_hot_path(case, cube0=extras["prefill"])
+    x_lo, x_hi = extras["slab"] or (0, nx)
+    x_lo, x_hi = int(x_lo), int(x_hi)
+    cube0 = None
+    if extras["prefill"] is not None:
+        cube0 = eng.to_device(np.ascontiguousarray(extras["prefill"][x_lo:x_hi]))
+    out = run_hot_path(eng, case, cube=cube0, x_lo=x_lo, x_hi=x_hi)
+    assert np.array_equal(out["accept"].numpy().astype(bool), ref["accept"])
+    assert np.array_equal(out["sm_range"].numpy(), ref["sm_ranges"])
+    if ref["kernel_indices"] is not None:
+        assert np.array_equal(out["kernel_id"].numpy().astype(int), np.maximum(ref["kernel_indices"], 0))
+    if (x_lo, x_hi) == (0, nx):
+        assert out["plan"].updates_dense == ref["updates"]
+    got, want = out["cube"].numpy(), ref["cube"][x_lo:x_hi]
+    peak = np.abs(ref["cube"]).max()
+    # per voxel against the peak of the WHOLE cube (north-star tolerance); flux of the slab
+    assert np.abs(got - want).max() <= 1e-6 * peak
+    if peak > 0 and want.size:
+        assert abs(got.sum() - want.sum()) <= 1e-9 * max(abs(want.sum()), 1e-3 * abs(ref["cube"].sum()))
+    # far tighter in practice: the device evaluates the same float64 arithmetic (Wendland C6:
+    # the reference's 40-term closed form carries ~1e-12 of its peak in rounding noise, which
+    # the tabulated integral does not reproduce -- seen as 2e-11 of the cube peak at seed 99)
+    if peak > 0:
+        tight = 1e-10 if "WendlandC6" in case["kernel"][0] else 1e-11
+        assert np.abs(got - want).max() <= tight * peak
