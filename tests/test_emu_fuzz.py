@@ -54,3 +54,22 @@ def test_random_case_vs_oracle(eng, seed):
     if peak > 0:
         tight = 1e-10 if "WendlandC6" in case["kernel"][0] else 1e-11
         assert np.abs(got - want).max() <= tight * peak
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_beam_convolution_vs_scipy(eng, seed):
+    """mtn_convolve_beam on random cube shapes and odd x odd beam images (up to the 96 x 96 tap
+    limit's aspect ratios) against scipy.signal.fftconvolve(mode="same") per channel, the
+    reference's own call (martini.py:885-895)."""
+    from scipy.signal import fftconvolve
+
+    rng = np.random.Generator(np.random.PCG64(5000 + seed))
+    nx, ny, nc = int(rng.integers(1, 30)), int(rng.integers(1, 30)), int(rng.choice([1, 2, 31, 32, 33, 70]))
+    ka, kb = 2 * int(rng.integers(0, 8)) + 1, 2 * int(rng.integers(0, 8)) + 1
+    cube = rng.normal(size=(nx, ny, nc))
+    beam = rng.uniform(0.0, 1.0, (ka, kb))
+    scale = float(rng.uniform(0.1, 10.0))
+    out = eng.convolve_beam(eng.to_device(cube), eng.to_device(beam), scale=scale).numpy()
+    ref = np.stack([fftconvolve(cube[..., c], beam, mode="same") for c in range(nc)], axis=-1) * scale
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1e-300)
