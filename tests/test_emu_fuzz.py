@@ -73,3 +73,22 @@ def test_random_beam_convolution_vs_scipy(eng, seed):
     ref = np.stack([fftconvolve(cube[..., c], beam, mode="same") for c in range(nc)], axis=-1) * scale
     assert out.shape == ref.shape
     assert np.abs(out - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1e-300)
+
+
+@pytest.mark.parametrize("seed", range(0, 280, 5))
+def test_random_case_is_schedule_independent(eng, seed):
+    """The same random cases with the block's threads taking their turns in reverse and in
+    shuffled order: not a bit of the cube may change (a missing barrier, or a shared-memory
+    buffer reused one phase too early, shows up here)."""
+    case, extras = random_case(seed)
+    nx = case["shape"][0]
+    x_lo, x_hi = (int(b) for b in (extras["slab"] or (0, nx)))
+    eng.set_schedule("forward")
+    want = run_hot_path(eng, case, x_lo=x_lo, x_hi=x_hi)["cube"]
+    try:
+        for mode in ("reverse", "shuffle"):
+            eng.set_schedule(mode, seed=seed)
+            got = run_hot_path(eng, case, x_lo=x_lo, x_hi=x_hi)["cube"]
+            assert torch.equal(got, want), mode
+    finally:
+        eng.set_schedule("forward")
