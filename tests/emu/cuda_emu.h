@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <vector>
 
 // ------------------------------------------------------------------------- qualifiers
 #undef __shared__
@@ -177,8 +178,13 @@ template <typename... A>
 inline cudaError_t cudaFuncSetAttribute(void (*)(A...), cudaFuncAttribute, int) { return cudaSuccess; }
 
 // ----------------------------------------------------------- mbarrier + bulk copy (project.cuh)
-// The copy is done at issue and reported to the barrier, which completes a phase once its
-// pending arrivals and its transaction bytes are both zero -- the PTX mbarrier contract.
+// A bulk copy is asynchronous on the GPU: its bytes land at some time between issue and the
+// completion of the mbarrier phase it reports to.  The emulator makes both ends of that window
+// bite: at issue the destination is POISONED (0xff bytes: NaN as a double, -1 as an integer),
+// so a thread still reading the buffer being refilled, or reading it before it has observed
+// the barrier, gets garbage; the bytes land as late as possible, when a waiter first polls the
+// barrier.  The barrier completes a phase once its pending arrivals and its transaction bytes
+// are both zero -- the PTX mbarrier contract.
 namespace mtn {
 struct EmuBar {
   int32_t tx;       // outstanding transaction bytes (may go negative before expect_tx)
@@ -187,11 +193,36 @@ struct EmuBar {
   uint8_t phase;    // parity of the phase in progress
 };
 static_assert(sizeof(EmuBar) == 8, "lives in the kernel's uint64_t mbarrier slot");
+struct EmuBulkCopy {
+  void* dst;
+  const void* src;
+  uint32_t bytes;
+  uint64_t* bar;
+};
+inline std::vector<EmuBulkCopy>& emu_bulk_in_flight() {
+  static std::vector<EmuBulkCopy> v;  // blocks run one after the other: one list
+  return v;
+}
 inline void emu_bar_check(EmuBar* b) {
   if (b->pending == 0 && b->tx == 0) {
     b->phase ^= 1;
     b->pending = b->count;
   }
+}
+inline void emu_bulk_land(uint64_t* bar) {  // the copies reporting to `bar` arrive now
+  auto& v = emu_bulk_in_flight();
+  EmuBar* b = reinterpret_cast<EmuBar*>(bar);
+  size_t keep = 0;
+  for (size_t i = 0; i < v.size(); ++i) {
+    if (v[i].bar == bar) {
+      memcpy(v[i].dst, v[i].src, v[i].bytes);
+      b->tx -= (int32_t)v[i].bytes;
+    } else {
+      v[keep++] = v[i];
+    }
+  }
+  v.resize(keep);
+  emu_bar_check(b);
 }
 inline void mbar_init(uint64_t* bar, uint32_t count) {
   EmuBar* b = reinterpret_cast<EmuBar*>(bar);
@@ -199,6 +230,11 @@ inline void mbar_init(uint64_t* bar, uint32_t count) {
   b->pending = (uint16_t)count;
   b->count = (uint8_t)count;
   b->phase = 0;
+  auto& v = emu_bulk_in_flight();  // a new block: nothing of the previous one is in flight
+  size_t keep = 0;
+  for (size_t i = 0; i < v.size(); ++i)
+    if (v[i].bar != bar) v[keep++] = v[i];
+  v.resize(keep);
 }
 inline void mbar_fence_init() {}
 inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -210,6 +246,8 @@ inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
 inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   EmuBar* b = reinterpret_cast<EmuBar*>(bar);
   if (b->phase != (uint8_t)parity) return true;  // the phase with that parity has completed
+  emu_bulk_land(bar);
+  if (b->phase != (uint8_t)parity) return true;
   mtn_emu::yield();
   return false;
 }
@@ -218,9 +256,7 @@ inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint6
     fprintf(stderr, "mtn_emu: cp.async.bulk needs 16-byte aligned size and addresses\n");
     abort();
   }
-  memcpy(dst_smem, src_gmem, bytes);
-  EmuBar* b = reinterpret_cast<EmuBar*>(bar);
-  b->tx -= (int32_t)bytes;
-  emu_bar_check(b);
+  memset(dst_smem, 0xff, bytes);  // in flight: whoever reads it now reads garbage
+  emu_bulk_in_flight().push_back(EmuBulkCopy{dst_smem, src_gmem, bytes, bar});
 }
 }  // namespace mtn
