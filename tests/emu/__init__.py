@@ -31,11 +31,21 @@ CSRC = os.path.join(ROOT, "martini_b200", "csrc")
 LIB = os.path.join(HERE, "libmartini_emu.so")
 
 
+#: MTN_EMU_SANITIZE=address (or "address,undefined"): build the emulated library with the
+#: compiler's sanitizers, so that a kernel reading or writing outside a caller's buffer (inputs,
+#: cube, accept mask ...) or outside a static __shared__ array aborts the test run.  Run as
+#:   LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 \
+#:   MTN_EMU_SANITIZE=address python -m pytest tests/test_emu_parity.py tests/test_emu_fuzz.py
+SANITIZE = os.environ.get("MTN_EMU_SANITIZE", "")
+
+
 def lib_path(defines=()) -> str:
     """One emulated library per set of -D switches (experimental kernel variants)."""
-    if not defines:
-        return LIB
     tag = "_".join(d.replace("=", "").replace("MTN_", "").lower() for d in sorted(defines))
+    if SANITIZE:
+        tag = "_".join(t for t in (tag, "san" + SANITIZE.replace(",", "")) if t)
+    if not tag:
+        return LIB
     return os.path.join(HERE, f"libmartini_emu_{tag}.so")
 
 CUDA_INCLUDE = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
@@ -61,6 +71,7 @@ def build(force: bool = False, defines=()) -> str:
         cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off",
                "-Wl,-Bsymbolic",  # our cuda* stand-ins, not the libcudart torch has loaded
                *[f"-D{d}" for d in defines],
+               *([f"-fsanitize={SANITIZE}", "-fno-omit-frame-pointer"] if SANITIZE else []),
                "-include", os.path.join(HERE, "cuda_emu.h"), f"-I{CUDA_INCLUDE}", f"-I{HERE}",
                "-x", "c++", os.path.join(CSRC, "api.cu"), os.path.join(HERE, "cuda_emu.cpp"),
                "-o", lib]
