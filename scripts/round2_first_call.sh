@@ -32,7 +32,7 @@ done
 # 4. queued A/Bs: separable Gaussian kernel integrals on config 4, closed forms against tables
 #    for Wendland C6 (config-2 geometry with the C6 kernel)
 cp martini_b200/libmartini_b200.so /tmp/orig.so
-for v in base gauss_sep wtab_more0; do
+for v in gauss_sep wtab_more0; do
   [ -f martini_b200/lib_var_$v.so ] || continue
   cp martini_b200/lib_var_$v.so martini_b200/libmartini_b200.so
   for w in cfg4 cfg2c6; do

@@ -75,3 +75,121 @@ def check_cube(cube, ref, rtol_voxel=1e-6, rtol_flux=1e-9):
     s = ref.sum()
     assert abs(cube.sum() - s) <= rtol_flux * abs(s), (cube.sum(), s)
     return err / peak if peak > 0 else 0.0
+
+
+class PixelOracle:
+    """Reference-structured per-pixel sums for big cases (1e7 particles), affordable because
+    the candidate scan is pre-filtered.
+
+    The reference selects a pixel's particles with a boolean mask over all N
+    (martini.py:272-274).  Here the particles are bucketed once by a spatial hash (classes of
+    sm_range, cells at least as wide as the class's largest range, so a pixel's candidates
+    live in the 3 x 3 cells around it); the exact predicate of the reference is then applied
+    to those candidates only, and the survivors are put in ascending particle order -- an
+    ascending index array selects the same elements in the same order as the boolean mask,
+    so every later operation (``px_weight``, ``init_spectra``, the sequential
+    ``np.sum(axis=-2)``) sees bit-identical operands.  ``tests/test_oracle_golden.py`` checks
+    this class against :func:`oracle_pixels` (full mask) on small cases.
+    """
+
+    def __init__(self, case, prune=(True, True, True)):
+        k, kind, pix, acc = oracle_prepare(case, prune)
+        k.apply_mask(acc)
+        self.case, self.k, self.kind, self.acc = case, k, kind, acc
+        self.p = pix[:, acc]
+        sig = case["sigma"]
+        self.sig = sig[acc] if np.ndim(sig) > 0 else sig
+        self.v, self.mHI, self.D = case["v"][acc], case["mHI"][acc], case["D"][acc]
+        r = np.asarray(k.sm_ranges, dtype=np.float64)
+        px, py = self.p[0], self.p[1]
+        self.always = np.flatnonzero(~np.isfinite(r))  # r = inf: candidate of every pixel
+        fin = np.isfinite(r)
+        cls = np.zeros(r.shape, dtype=np.int64)
+        cls[fin] = np.ceil(np.log2(np.maximum(r[fin], 1.0))).astype(np.int64)  # cell = 2^cls >= r
+        self.classes = []
+        for c in np.unique(cls[fin]):
+            idx = np.flatnonzero(fin & (cls == c))
+            s = float(2 ** int(c))
+            cx = np.floor(px[idx] / s).astype(np.int64)
+            cy = np.floor(py[idx] / s).astype(np.int64)
+            cx0, cy0 = cx.min() - 1, cy.min() - 1
+            ncy = int(cy.max() - cy0 + 3)
+            key = (cx - cx0) * ncy + (cy - cy0)
+            order = np.argsort(key, kind="stable")  # ascending particle index inside a cell
+            self.classes.append((s, cx0, cy0, ncy, key[order], idx[order]))
+
+    def candidates(self, i, j):
+        out = [self.always]
+        for s, cx0, cy0, ncy, keys, idx in self.classes:
+            ci, cj = int(np.floor(i / s)) - cx0, int(np.floor(j / s)) - cy0
+            for a in (ci - 1, ci, ci + 1):
+                lo = np.searchsorted(keys, a * ncy + max(cj - 1, 0), side="left")
+                hi = np.searchsorted(keys, a * ncy + cj + 1, side="right")
+                if hi > lo:
+                    out.append(idx[lo:hi])
+        return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
+
+    def select(self, i, j):
+        """Ascending indices of the particles the reference's mask selects for pixel (i, j)."""
+        cand = self.candidates(i, j)
+        ijc = np.array((i, j))[..., np.newaxis]
+        m = (np.abs(ijc - self.p[:2, cand]) <= self.k.sm_ranges[cand]).all(axis=0)
+        return np.sort(cand[m])
+
+    def pixel(self, ij):
+        i, j = int(ij[0]), int(ij[1])
+        sel = self.select(i, j)
+        ijc = np.array((i, j))[..., np.newaxis]
+        w = self.k.px_weight(self.p[:2, sel] - ijc, mask=sel)
+        sp = O.init_spectra(self.kind, self.case["edges"], self.v[sel],
+                            self.sig if np.ndim(self.sig) == 0 else self.sig[sel],
+                            self.mHI[sel], self.D[sel])
+        np.multiply(sp, w[:, np.newaxis], out=sp)
+        return np.sum(sp, axis=-2) / self.case["px_size"] ** 2
+
+    def pixels(self, pixels, threads=None):
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        threads = threads or min(32, os.cpu_count() or 1)
+        if threads == 1 or len(pixels) < 4:
+            return np.array([self.pixel(ij) for ij in pixels])
+        with ThreadPoolExecutor(threads) as pool:
+            return np.array(list(pool.map(self.pixel, pixels, chunksize=8)))
+
+    def total_flux(self, chunk=200_000):
+        """Sum of the whole cube [Jy/arcsec^2 summed over voxels] without building it:
+        sum_p (sum over the pixels of p's clipped candidate box of W_p) x (sum_c S_p(c)) /
+        px_size^2, every factor from the same oracle functions the per-pixel path uses;
+        accumulated with math.fsum.  (A re-association of the reference's sum: good to ~1e-13
+        relative, the check it serves is the north-star's 1e-9.)"""
+        import math
+
+        X, Y, C = self.case["shape"]
+        px, py = self.p[0], self.p[1]
+        r = self.k.sm_ranges
+        terms = []
+        for a in range(0, px.size, chunk):
+            b = min(px.size, a + chunk)
+            sl = np.arange(a, b)
+            ilo = np.maximum(0, np.ceil(px[sl] - r[sl])).astype(np.int64)
+            ihi = np.minimum(X - 1, np.floor(px[sl] + r[sl])).astype(np.int64)
+            jlo = np.maximum(0, np.ceil(py[sl] - r[sl])).astype(np.int64)
+            jhi = np.minimum(Y - 1, np.floor(py[sl] + r[sl])).astype(np.int64)
+            nxp, nyp = np.maximum(0, ihi - ilo + 1), np.maximum(0, jhi - jlo + 1)
+            cnt = nxp * nyp
+            tot = int(cnt.sum())
+            if tot == 0:
+                continue
+            rep = np.repeat(np.arange(sl.size), cnt)
+            kk = np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+            nyr = nyp[rep]
+            ii, jj = ilo[rep] + kk // nyr, jlo[rep] + kk % nyr
+            pid = sl[rep]
+            w = self.k.px_weight(self.p[:2, pid] - np.vstack((ii, jj)), mask=pid)
+            wsum = np.bincount(rep, weights=w, minlength=sl.size)
+            sp = O.init_spectra(self.kind, self.case["edges"], self.v[sl],
+                                self.sig if np.ndim(self.sig) == 0 else self.sig[sl],
+                                self.mHI[sl], self.D[sl])
+            terms.append(wsum * sp.sum(axis=1))
+        return math.fsum(np.concatenate(terms).tolist()) / self.case["px_size"] ** 2 if terms else 0.0
