@@ -159,13 +159,14 @@ class _BaseMartini:
     def reset(self):
         """martini.py:409-425."""
         dc = self._datacube
-        pad = (dc.padx, dc.pady)
         new = DataCube(n_px_x=dc.n_px_x, n_px_y=dc.n_px_y, n_channels=dc.n_channels,
                        px_size=dc.px_size, channel_width=dc.channel_width,
                        spectral_centre=dc.spectral_centre, ra=dc.ra, dec=dc.dec,
                        stokes_axis=dc.stokes_axis)
         if self.beam is not None:
-            new.add_pad(pad)
+            # the reference re-pads with the beam's own requirement (martini.py:423-424), not
+            # with the current pad: convolve_beam() has dropped that one
+            new.add_pad(self.beam.needs_pad())
         self._datacube = new
 
 

@@ -34,38 +34,9 @@ from martini_b200.synthetic import channel_edges  # noqa: E402
 
 
 def generate(n, nx, ny, nc, device, seed=20260005):
-    """Config-5 recipe of SURVEY.md section 8(d) (64 discs on a jittered 8 x 8 grid + 10 %
-    uniform background) on the device; returns a case dict of device tensors."""
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    f64 = dict(dtype=torch.float64, device=device)
-    u = lambda m: torch.rand(m, generator=g, **f64)  # noqa: E731
-    scale = nx / 2048.0
-    nb = n // 10
-    nd = n - nb
-    which = torch.randint(0, 64, (nd,), generator=g, device=device)
-    jx, jy = u(64) * 0.4 - 0.2, u(64) * 0.4 - 0.2
-    vsys = u(64) * 1200.0 - 600.0
-    gx = ((which % 8).double() + 0.5 + jx[which]) * nx / 8.0
-    gy = ((which // 8).double() + 0.5 + jy[which]) * ny / 8.0
-    # R ~ Gamma(2, 30 px) as the sum of two exponentials
-    R = -(30.0 * scale) * (torch.log(u(nd)) + torch.log(u(nd)))
-    phi = u(nd) * (2 * np.pi)
-    px = torch.cat((gx + R * torch.cos(phi), u(nb) * nx))
-    py = torch.cat((gy + R * torch.sin(phi) * 0.5, u(nb) * ny))
-    v = torch.cat((vsys[which] + 200.0 * (2 / np.pi) * torch.atan(R / (10.0 * scale)) * 0.866 * torch.cos(phi)
-                   + torch.randn(nd, generator=g, **f64) * 8.0, u(nb) * 1800.0 - 900.0))
-    del gx, gy, R, phi, which
-    sm = torch.clamp(torch.exp(np.log(3.0) + 0.6 * torch.randn(n, generator=g, **f64)), 0.2, 20.0)
-    mHI = (1.0e9 / n) * (1.0 + 0.01 * (u(n) - 0.5))
-    edges = channel_edges(nc, 4.0)
-    pz = (edges[0] - v) / 4.0 - 0.5
-    dev = {"px": px, "py": py, "pz": pz, "sm_length": sm, "v": v, "mHI": mHI,
-           "D": torch.full((n,), 10.0, **f64), "sigma": 7.0,
-           "edges": torch.from_numpy(edges).to(device)}
-    case = {"name": "cfg5", "shape": (nx, ny, nc), "edges": edges, "px_size": 10.0, "sigma": 7.0,
-            "kernel": ("WendlandC2Kernel", {}), "spectrum": "gaussian"}
-    return case, dev
+    from martini_b200.synthetic import make_case_device
+
+    return make_case_device("cfg5", device, n=n, nx=nx, nc=nc, seed=seed)
 
 
 def main():

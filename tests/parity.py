@@ -136,16 +136,29 @@ class PixelOracle:
         m = (np.abs(ijc - self.p[:2, cand]) <= self.k.sm_ranges[cand]).all(axis=0)
         return np.sort(cand[m])
 
-    def pixel(self, ij):
+    #: rows per block of the per-pixel spectra array (keeps the temporaries in cache for pixels
+    #: with 1e5 contributors).  np.sum(axis=-2) adds the rows one after the other, so carrying
+    #: the running sum in as row 0 of the next block reproduces the one-shot sum bit for bit
+    #: (tests/test_pixel_oracle.py).
+    BLOCK = 4096
+
+    def pixel(self, ij, block=None):
         i, j = int(ij[0]), int(ij[1])
         sel = self.select(i, j)
         ijc = np.array((i, j))[..., np.newaxis]
         w = self.k.px_weight(self.p[:2, sel] - ijc, mask=sel)
-        sp = O.init_spectra(self.kind, self.case["edges"], self.v[sel],
-                            self.sig if np.ndim(self.sig) == 0 else self.sig[sel],
-                            self.mHI[sel], self.D[sel])
-        np.multiply(sp, w[:, np.newaxis], out=sp)
-        return np.sum(sp, axis=-2) / self.case["px_size"] ** 2
+        block = block or self.BLOCK
+        run = None
+        for a in range(0, max(sel.size, 1), block):
+            s = sel[a:a + block]
+            sp = O.init_spectra(self.kind, self.case["edges"], self.v[s],
+                                self.sig if np.ndim(self.sig) == 0 else self.sig[s],
+                                self.mHI[s], self.D[s])
+            np.multiply(sp, w[a:a + block, np.newaxis], out=sp)
+            if run is not None:
+                sp = np.concatenate((run[np.newaxis], sp), axis=0)
+            run = np.sum(sp, axis=-2)
+        return run / self.case["px_size"] ** 2
 
     def pixels(self, pixels, threads=None):
         import os
@@ -157,19 +170,21 @@ class PixelOracle:
         with ThreadPoolExecutor(threads) as pool:
             return np.array(list(pool.map(self.pixel, pixels, chunksize=8)))
 
-    def total_flux(self, chunk=200_000):
+    def total_flux(self, chunk=100_000, threads=None):
         """Sum of the whole cube [Jy/arcsec^2 summed over voxels] without building it:
         sum_p (sum over the pixels of p's clipped candidate box of W_p) x (sum_c S_p(c)) /
         px_size^2, every factor from the same oracle functions the per-pixel path uses;
         accumulated with math.fsum.  (A re-association of the reference's sum: good to ~1e-13
         relative, the check it serves is the north-star's 1e-9.)"""
         import math
+        import os
+        from concurrent.futures import ThreadPoolExecutor
 
         X, Y, C = self.case["shape"]
         px, py = self.p[0], self.p[1]
         r = self.k.sm_ranges
-        terms = []
-        for a in range(0, px.size, chunk):
+
+        def part(a):
             b = min(px.size, a + chunk)
             sl = np.arange(a, b)
             ilo = np.maximum(0, np.ceil(px[sl] - r[sl])).astype(np.int64)
@@ -180,7 +195,7 @@ class PixelOracle:
             cnt = nxp * nyp
             tot = int(cnt.sum())
             if tot == 0:
-                continue
+                return np.zeros(0)
             rep = np.repeat(np.arange(sl.size), cnt)
             kk = np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt)
             nyr = nyp[rep]
@@ -188,8 +203,22 @@ class PixelOracle:
             pid = sl[rep]
             w = self.k.px_weight(self.p[:2, pid] - np.vstack((ii, jj)), mask=pid)
             wsum = np.bincount(rep, weights=w, minlength=sl.size)
-            sp = O.init_spectra(self.kind, self.case["edges"], self.v[sl],
-                                self.sig if np.ndim(self.sig) == 0 else self.sig[sl],
-                                self.mHI[sl], self.D[sl])
-            terms.append(wsum * sp.sum(axis=1))
-        return math.fsum(np.concatenate(terms).tolist()) / self.case["px_size"] ** 2 if terms else 0.0
+            ssum = np.zeros(sl.size)
+            for c in range(0, sl.size, 8192):  # spectra in cache-sized row blocks
+                s2 = sl[c:c + 8192]
+                sp = O.init_spectra(self.kind, self.case["edges"], self.v[s2],
+                                    self.sig if np.ndim(self.sig) == 0 else self.sig[s2],
+                                    self.mHI[s2], self.D[s2])
+                ssum[c:c + 8192] = sp.sum(axis=1)
+            return wsum * ssum
+
+        starts = list(range(0, px.size, chunk))
+        threads = threads or min(32, os.cpu_count() or 1)
+        if threads > 1 and len(starts) > 1:
+            with ThreadPoolExecutor(threads) as pool:
+                terms = list(pool.map(part, starts))
+        else:
+            terms = [part(a) for a in starts]
+        if not terms:
+            return 0.0
+        return math.fsum(np.concatenate(terms).tolist()) / self.case["px_size"] ** 2

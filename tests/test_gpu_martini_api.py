@@ -111,6 +111,21 @@ def test_reset_and_reinsert():
     assert np.array_equal(m.datacube._array, first)
 
 
+def test_reset_after_convolve_repads_for_the_beam():
+    """insert -> convolve_beam -> reset -> insert -> convolve_beam equals a fresh instance:
+    reset() re-pads with beam.needs_pad() (reference martini.py:409-425), not with the pad
+    convolve_beam() has already dropped (which shifted the re-inserted source by 13 px)."""
+    m = demo(quiet=True, convolve=True)
+    first = m.datacube._array.copy()
+    assert first.shape[:2] == (128, 128) and m.datacube.padx == 0
+    m.reset()
+    assert (m.datacube.padx, m.datacube.pady) == (13, 13)
+    assert m.datacube._array.shape[:2] == (154, 154) and m.datacube._array.sum() == 0
+    m.insert_source_in_cube()
+    m.convolve_beam()
+    assert np.array_equal(m.datacube._array, first)
+
+
 def test_demo_mass_and_spectra_attribute():
     """BASELINE config 1: demo source into the demo cube; reference test_martini.py:523-531."""
     m = demo(quiet=True)
