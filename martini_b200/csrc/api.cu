@@ -8,11 +8,6 @@
 #include "kernel_integrals.cuh"
 #include "plan.cuh"
 #include "project.cuh"
-// (inline PTX throughout: not run by the test emulator; written for the 64-byte record of MTN_FOOTREC=0)
-#if MTN_TILE == 8 && !defined(MTN_HOST_EMU) && !MTN_FOOTREC
-#define MTN_HAVE_WS 1
-#include "project_ws.cuh"  // the warp-specialised variant is written for 8 x 8 tiles
-#endif
 #include "scan.cuh"
 #include "sort.cuh"
 #include "tables_host.hpp"
@@ -109,57 +104,22 @@ static int ensure_tables() {
   return MTN_OK;
 }
 
-// The projection kernel is project.cuh's; in a -DMTN_FOOTREC=0 build MTN_PROJECT=ws selects the
-// warp-specialised variant of project_ws.cuh instead (experimental: correct, but measured
-// slower -- profiles/README.md).
-static bool use_classic_project() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MTN_PROJECT");
-    v = (e && strcmp(e, "ws") == 0) ? 0 : 1;
-  }
-  return v == 1;
-}
-
 // One instantiation per (diagnostic counting, uniform kernel kind).
 template <bool COUNT, int KIND>
 static int launch_project_as(const ProjArgs& a, int64_t max_items, cudaStream_t st) {
-  static bool attr_set_dev[MAX_DEVICES][2] = {{false, false}};
-  bool* attr_set = attr_set_dev[current_device()];
-#ifdef MTN_HAVE_WS
-  const bool classic = use_classic_project();
-#else
-  if (!use_classic_project())  // asked for, not built: say so instead of running something else
-    return fail(MTN_ERR_INVALID, "MTN_PROJECT=ws: this library was built without the warp-specialised "
-                "kernel (it needs -DMTN_FOOTREC=0, scripts/build_variants.sh)%s", "");
-  const bool classic = true;
-#endif
+  static bool attr_set_dev[MAX_DEVICES] = {false};
+  const int dev = current_device();
   {
     std::lock_guard<std::mutex> lock(g_once_mutex);
-    if (!attr_set[classic]) {
-      if (classic)
-        MTN_CUDA(cudaFuncSetAttribute(project_kernel<COUNT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(ProjSmem)));
-#ifdef MTN_HAVE_WS
-      else
-        MTN_CUDA(cudaFuncSetAttribute(project_ws_kernel<COUNT, KIND>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSmem)));
-#endif
-      attr_set[classic] = true;
+    if (!attr_set_dev[dev]) {
+      MTN_CUDA(cudaFuncSetAttribute(project_kernel<COUNT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(ProjSmem)));
+      attr_set_dev[dev] = true;
     }
   }
-  if (classic) {
-    const unsigned grid = (unsigned)std::min<int64_t>(max_items, (int64_t)sm_count() * PROJ_CTAS_PER_SM);
-    auto kfn = project_kernel<COUNT, KIND>;
-    MTN_LAUNCH(kfn, grid, PROJ_THREADS, sizeof(ProjSmem), st, a);
-  }
-#ifdef MTN_HAVE_WS
-  else {
-    const unsigned grid = (unsigned)std::min<int64_t>(max_items, (int64_t)sm_count() * WS_CTAS_PER_SM);
-    auto kfn = project_ws_kernel<COUNT, KIND>;
-    MTN_LAUNCH(kfn, grid, WS_THREADS, sizeof(WsSmem), st, a);
-  }
-#endif
+  const unsigned grid = (unsigned)std::min<int64_t>(max_items, (int64_t)sm_count() * PROJ_CTAS_PER_SM);
+  auto kfn = project_kernel<COUNT, KIND>;
+  MTN_LAUNCH(kfn, grid, PROJ_THREADS, sizeof(ProjSmem), st, a);
   return MTN_OK;
 }
 
@@ -168,13 +128,8 @@ static int launch_project_count(const ProjArgs& a, int primary_kind, int64_t max
   switch (primary_kind) {
     case MTN_KERNEL_WENDLANDC2: return launch_project_as<COUNT, MTN_KERNEL_WENDLANDC2>(a, max_items, st);
     case MTN_KERNEL_CUBICSPLINE: return launch_project_as<COUNT, MTN_KERNEL_CUBICSPLINE>(a, max_items, st);
-#if MTN_WTAB_MORE
     case MTN_KERNEL_WENDLANDC6: return launch_project_as<COUNT, MTN_KERNEL_WENDLANDC6>(a, max_items, st);
     case MTN_KERNEL_QUARTICSPLINE: return launch_project_as<COUNT, MTN_KERNEL_QUARTICSPLINE>(a, max_items, st);
-#endif
-#if MTN_GAUSS_SEP
-    case MTN_KERNEL_GAUSSIAN: return launch_project_as<COUNT, MTN_KERNEL_GAUSSIAN>(a, max_items, st);
-#endif
     default: return launch_project_as<COUNT, -1>(a, max_items, st);
   }
 }
@@ -493,10 +448,8 @@ int mtn_plan(const MtnParticles* p, const MtnCube* cube, void* scratch, size_t s
   plan->n_pairs = (int64_t)tot[1];
   plan->updates_dense = (int64_t)tot[2];
   plan->n_bricks = g.n_bricks;
-#if MTN_FOOTREC
   if (cube->n_channels > 65535)
     return fail(MTN_ERR_LIMIT, "plan: more than 65535 channels%s", "");
-#endif
   if (plan->n_pairs >= (1ll << 32) - 1 || plan->n_kept >= (1ll << 32) - 1)
     return fail(MTN_ERR_LIMIT, "plan: %s%lld pairs exceed the 32-bit sort index; split the slab", "",
                 (long long)plan->n_pairs);
@@ -587,7 +540,6 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
     a.slab = cube->slab;
     a.partials = ws.partials;
     a.px_area = px_area;
-    a.inv_px_area = 1.0 / px_area;
     a.zeroed = zeroed;
     a.exec_counts = (unsigned long long*)(ws.scalars + 8);  // zeroed with the scalars
     // the instantiation specialised on the kind of table entry 0 (if that kind is tabulated)
@@ -595,7 +547,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
     if (int rc = launch_project(a, t.kind[0], g_count_exec != 0, ws.max_items, st)) return rc;
     MTN_LAUNCH_CHECK();
     mark(4, st);
-    MTN_LAUNCH(reduce_partials_kernel, dim3((unsigned)ws.max_multi, SUB_PIX), PROJ_THREADS, 0, st, g,
+    MTN_LAUNCH(reduce_partials_kernel, dim3((unsigned)ws.max_multi, REDUCE_PARTS), REDUCE_THREADS, 0, st, g,
                ws.multis, ws.scalars + 2, ws.partials, cube->slab, px_area, zeroed);
     MTN_LAUNCH_CHECK();
     if (g_count_exec) {
@@ -606,7 +558,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
   }
   mark(5, st);
   if (!zeroed) {
-    MTN_LAUNCH(empty_brick_kernel, (unsigned)g.n_bricks, PROJ_THREADS, 0, st, g, ws.brick_count, cube->slab,
+    MTN_LAUNCH(empty_brick_kernel, (unsigned)g.n_bricks, REDUCE_THREADS, 0, st, g, ws.brick_count, cube->slab,
                px_area);
     MTN_LAUNCH_CHECK();
   }

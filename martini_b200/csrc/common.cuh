@@ -16,30 +16,30 @@ namespace mtn {
 // Brick geometry.  A brick is TILE_X x TILE_Y pixels x CB channels; it is the unit of
 // binning (sort key) and the unit of register accumulation in the projection kernel.
 // ---------------------------------------------------------------------------------------
-#ifndef MTN_TILE
-#define MTN_TILE 8
-#endif
-constexpr int TILE_X = MTN_TILE;      // pixels along x (slowest cube axis)
-constexpr int TILE_Y = MTN_TILE;      // pixels along y
+constexpr int TILE_X = 8;             // pixels along x (slowest cube axis)
+constexpr int TILE_Y = 8;             // pixels along y
 constexpr int TILE_PIX = TILE_X * TILE_Y;
-constexpr int CH_HALF = 64;           // channels one warp covers: each lane owns 2 adjacent ones
-constexpr int N_HALF = 1;             // channel halves per brick, handled by different warps (1: brick = 64 channels)
-constexpr int CB = CH_HALF * N_HALF;  // channels per brick (unit of binning)
-#ifndef MTN_SUB_Y
-#define MTN_SUB_Y 4
+constexpr int CB = 64;                // channels per brick (unit of binning)
+// The projection kernel's thread layout (project.cuh): a thread owns one pixel and NCH
+// consecutive channels; warp (ph, cw) = pixel half ph (32 pixels, one per lane) x channel
+// group cw.  MTN_NCW = 2: 4-warp CTAs, 32 accumulators per thread; 4: 8-warp CTAs, 16.
+#ifndef MTN_NCW
+#define MTN_NCW 2
 #endif
 #ifndef MTN_CTAS_PER_SM
 #define MTN_CTAS_PER_SM 0
 #endif
-constexpr int SUB_X = 4;              // a warp owns a SUB_X x SUB_Y pixel sub-block of the tile
-constexpr int SUB_Y = MTN_SUB_Y;
-constexpr int SUB_PIX = SUB_X * SUB_Y;  // = accumulator pairs per thread
-constexpr int SUBS_Y = TILE_Y / SUB_Y;  // sub-blocks per tile row
-constexpr int N_SUB = TILE_PIX / SUB_PIX;      // sub-blocks per tile
-constexpr int PROJ_WARPS = N_SUB * N_HALF;     // warp = (channel half, sub-block)
+constexpr int N_PH = 2;               // pixel halves of a tile (rows 0-3 / 4-7)
+constexpr int N_CW = MTN_NCW;         // channel groups of a brick
+constexpr int NCH = CB / N_CW;        // channels (= float64 accumulators) per thread
+constexpr int NQ = NCH / 4;           // groups of four channels per thread
+static_assert(TILE_PIX == N_PH * 32, "one lane per pixel of a pixel half");
+static_assert(TILE_Y == 8, "lane -> (row, column) uses lane >> 3, lane & 7");
+static_assert(NCH % 4 == 0 && NCH * N_CW == CB, "channel groups are multiples of four");
+constexpr int PROJ_WARPS = N_PH * N_CW;
 constexpr int PROJ_THREADS = PROJ_WARPS * 32;
-// resident CTAs per SM: register-limited (16 warps per SM at 128 registers) unless overridden
-constexpr int PROJ_CTAS_PER_SM = MTN_CTAS_PER_SM ? MTN_CTAS_PER_SM : 512 / PROJ_THREADS;
+// resident CTAs per SM: register-limited unless overridden
+constexpr int PROJ_CTAS_PER_SM = MTN_CTAS_PER_SM ? MTN_CTAS_PER_SM : (N_CW == 2 ? 4 : 3);
 constexpr int PBATCH = 32;            // particle records staged per batch (= one per lane)
 static_assert(PBATCH == 32, "the batch is indexed by lane in several places");
 
@@ -56,27 +56,9 @@ constexpr int ERF_DEG = MTN_ERF_DEG;
 static_assert(ERF_DEG % 2 == 1, "rows are read as pairs of coefficients");
 constexpr int ERF_NCOEF = ERF_DEG + 1;  // 10 doubles = 80 B per interval (16-B aligned rows)
 constexpr int ERF_NINT = 6 * ERF_INV_W + 1;
-// MTN_FOOTREC: the particle's footprint (candidate box in the slab, live channel window) is
-// computed once, by the plan kernels that need it anyway, and travels in an 80-byte record;
-// the projection kernel's per-batch set-up is then integer clipping -- no candidate-box
-// predicate and no edge search per (particle, brick).
-//   2 (default): batch b+1 is set up by warps 0 / 1 while batch b is evaluated, two block
-//      barriers per batch.  B200, config 2: projection kernel 4.21 -> 4.04 ms, step 4.94 ->
-//      4.78 ms; 115 GPU parity tests green (profiles/README.md, r1_variants.log).
-//   1: set-up in line from the record, three barriers per batch (4.08 ms).
-//   0: 64-byte record, footprint searched per (particle, brick) in the kernel, four barriers
-//      (4.21 ms); the build that also carries the warp-specialised kernel (project_ws.cuh).
-#ifndef MTN_FOOTREC
-#define MTN_FOOTREC 2
-#endif
-// MTN_GAUSS_SEP (experimental, default off): a projection-kernel instantiation for Gaussian
-// SPH kernels (BASELINE config 4) that evaluates the kernel integral's two separable erf
-// factors once per (particle, pixel column / row) of a brick -- 2 x 16 + 64 erfs per full
-// brick instead of 5 x 64 -- with bit-identical results.
-#ifndef MTN_GAUSS_SEP
-#define MTN_GAUSS_SEP 0
-#endif
-constexpr int REC_DOUBLES = MTN_FOOTREC ? 10 : 8;  // 64-byte (80-byte) particle record
+// One staged particle record: 80 bytes (common.cuh: Record), 16-B aligned so a single
+// cp.async.bulk moves it.
+constexpr int REC_DOUBLES = 10;
 constexpr int REC_BYTES = REC_DOUBLES * 8;
 
 // erf(x) == 1.0 exactly for x >= ~5.93 (1 - erf(x) < 2^-54); channels whose edges are
@@ -94,8 +76,10 @@ struct Geo {
   int edges_increasing; // 1 if edges[c+1] > edges[c]
 };
 
-// One staged particle: everything the projection kernel needs, 64 bytes, 16-B aligned so
-// a single cp.async.bulk moves it.
+// One staged particle: everything the projection kernel needs.  The footprint (candidate box
+// of martini.py:272-274 clipped to the slab, live channel window) is computed once, by the plan
+// kernels that need it anyway, with the exact predicates; the projection kernel only clips it
+// to the brick with integer arithmetic.
 struct __align__(16) Record {
   double px, py;     // pixel coordinates
   double h;          // h_eff = sm_length * rescale
@@ -103,15 +87,10 @@ struct __align__(16) Record {
   double v;          // line centre [km/s]
   double inv_s;      // 1 / (sqrt(2) * sigma)   (Gaussian spectrum)
   double amp;        // mHI * D^-2 / 2.36e5  [Jy km/s]
-#if MTN_FOOTREC
   int32_t i0, i1, j0, j1;     // candidate box clipped to the slab, inclusive (plan.cuh: Foot)
   uint16_t c_first, c_last;   // live channel window, inclusive (plan.cuh: channel_window)
   uint8_t kid;                // kernel table index
   uint8_t pad[3];
-#else
-  float r;           // sm_range (integer valued or +inf)
-  int32_t kid;       // kernel table index
-#endif
 };
 static_assert(sizeof(Record) == REC_BYTES, "record size");
 static_assert(REC_BYTES % 16 == 0, "cp.async.bulk moves multiples of 16 bytes");

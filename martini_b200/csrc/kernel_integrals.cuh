@@ -131,30 +131,6 @@ __device__ __forceinline__ double w_gaussian(double dx, double dy, double h, dou
   return 0.25 * ez * ex * ey / norm;
 }
 
-// The same with the two separable factors given: ex = erf(x1) - erf(x0) depends on the pixel
-// column only, ey on the pixel row only (MTN_GAUSS_SEP: the projection kernel evaluates them
-// once per (particle, column / row) of a brick instead of once per pixel).  Same operations
-// in the same order as w_gaussian, hence the same bits.
-__device__ __forceinline__ double w_gaussian_sep(double dx, double dy, double h, double truncate,
-                                                 double norm, double ex, double ey) {
-  const double sig = 0.42466090014400953;
-  const double dr = sqrt(sq_dist(dx, dy));
-  if (__ddiv_rn(__ddiv_rn(__dsub_rn(dr, 0.70710678118654757), h), sig) > truncate) return 0.0;
-  const double u = __ddiv_rn(__ddiv_rn(dr, h), sig);
-  double ez = 0.0;
-  if (truncate > u) {
-    const double zmax = sqrt(__dsub_rn(__dmul_rn(truncate, truncate), __dmul_rn(u, u)));
-    ez = erf_tab(zmax / 1.4142135623730951);
-  }
-  return 0.25 * ez * ex * ey / norm;
-}
-// one separable factor: erf((d + 0.5) c) - erf((d - 0.5) c), c = 1 / (h sqrt2 sig)
-__device__ __forceinline__ double gaussian_axis_factor(double d, double h) {
-  const double sig = 0.42466090014400953;
-  const double c = 1.0 / (h * 1.4142135623730951 * sig);
-  return erf_tab((d + 0.5) * c) - erf_tab((d - 0.5) * c);
-}
-
 // DiracDeltaKernel._kernel_integral, sph_kernels.py:1165 (strict on both axes).
 __device__ __forceinline__ double w_dirac_delta(double dx, double dy) {
   return (fabs(dx) < 0.5 && fabs(dy) < 0.5) ? 1.0 : 0.0;

@@ -319,7 +319,6 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
     rec.inv_s = 1.0;
     rec.amp = amp;
   }
-#if MTN_FOOTREC
   rec.i0 = f.i0;
   rec.i1 = f.i1;
   rec.j0 = f.j0;
@@ -328,10 +327,6 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
   rec.c_last = (uint16_t)f.c1;
   rec.kid = in.kernel_id ? in.kernel_id[i] : (uint8_t)0;
   for (int k = 0; k < 3; ++k) rec.pad[k] = 0;
-#else
-  rec.r = (float)in.sm_range[i];
-  rec.kid = in.kernel_id ? (int32_t)in.kernel_id[i] : 0;
-#endif
   records[ridx] = rec;
   int tx0, tx1, ty0, ty1;
   tile_range(f, g, tx0, tx1, ty0, ty1);

@@ -5,7 +5,7 @@
 //
 //  * erf: Taylor coefficients about the centres of 1/16-wide intervals on [0, 6);
 //  * pixel-integrated SPH kernels W(R^2) for the kernels whose closed form costs logs and
-//    square roots (Wendland C2, cubic spline; with MTN_WTAB_MORE also Wendland C6 and the
+//    square roots (Wendland C2, Wendland C6, cubic spline,
 //    quartic spline): piecewise degree-9 polynomials in R^2 on
 //    intervals refined towards the points where the closed form is not analytic (below).
 //    ~35 straight-line instructions instead of ~145 branchy ones, and two evaluations
@@ -55,15 +55,12 @@ __device__ __forceinline__ double erf_tab(double t) {
 // zone below), so only the ten coefficients are loaded.
 constexpr int WT_DEG = 9;
 constexpr int WT_ROW = 12;          // c0..c9 (in t = u - centre), interval centre, unused
-// MTN_WTAB_MORE: tables for Wendland C6 and the quartic spline too (their closed forms cost
-// ~350 instructions: 40-term polynomials, a log or up to three asinh, up to four square
-// roots); 0 restores the closed forms on the device for an A/B.
-#ifndef MTN_WTAB_MORE
-#define MTN_WTAB_MORE 1
-#endif
-constexpr int WT_MAX_ZONES = MTN_WTAB_MORE ? 6 : 4;
+// Wendland C6 and the quartic spline are tabulated too: their closed forms cost ~350
+// instructions (40-term polynomials, a log or up to three asinh, up to four square roots);
+// measured on the config-2 geometry with the C6 kernel: 5.45 ms (table) against 8.03 ms.
+constexpr int WT_MAX_ZONES = 6;
 constexpr int WT_KINDS = 6;         // indexed by MTN_KERNEL_*
-constexpr int WT_MAX_ROWS = MTN_WTAB_MORE ? 4096 : 2048;
+constexpr int WT_MAX_ROWS = 4096;
 // zones of a kind (compile-time kinds fold the zone search to the compares they need)
 __host__ __device__ constexpr int wtab_zones_of(int kind) {
   return kind == MTN_KERNEL_WENDLANDC2 || kind == MTN_KERNEL_WENDLANDC6 ? 2

@@ -283,7 +283,6 @@ static HostTables build_kernel_tables() {
   // (4 - s)^(7/2) at the edge
   build_kind(T, MTN_KERNEL_CUBICSPLINE, 4.0, F_cubic_spline,
              {{0.0L, 0.5L, 0.0L, 28}, {0.5L, 1.0L, 1.0L, 54}, {1.0L, 2.5L, 1.0L, 6}, {2.5L, 4.0L, 4.0L, 16}});
-#if MTN_WTAB_MORE
   // Wendland C6: s^4 log s at 0, (1 - s)^(17/2) at the edge
   build_kind(T, MTN_KERNEL_WENDLANDC6, 1.0, F_wendland_c6,
              {{0.0L, 0.5L, 0.0L, WTAB_C6_K0}, {0.5L, 1.0L, 1.0L, WTAB_C6_K1}});
@@ -296,7 +295,6 @@ static HostTables build_kernel_tables() {
                {{0.0L, 0.02L, 0.0L, WTAB_Q_K0}, {0.02L, k1, k1, WTAB_Q_KNOT}, {k1, 0.2L, k1, WTAB_Q_UP},
                 {0.2L, k2, k2, WTAB_Q_KNOT}, {k2, 0.68L, k2, WTAB_Q_UP}, {0.68L, 1.0L, 1.0L, WTAB_Q_KNOT}});
   }
-#endif
   return T;
 }
 

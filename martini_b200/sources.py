@@ -162,7 +162,9 @@ class SPHSource:
     def sm_lengths_px(self, datacube):
         """Smoothing lengths in pixels: arctan(hsm / D) / px_size (sph_kernels.py:250-253)."""
         hsm = np.broadcast_to(self.hsm_g, (self.npart,)) if self.hsm_g is not None else np.zeros(self.npart)
-        return np.rad2deg(np.arctan(hsm / (self.distance_p * 1.0e3))) * 3600.0 / datacube.px_size
+        # kpc / Mpc -> dimensionless, radians -> pixels: the operation order astropy's unit
+        # converters give the reference (pinned by tests/golden/seam.npz)
+        return np.arctan(hsm / self.distance_p * 1.0e-3) * (1.0 / (datacube.px_size * (np.pi / 648000.0)))
 
     # ------------------------------------------------------------------ pruning
     def apply_mask(self, mask):

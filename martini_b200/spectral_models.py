@@ -89,7 +89,7 @@ class GaussianSpectrum(_BaseSpectrum):
         if isinstance(self.sigma_mode, str):
             if self.sigma_mode != "thermal":
                 raise ValueError("sigma must be a velocity or 'thermal'")
-            return np.sqrt(K_B * np.asarray(source.T_g, dtype=np.float64) / M_P) / 1.0e3
+            return np.sqrt(K_B * np.asarray(source.T_g, dtype=np.float64) / M_P) * 1.0e-3
         return self.sigma_mode
 
 

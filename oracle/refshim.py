@@ -193,3 +193,223 @@ def load_reference(root: str = REFERENCE_ROOT):
             if v is not None:
                 sys.modules[k] = v
     return mods[0], mods[1], mods[2], units
+
+
+# --------------------------------------------------------------------------------------------
+# Units WITH scale factors, for the two seam functions whose arithmetic is a unit conversion:
+# _BaseSPHKernel._init_sm_lengths (sph_kernels.py:235-255: arctan(hsm / D) -> pixels) and
+# GaussianSpectrum.half_width, sigma="thermal" (spectral_models.py:465-485: sqrt(k_B T / m_p)
+# -> km/s).  Under the scale-1 shim above both would be meaningless, so make_golden.py runs
+# them -- unmodified -- under this second stand-in, in which a unit is (exact rational scale,
+# dimension vector), a Quantity carries its unit through * / sqrt / arctan, and ``.to`` multiplies
+# the value by ONE correctly rounded factor from_scale / to_scale (what astropy's converters do
+# up to the order of their own floating-point operations, which cannot be known without
+# astropy: the fixtures pin the formulas and constants, not astropy's last ulp).
+# --------------------------------------------------------------------------------------------
+from fractions import Fraction  # noqa: E402
+
+_DIMS = ("length", "time", "mass", "temperature", "angle", "pix")
+
+
+class SUnit:
+    __array_ufunc__ = None
+    __array_priority__ = 1.0e6
+
+    def __init__(self, scale, dims):
+        self.scale = Fraction(scale)
+        self.dims = tuple(Fraction(d) for d in dims)
+
+    @classmethod
+    def base(cls, name, scale=1):
+        return cls(scale, [1 if d == name else 0 for d in _DIMS])
+
+    def __mul__(self, other):
+        if isinstance(other, SUnit):
+            return SUnit(self.scale * other.scale, [a + b for a, b in zip(self.dims, other.dims)])
+        if isinstance(other, SQuantity):
+            return SQuantity(other.view(np.ndarray), other.unit * self)
+        return SQuantity(other, self)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        if isinstance(other, SUnit):
+            return SUnit(self.scale / other.scale, [a - b for a, b in zip(self.dims, other.dims)])
+        return SQuantity(1.0 / np.asarray(other, dtype=np.float64), self)
+
+    def __rtruediv__(self, other):
+        if isinstance(other, SQuantity):
+            return SQuantity(other.view(np.ndarray), other.unit / self)
+        return SQuantity(other, SUnit(1, [0] * len(_DIMS)) / self)
+
+    def __pow__(self, p):
+        p = Fraction(p).limit_denominator(16)
+        if p.denominator == 1:
+            scale = self.scale ** int(p)
+        else:  # half-integer powers only arise on units whose scale is 1 here (SI: J / kg)
+            assert self.scale == 1, "fractional power of a scaled unit"
+            scale = Fraction(1)
+        return SUnit(scale, [d * p for d in self.dims])
+
+    def __eq__(self, other):
+        return isinstance(other, SUnit) and self.scale == other.scale and self.dims == other.dims
+
+    def __hash__(self):
+        return hash((self.scale, self.dims))
+
+    def factor_to(self, other):
+        """Multiply a value in this unit by the result to express it in `other`."""
+        assert self.dims == other.dims, f"incompatible units {self.dims} -> {other.dims}"
+        return float(self.scale / other.scale)
+
+    def to(self, other, *a, **k):
+        return self.factor_to(other)
+
+    def __repr__(self):
+        return f"<SUnit {float(self.scale):g} {dict((n, str(d)) for n, d in zip(_DIMS, self.dims) if d)}>"
+
+
+_ONE = SUnit(1, [0] * len(_DIMS))
+
+
+class SQuantity(np.ndarray):
+    def __new__(cls, value, unit=None, dtype=None, copy=True):
+        if isinstance(value, SQuantity) and unit is None:
+            unit = value.unit
+        arr = np.array(value, dtype=dtype, subok=False)
+        if arr.dtype.kind in "iub" and dtype is None:
+            arr = arr.astype(np.float64)
+        out = arr.view(cls)
+        out._unit = unit if unit is not None else _ONE
+        return out
+
+    def __array_finalize__(self, obj):
+        self._unit = getattr(obj, "_unit", _ONE)
+
+    def __class_getitem__(cls, item):
+        return cls
+
+    @property
+    def unit(self):
+        return self._unit
+
+    @property
+    def value(self):
+        return self.view(np.ndarray)
+
+    @property
+    def isscalar(self):
+        return self.ndim == 0
+
+    def _converted(self, unit, equivalencies=()):
+        if unit.dims == self._unit.dims:
+            return self.view(np.ndarray) * self._unit.factor_to(unit)
+        for funit, tunit in equivalencies:  # pixel_scale: (pix, physical unit)
+            if self._unit.dims == tunit.dims and unit.dims == funit.dims:
+                return self.view(np.ndarray) * float(self._unit.scale / tunit.scale * funit.scale / unit.scale)
+            if self._unit.dims == funit.dims and unit.dims == tunit.dims:
+                return self.view(np.ndarray) * float(self._unit.scale / funit.scale * tunit.scale / unit.scale)
+        raise ValueError(f"cannot convert {self._unit} to {unit}")
+
+    def to(self, unit, equivalencies=()):
+        return SQuantity(self._converted(unit, equivalencies), unit)
+
+    def to_value(self, unit=None, equivalencies=()):
+        v = self.view(np.ndarray) if unit is None else self._converted(unit, equivalencies)
+        return v[()] if np.ndim(v) == 0 else v
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        units = [i.unit if isinstance(i, SQuantity) else _ONE for i in inputs]
+        raw = [i.view(np.ndarray) if isinstance(i, SQuantity) else i for i in inputs]
+        if method != "__call__":
+            return NotImplemented
+        if ufunc is np.multiply:
+            return SQuantity(ufunc(*raw, **kwargs), units[0] * units[1])
+        if ufunc in (np.divide, np.true_divide):
+            return SQuantity(ufunc(*raw, **kwargs), units[0] / units[1])
+        if ufunc is np.sqrt:
+            return SQuantity(ufunc(*raw, **kwargs), units[0] ** Fraction(1, 2))
+        if ufunc is np.arctan:  # argument to dimensionless first, result in radians
+            x = raw[0] * units[0].factor_to(_ONE)
+            return SQuantity(ufunc(x, **kwargs), SUNITS["rad"])
+        if ufunc in (np.add, np.subtract):
+            other = raw[1] * units[1].factor_to(units[0]) if units[1] != units[0] else raw[1]
+            return SQuantity(ufunc(raw[0], other, **kwargs), units[0])
+        if ufunc in (np.greater, np.greater_equal, np.less, np.less_equal, np.equal, np.not_equal):
+            other = raw[1] * units[1].factor_to(units[0]) if units[1] != units[0] else raw[1]
+            return ufunc(raw[0], other, **kwargs)
+        if ufunc in (np.ceil, np.floor, np.absolute, np.negative):
+            return SQuantity(ufunc(*raw, **kwargs), units[0])
+        return NotImplemented
+
+    def __lshift__(self, unit):
+        return self.to(unit)
+
+
+_PC = Fraction(30856775814913673)  # metres per parsec (IAU 2015, as astropy rounds it)
+SUNITS = {
+    "m": SUnit.base("length"), "km": SUnit.base("length", 1000), "pc": SUnit.base("length", _PC),
+    "kpc": SUnit.base("length", 1000 * _PC), "Mpc": SUnit.base("length", 10**6 * _PC),
+    "s": SUnit.base("time"), "kg": SUnit.base("mass"), "K": SUnit.base("temperature"),
+    "rad": SUnit.base("angle"), "pix": SUnit.base("pix"),
+    "dimensionless_unscaled": _ONE, "one": _ONE,
+}
+# pi / 648000 rad per arcsec, pi / 180 per degree: one correctly rounded float each
+SUNITS["arcsec"] = SUnit.base("angle", Fraction(np.pi) / 648000)
+SUNITS["deg"] = SUnit.base("angle", Fraction(np.pi) / 180)
+SUNITS["Msun"] = SUnit.base("mass", Fraction(1.988409870698051e30))
+SUNITS["J"] = SUNITS["kg"] * SUNITS["m"] ** 2 / SUNITS["s"] ** 2
+SUNITS["Hz"] = _ONE / SUNITS["s"]
+SUNITS["Jy"] = SUnit(Fraction(1, 10**26), (SUNITS["J"] / SUNITS["m"] ** 2).dims)  # W m^-2 Hz^-1
+SUNITS["beam"] = _ONE
+
+
+def _scaled_units_module():
+    m = types.ModuleType("astropy.units")
+    for name, u in SUNITS.items():
+        setattr(m, name, u)
+    m.Quantity = SQuantity
+    m.Unit = SUnit
+    # astropy.units.pixel_scale(pixscale): pix <-> the physical unit one pixel spans
+    m.pixel_scale = lambda q: [(SUNITS["pix"], SUnit(q.unit.scale * Fraction(float(q.value)), q.unit.dims)
+                                * SUNITS["pix"])]
+    return m
+
+
+def load_reference_scaled(root: str = REFERENCE_ROOT):
+    """(sph_kernels, spectral_models, units) of the reference loaded under the scaled-unit
+    stand-in; CODATA 2018 k_B and m_p as astropy.constants ships them."""
+    if not os.path.isdir(os.path.join(root, "martini")):
+        raise FileNotFoundError(f"reference tree not found at {root}")
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.split(".")[0] in ("astropy", "martini")}
+    units = _scaled_units_module()
+    consts = _stub("astropy.constants",
+                   k_B=SQuantity(1.380649e-23, SUNITS["J"] / SUNITS["K"]),
+                   m_p=SQuantity(1.67262192369e-27, SUNITS["kg"]))
+    fakes = {
+        "astropy": _stub("astropy", units=units, constants=consts, __version__="shim", __path__=[]),
+        "astropy.units": units,
+        "astropy.constants": consts,
+        "martini": _stub("martini", __path__=[os.path.join(root, "martini")]),
+        "martini.datacube": _stub("martini.datacube", DataCube=object, _GlobalProfileDataCube=object),
+        "martini.sources": _stub("martini.sources", SPHSource=object),
+        "martini.sources.sph_source": _stub("martini.sources.sph_source", SPHSource=object),
+    }
+    sys.modules.update(fakes)
+    try:
+        mods = []
+        for sub in ("sph_kernels", "spectral_models"):
+            name = f"martini.{sub}"
+            spec = importlib.util.spec_from_file_location(name, os.path.join(root, "martini", f"{sub}.py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+            mods.append(mod)
+    finally:
+        for k in list(sys.modules):
+            if k.split(".")[0] in ("astropy", "martini"):
+                del sys.modules[k]
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+    return mods[0], mods[1], units

@@ -1,21 +1,10 @@
 #!/bin/bash
-# Build the experimental kernel variants as martini_b200/lib_var_<name>.so for
-# scripts/try_variants.sh (which times bench.py and runs the GPU parity tests with each).
-# A variant is a set of -D switches of csrc/; every one of them is logic-checked on the CPU by
-# tests/test_emu_variants.py under the SIMT emulator before it is given GPU time.
-#   usage: scripts/build_variants.sh [name=-DFLAG[,-DFLAG...]]...   (default: the queued set)
+# Build experimental kernel variants as martini_b200/lib_var_<name>.so (same C ABI; load one
+# with MTN_B200_LIB=... ).  A variant is a set of -D switches of csrc/; each is logic-checked
+# on the CPU by tests/test_emu_variants.py under the SIMT emulator before it gets GPU time.
+#   usage: scripts/build_variants.sh name=-DFLAG[,-DFLAG...] ...
 cd "$(dirname "$0")/.."
-variants=("$@")
-if [ ${#variants[@]} -eq 0 ]; then
-  variants=(
-    "base="
-    "ws=-DMTN_FOOTREC=0"
-    "footrec1=-DMTN_FOOTREC=1"
-    "gauss_sep=-DMTN_GAUSS_SEP=1"
-    "wtab_more0=-DMTN_WTAB_MORE=0"
-  )
-fi
-for v in "${variants[@]}"; do
+for v in "$@"; do
   name="${v%%=*}"
   flags="${v#*=}"
   echo "== lib_var_${name}.so  ${flags}"

@@ -337,11 +337,57 @@ def gen_insert(dtype=np.float64, prefix="insert", only=None):
         np.savez_compressed(os.path.join(HERE, f"{prefix}_{tag(name, kw)}_{sname}.npz"), **out)
 
 
+def gen_seam():
+    """The two seam functions whose arithmetic IS a unit conversion, run unmodified under the
+    scaled-unit stand-in (oracle/refshim.py: load_reference_scaled):
+    _BaseSPHKernel._init_sm_lengths (sph_kernels.py:235-255) -- arctan(hsm / D) in pixels,
+    through _AdaptiveKernel._init_sm_lengths (:1241-1274) as well, so that the adaptive
+    selection is pinned end to end from kpc / Mpc / arcsec inputs -- and
+    GaussianSpectrum.half_width with sigma="thermal" (spectral_models.py:465-485)."""
+    from oracle.refshim import load_reference_scaled
+
+    Ks, Ss, Us = load_reference_scaled()
+    Qs = Us.Quantity
+    rng = np.random.Generator(np.random.PCG64(20260107))
+    n = 4000
+    hsm = np.r_[10 ** rng.uniform(-2.5, 1.5, n - 4), 0.0, 1e-6, 1.0, 100.0]  # kpc
+    dist = np.r_[rng.uniform(0.5, 80.0, n - 4), 3.0, 3.0, 3.0, 0.05]  # Mpc, per particle
+    out = {"hsm_kpc": hsm, "distance_Mpc": dist}
+    for px_size in (10.0, 3.0, 0.7):
+        src = SimpleNamespace(
+            hsm_g=Qs(hsm, Us.kpc), mHI_g=Qs(np.ones(n), Us.Msun),
+            skycoords=SimpleNamespace(transform_to=lambda frame: SimpleNamespace(distance=Qs(dist, Us.Mpc))))
+        dc = SimpleNamespace(px_size=Qs(px_size, Us.arcsec), coordinate_frame=None)
+        t = f"px{px_size:g}".replace(".", "p")
+        k = Ks._WendlandC2Kernel()
+        k._init_sm_lengths(src, dc)
+        assert k.sm_lengths.unit == Us.pix
+        out[f"sm_lengths_{t}"] = np.asarray(k.sm_lengths.value)
+        for name in ("WendlandC2Kernel", "CubicSplineKernel", "GaussianKernel"):
+            ka = getattr(Ks, name)()
+            ka._init_sm_lengths(source=src, datacube=dc)
+            ka._init_sm_ranges()
+            assert np.array_equal(np.asarray(ka.sm_lengths.value), out[f"sm_lengths_{t}"])
+            out[f"kidx_{name}_{t}"] = np.asarray(ka.kernel_indices)
+            out[f"sm_ranges_{name}_{t}"] = np.asarray(ka.sm_ranges.value)
+    T = np.r_[10 ** rng.uniform(1.0, 7.0, n - 2), 1.0e4, 8.0e3]
+    g = Ss.GaussianSpectrum(sigma="thermal")
+    hw = g.half_width(SimpleNamespace(T_g=Qs(T, Us.K)))
+    assert hw.unit == Us.km / Us.s
+    out["T_K"] = T
+    out["half_width_thermal_kms"] = np.asarray(hw.value)
+    np.savez_compressed(os.path.join(HERE, "seam.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--seam-only" in sys.argv:
+        gen_seam()
+        sys.exit(0)
     gen_kernels()
     gen_adaptive()
     gen_spectra()
     gen_prune()
+    gen_seam()
     gen_insert()
     gen_insert(dtype=np.float32, prefix="insertf32",
                only={("WendlandC2Kernel", "gauss7"), ("CubicSplineKernel", "gaussP")})

@@ -34,6 +34,7 @@ test_kernel_integral_vs_reference = G.test_kernel_integral_vs_reference
 test_tabulated_kernels_match_their_closed_form = G.test_tabulated_kernels_match_their_closed_form
 test_spectra_vs_reference = G.test_spectra_vs_reference
 test_smoothing_setup_bit_exact = G.test_smoothing_setup_bit_exact
+test_smoothing_setup_from_reference_made_lengths = G.test_smoothing_setup_from_reference_made_lengths
 test_prune_bit_exact = G.test_prune_bit_exact
 
 # --- the whole hot path against cubes made by the reference's _insert_source_in_cube ---------
@@ -41,30 +42,6 @@ test_insert_vs_reference_cube = G.test_insert_vs_reference_cube
 test_insert_vs_reference_float32_mode = G.test_insert_vs_reference_float32_mode
 test_empty_and_fully_pruned = G.test_empty_and_fully_pruned
 test_channel_limit_is_reported = G.test_channel_limit_is_reported
-
-
-def test_unbuilt_kernel_variant_is_an_error_not_a_substitute(tmp_path):
-    """MTN_PROJECT=ws on a library without the warp-specialised kernel (the default build, and
-    this emulated one) must fail loudly.  The switch is read once per process: child process."""
-    import os
-    import subprocess
-    import sys
-
-    code = (
-        "from martini_b200 import synthetic\n"
-        "from martini_b200._lib import MartiniB200Error\n"
-        "from martini_b200.pipeline import run_hot_path\n"
-        "from tests.emu import EmuEngine\n"
-        "try:\n"
-        "    run_hot_path(EmuEngine(), synthetic.make_case('cfg2', n=200, nx=16, ny=16, nc=8))\n"
-        "except MartiniB200Error as e:\n"
-        "    assert 'warp-specialised' in str(e), e\n"
-        "    print('refused')\n"
-    )
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MTN_PROJECT="ws", PYTHONPATH=root),
-                         cwd=root, capture_output=True, text=True, timeout=300)
-    assert res.returncode == 0 and "refused" in res.stdout, res.stdout + res.stderr
 
 
 def emu_cases():

@@ -1,8 +1,8 @@
-"""Kernel variants (compile-time switches of csrc/: the two older footprint set-ups of the
-projection kernel, MTN_FOOTREC=0 / 1, and the experimental MTN_GAUSS_SEP, measurements in
-profiles/README.md) under the SIMT emulator: each must reproduce the oracle and -- where the
-variant only moves work around -- the default kernel's cube bit for bit, under every thread
-schedule.  Test infrastructure; see tests/emu/__init__.py.
+"""Kernel variants (compile-time switches of csrc/: MTN_NCW = 4 gives 8-warp CTAs with 16
+accumulators per thread instead of 4-warp CTAs with 32, measurements in profiles/README.md)
+under the SIMT emulator: each must reproduce the oracle and -- where the variant only moves
+work between threads -- the default kernel's cube bit for bit, under every thread schedule.
+Test infrastructure; see tests/emu/__init__.py.
 """
 
 import numpy as np
@@ -16,13 +16,9 @@ from tests.emu import EmuEngine  # noqa: E402
 
 #: name -> (switches, bit-identical to the default kernel?)
 VARIANTS = {
-    "footrec0": (("MTN_FOOTREC=0",), True),
-    "footrec1": (("MTN_FOOTREC=1",), True),
-    "gauss_sep": (("MTN_GAUSS_SEP=1",), True),
-    "footrec0_gauss_sep": (("MTN_FOOTREC=0", "MTN_GAUSS_SEP=1"), True),
-    # closed forms instead of tables for Wendland C6 / quartic spline (none of FAST_CASES uses
-    # them as primary kernel, so the cubes are bit-identical; the switch must keep building)
-    "wtab_more0": (("MTN_WTAB_MORE=0",), True),
+    # (not bit-identical: the work-item chunk length follows the resident CTA count, so crowded
+    # bricks are cut -- and their partial sums associated -- differently)
+    "ncw4": (("MTN_NCW=4",), False),
 }
 FAST_CASES = ("cfg2_odd_shape", "cfg2_one_channel_block_partial", "cfg3_thermal", "cfg4_wide_dirac",
               "adaptive_gauss", "increasing_edges", "dirac_edges", "crowded_bricks")

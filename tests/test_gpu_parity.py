@@ -147,6 +147,20 @@ def test_smoothing_setup_bit_exact(eng, tag):
     assert np.array_equal(heff.cpu().numpy(), g["sm_lengths"] * g[f"rescale_{tag}"])
 
 
+@pytest.mark.parametrize("px", ("px10", "px3", "px0p7"))
+@pytest.mark.parametrize("name", ("WendlandC2Kernel", "CubicSplineKernel", "GaussianKernel"))
+def test_smoothing_setup_from_reference_made_lengths(eng, name, px):
+    """K0 on the pixel-unit smoothing lengths the reference's own _init_sm_lengths produced from
+    kpc / Mpc / arcsec inputs (tests/golden/seam.npz, sph_kernels.py:235-255 + :1241-1274 run
+    unmodified under the scaled-unit stand-in): kernel choice and sm_ranges bit-exact."""
+    g = np.load(os.path.join(GOLDEN, "seam.npz"))
+    k = getattr(K, name)()
+    kid, valid, rng, _ = eng.smoothing_setup(eng.to_device(g[f"sm_lengths_{px}"]), K.kernel_table(k))
+    kid, valid = kid.cpu().numpy().astype(int), valid.cpu().numpy().astype(bool)
+    assert np.array_equal(np.where(valid, kid, -1), g[f"kidx_{name}_{px}"])
+    assert np.array_equal(rng.cpu().numpy(), g[f"sm_ranges_{name}_{px}"])
+
+
 @pytest.mark.parametrize("sname", ("gauss3", "gaussP", "dirac"))
 @pytest.mark.parametrize("flags", range(1, 8))
 def test_prune_bit_exact(eng, sname, flags):
@@ -498,44 +512,6 @@ def test_cfg5_cube_size_columns_and_flux(eng):
     out = run_hot_path(eng, case)
     pix = seeded_columns(out["cube"], 2048, 505, 512)
     check_columns_and_flux(out["cube"], case, pix)
-
-
-@pytest.mark.parametrize("name", ("cfg2_small", "cfg3_thermal", "dirac_edges"))
-def test_warp_specialised_variant_matches(eng, name, tmp_path):
-    """The opt-in MTN_PROJECT=ws kernel (csrc/project_ws.cuh) against the oracle and the default
-    kernel.  It is written for the 64-byte record, i.e. lives in the -DMTN_FOOTREC=0 build
-    (martini_b200/lib_var_ws.so, scripts/build_variants.sh; built here if nvcc is at hand).
-    The switch is read once per process, so the variant runs in a child process."""
-    import pickle
-    import shutil
-    import subprocess
-    import sys
-
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    ws_lib = os.path.join(root, "martini_b200", "lib_var_ws.so")
-    if not os.path.exists(ws_lib):
-        if shutil.which("nvcc") is None:
-            pytest.skip("lib_var_ws.so not built and no nvcc here (scripts/build_variants.sh ws=-DMTN_FOOTREC=0)")
-        subprocess.run(["bash", os.path.join(root, "scripts", "build_variants.sh"), "ws=-DMTN_FOOTREC=0"],
-                       check=True, cwd=root, timeout=600)
-    case = SMALL[name]
-    case_file, out_file = tmp_path / "case.pkl", tmp_path / "cube.npy"
-    case_file.write_bytes(pickle.dumps(case))
-    code = (
-        "import pickle, sys, numpy as np\n"
-        "from martini_b200.engine import Engine\n"
-        "from martini_b200.pipeline import run_hot_path\n"
-        "case = pickle.load(open(sys.argv[1], 'rb'))\n"
-        "out = run_hot_path(Engine('cuda:0'), case)\n"
-        "np.save(sys.argv[2], out['cube'].cpu().numpy())\n"
-    )
-    env = dict(os.environ, MTN_PROJECT="ws", MTN_B200_LIB=ws_lib, PYTHONPATH=root)
-    subprocess.run([sys.executable, "-c", code, str(case_file), str(out_file)], check=True, env=env,
-                   cwd=root, timeout=300)
-    ws = np.load(out_file)
-    check_cube(ws, oracle_hot_path(case)["cube"])
-    default = run_hot_path(eng, case)["cube"].cpu().numpy()
-    assert np.abs(ws - default).max() <= 1e-13 * np.abs(default).max()
 
 
 @pytest.mark.parametrize("n_slabs", (1, 2, 3))

@@ -155,3 +155,51 @@ def test_insert_float32_mode_bit_exact(path):
 def test_insert_fixture_count():
     assert len(F32_FILES) == 2
     assert len(INSERT_FILES) == 42  # (8 primitive + 6 adaptive) kernels x 3 spectra
+
+
+# ------------------------------------------------------------------------------------------
+# seam.npz: the reference's _init_sm_lengths (sph_kernels.py:235-255, and through
+# _AdaptiveKernel._init_sm_lengths :1241-1274) and GaussianSpectrum.half_width("thermal")
+# (spectral_models.py:465-485), run unmodified under the scaled-unit stand-in
+# ------------------------------------------------------------------------------------------
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+SEAM_PX = (("px10", 10.0), ("px3", 3.0), ("px0p7", 0.7))
+
+
+@pytest.mark.parametrize("tag,px_size", SEAM_PX)
+def test_sm_lengths_px_vs_reference(tag, px_size):
+    g = np.load(os.path.join(GOLDEN, "seam.npz"))
+    got = O.sm_lengths_px(g["hsm_kpc"], g["distance_Mpc"], px_size)
+    ref = g[f"sm_lengths_{tag}"]
+    assert np.array_equal(got == 0, ref == 0)
+    assert np.allclose(got, ref, rtol=4.5e-16, atol=0)  # the converter factor's last ulp is astropy's
+    # adaptive selection and ranges from the oracle's own lengths: same choices as the reference
+    for name in ("WendlandC2Kernel", "CubicSplineKernel", "GaussianKernel"):
+        k = O.make_kernel(name)
+        k.init_sm(got)
+        assert np.array_equal(k.kernel_indices, g[f"kidx_{name}_{tag}"])
+        assert np.array_equal(k.sm_ranges, g[f"sm_ranges_{name}_{tag}"])
+
+
+def test_thermal_half_width_vs_reference():
+    g = np.load(os.path.join(GOLDEN, "seam.npz"))
+    assert np.array_equal(O.thermal_sigma(g["T_K"]), g["half_width_thermal_kms"])
+
+
+def test_product_host_seam_functions_vs_reference():
+    """The product's host mirrors of the same two functions (martini_b200/sources.py,
+    spectral_models.py) against the reference-made fixture."""
+    from types import SimpleNamespace
+
+    from martini_b200.sources import SPHSource
+    from martini_b200.spectral_models import GaussianSpectrum
+
+    g = np.load(os.path.join(GOLDEN, "seam.npz"))
+    hw = GaussianSpectrum(sigma="thermal").half_width(SimpleNamespace(T_g=g["T_K"]))
+    assert np.array_equal(hw, g["half_width_thermal_kms"])
+    n = g["hsm_kpc"].size
+    for tag, px_size in SEAM_PX:
+        src = SPHSource.__new__(SPHSource)
+        src.npart, src.hsm_g, src.distance_p = n, g["hsm_kpc"], g["distance_Mpc"]
+        got = src.sm_lengths_px(SimpleNamespace(px_size=px_size))
+        assert np.allclose(got, g[f"sm_lengths_{tag}"], rtol=4.5e-16, atol=0)
