@@ -547,7 +547,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
     if (int rc = launch_project(a, t.kind[0], g_count_exec != 0, ws.max_items, st)) return rc;
     MTN_LAUNCH_CHECK();
     mark(4, st);
-    MTN_LAUNCH(reduce_partials_kernel, dim3((unsigned)ws.max_multi, REDUCE_PARTS), REDUCE_THREADS, 0, st, g,
+    MTN_LAUNCH(reduce_partials_kernel, dim3((unsigned)ws.max_multi, SUB_PIX), PROJ_THREADS, 0, st, g,
                ws.multis, ws.scalars + 2, ws.partials, cube->slab, px_area, zeroed);
     MTN_LAUNCH_CHECK();
     if (g_count_exec) {
@@ -558,7 +558,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
   }
   mark(5, st);
   if (!zeroed) {
-    MTN_LAUNCH(empty_brick_kernel, (unsigned)g.n_bricks, REDUCE_THREADS, 0, st, g, ws.brick_count, cube->slab,
+    MTN_LAUNCH(empty_brick_kernel, (unsigned)g.n_bricks, PROJ_THREADS, 0, st, g, ws.brick_count, cube->slab,
                px_area);
     MTN_LAUNCH_CHECK();
   }

@@ -19,27 +19,16 @@ namespace mtn {
 constexpr int TILE_X = 8;             // pixels along x (slowest cube axis)
 constexpr int TILE_Y = 8;             // pixels along y
 constexpr int TILE_PIX = TILE_X * TILE_Y;
-constexpr int CB = 64;                // channels per brick (unit of binning)
-// The projection kernel's thread layout (project.cuh): a thread owns one pixel and NCH
-// consecutive channels; warp (ph, cw) = pixel half ph (32 pixels, one per lane) x channel
-// group cw.  MTN_NCW = 2: 4-warp CTAs, 32 accumulators per thread; 4: 8-warp CTAs, 16.
-#ifndef MTN_NCW
-#define MTN_NCW 2
-#endif
-#ifndef MTN_CTAS_PER_SM
-#define MTN_CTAS_PER_SM 0
-#endif
-constexpr int N_PH = 2;               // pixel halves of a tile (rows 0-3 / 4-7)
-constexpr int N_CW = MTN_NCW;         // channel groups of a brick
-constexpr int NCH = CB / N_CW;        // channels (= float64 accumulators) per thread
-constexpr int NQ = NCH / 4;           // groups of four channels per thread
-static_assert(TILE_PIX == N_PH * 32, "one lane per pixel of a pixel half");
-static_assert(TILE_Y == 8, "lane -> (row, column) uses lane >> 3, lane & 7");
-static_assert(NCH % 4 == 0 && NCH * N_CW == CB, "channel groups are multiples of four");
-constexpr int PROJ_WARPS = N_PH * N_CW;
+constexpr int CB = 64;                // channels per brick (unit of binning): each lane owns 2 adjacent ones
+constexpr int SUB_X = 4;              // a warp owns a SUB_X x SUB_Y pixel sub-block of the tile
+constexpr int SUB_Y = 4;
+constexpr int SUB_PIX = SUB_X * SUB_Y;  // = accumulator pairs per thread
+constexpr int SUBS_Y = TILE_Y / SUB_Y;  // sub-blocks per tile row
+constexpr int N_SUB = TILE_PIX / SUB_PIX;      // sub-blocks per tile
+constexpr int PROJ_WARPS = N_SUB;              // warp = sub-block
 constexpr int PROJ_THREADS = PROJ_WARPS * 32;
-// resident CTAs per SM: register-limited unless overridden
-constexpr int PROJ_CTAS_PER_SM = MTN_CTAS_PER_SM ? MTN_CTAS_PER_SM : (N_CW == 2 ? 4 : 3);
+// resident CTAs per SM: register-limited (16 warps per SM at 128 registers)
+constexpr int PROJ_CTAS_PER_SM = 512 / PROJ_THREADS;
 constexpr int PBATCH = 32;            // particle records staged per batch (= one per lane)
 static_assert(PBATCH == 32, "the batch is indexed by lane in several places");
 

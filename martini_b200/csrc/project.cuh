@@ -1,35 +1,30 @@
-// The brick projection kernel and its small companions (work items, partial reduce).
+// The tile projection kernel and its small companions (work items, partial reduce).
 //
-// One CTA works on one brick -- 8 x 8 pixels x 64 channels -- at a time and keeps the brick's
-// sums in registers.  A thread owns ONE PIXEL and NCH consecutive channels of it: warp
-// (ph, cw) covers pixel half ph (rows 4 ph .. 4 ph + 3 of the tile, lane = (row, column)) and
-// channels [cw NCH, (cw + 1) NCH) of the brick.  This is the layout the two costs of the sum
+// One CTA works on one brick -- TILE x TILE pixels x 64 channels -- at a time and keeps the
+// brick's sums in registers: warp w owns a 4 x 4 pixel sub-block, lane l owns channels
+// (2l, 2l+1) of the brick, i.e. 16 pixels x 2 channels = 32 float64 accumulators per thread.
+// With the default 8 x 8 tile a CTA is 4 warps and four CTAs share an SM, so one CTA's
+// barrier waits are covered by the others.  The particle records of the brick are gathered
+// into shared memory with cp.async.bulk (one 80-byte bulk copy per record, completion on an
+// mbarrier, double buffered).  Per batch of 32 staged particles:
 //
-//     acc[pixel][c] += W_p(pixel) * S_p(c)
+//   setup  one lane per particle: the record carries the particle's footprint (candidate box
+//          of martini.py:272-274 in the slab, live channel window -- computed once by the
+//          plan kernels with the exact predicates), so warps 0/1 clip it to the brick with
+//          integer arithmetic and turn it into prefix sums of box areas and edge-run lengths,
+//          for batch b+1 while batch b is in phase A;
+//   A      every (particle, box pixel) pair and every (particle, live edge) pair is handed to
+//          one thread through those prefix sums -- all lanes hold real work, two items per
+//          lane so two dependency chains are in flight -- which evaluates the SPH-kernel
+//          pixel integral (tabulated, tables.cuh) or the edge erf ONCE into shared memory;
+//   C      each warp builds, with one ballot, the list of particles that touch its sub-block
+//          and their pixel masks, then walks it: the lane forms its two spectrum values
+//          S = (E[c+1] - E[c]) amp / dv from the shared edge erfs and does acc[pixel] += W * S
+//          for the masked pixels (W is a shared-memory broadcast); the next particle's mask
+//          shuffle and spectrum loads are issued ahead of the current FMAs.
 //
-// want: the kernel integral W_p(pixel) is evaluated by the very lane that accumulates it
-// (particle warp-uniform, one lane per pixel: no enumeration of (particle, pixel) items, no
-// per-lane kernel-kind divergence, no W broadcast loads), and the spectrum S_p(c), which
-// every pixel of the brick shares, is a warp-uniform shared-memory broadcast: two 16-byte
-// loads feed four FMAs of every lane.
-//
-// The particle records of the brick are gathered into shared memory with cp.async.bulk (one
-// 80-byte bulk copy per record, completion on an mbarrier, double buffered).  Per batch of 32
-// staged particles:
-//
-//   S   the line spectrum of every particle over the brick's 64 channels, ONCE per
-//       (particle, brick): lanes = channel edges, erf from the table, the difference of
-//       adjacent edges by shuffle, result (exact zeros outside the live window) in shared
-//       memory; the warps share the particles out.
-//   W   the kernel integrals of every particle over the brick's 64 pixels, once per
-//       (particle, pixel): the channel warps of a pixel half share the particles out and
-//       leave W[ph][p][lane] plus the ballot of its non-zero lanes in shared memory.
-//   C   each warp walks the particles that reach its pixels AND its channels (one ballot):
-//       w = W[ph][p][lane], then for every live group of four channels two broadcast loads of
-//       S and four FMAs.
-//
-// Two block barriers per batch.  No atomics on the data path; every voxel is stored exactly
-// once (16-byte vector stores, 32 x NCH x 8 contiguous bytes per thread).
+// No atomics on the data path; every voxel is stored exactly once, as a 16-byte vector store
+// (a warp writes 512 contiguous bytes per pixel).
 #pragma once
 
 #include "common.cuh"
@@ -81,6 +76,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t it = 0; it < (1u << 26); ++it)
     if (mbar_try_wait(bar, parity)) return;
   __trap();
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t x, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  return x;
 }
 
 // ------------------------------------------------------------------------------ work items
@@ -165,20 +169,38 @@ struct ProjArgs {
   unsigned long long* exec_counts;  // COUNT instantiation only: [updates, weights, erfs]
 };
 
+constexpr int W_STRIDE = TILE_PIX + 1;  // odd row stride: lane-per-particle reads hit 32 banks
+
+// What the per-batch set-up leaves for the evaluation and accumulation phases.
+struct SetupBuf {
+  uint32_t wprefix[PBATCH + 1];  // exclusive prefix of box areas
+  uint32_t eprefix[PBATCH + 1];  // exclusive prefix of edge-run lengths
+  float rny[PBATCH];             // 1 / (box height)
+  uint8_t wowner[PBATCH];        // particles with a non-empty box, in order
+  uint8_t eowner[PBATCH];        // particles with a non-empty edge run, in order
+  uint8_t box[PBATCH][4];        // tile-local box: x0, nx, y0, ny
+  uint8_t erun[PBATCH][2];       // first edge to evaluate, number of edges
+  uint8_t chan[PBATCH][2];       // live channels of the brick: [cs, ce)
+  uint8_t hlive[PBATCH];         // 1: the particle reaches a pixel and a live channel of the brick
+};
+
 struct ProjSmem {
   Record rec[2][PBATCH];
-  double S[PBATCH][CB];            // line spectra over the brick's channels, zero outside the window
-  double W[N_PH][PBATCH][32];      // kernel integrals, [pixel half][particle][lane = pixel]
-  double inv_dv[CB];               // (16-byte aligned: read as double2)
+  double W[PBATCH][W_STRIDE];   // kernel integrals, valid inside the particle's box only
+  double ES[PBATCH][CB + 2];    // edge erfs of the live channels (up to CB+1 per particle)
+  double inv_dv[CB];            // (16-byte aligned: read as double2)
   double edge[CB + 1];
-  uint32_t nz[N_PH][PBATCH];       // ballot of the lanes with W != 0
-  uint32_t quads[PBATCH];          // bit q: channels [4q, 4q+4) of the brick hold a live channel
+  SetupBuf sb[2];  // (two: batch b+1 is set up while batch b is evaluated)
   uint64_t bar[2];
   uint32_t item;
 };
 
-// One thread stores two adjacent channels of one pixel: out = (in + acc) / px_area
-// (martini.py:338, 364-366).  `nvalid` = how many of the two channels exist.
+// tile pixel (x, y) of pixel j of sub-block s
+__device__ __forceinline__ int sub_x(int s, int j) { return (s / SUBS_Y) * SUB_X + j / SUB_Y; }
+__device__ __forceinline__ int sub_y(int s, int j) { return (s % SUBS_Y) * SUB_Y + j % SUB_Y; }
+
+// One thread stores its two channels of one pixel: out = (in + acc) / px_area
+// (martini.py:338, 364-366).  `nvalid` = how many of the lane's two channels exist.
 __device__ __forceinline__ void store2(double* __restrict__ dst, double a0, double a1, int nvalid,
                                        double px_area, bool add_in, bool vec_ok) {
   if (nvalid == 2 && vec_ok) {
@@ -198,19 +220,29 @@ __device__ __forceinline__ void store2(double* __restrict__ dst, double a0, doub
   }
 }
 
+// Cooperative owner lookup for 32 consecutive enumerated items starting at q0: lane k knows
+// where run k starts (`my_start`, `my_nonempty`); returns for this lane the ordinal (among
+// non-empty runs) of the run that holds item q0 + lane.
+__device__ __forceinline__ int owner_ordinal(uint32_t q0, uint32_t my_start, bool my_nonempty,
+                                             int lane) {
+  const uint32_t before = __popc(__ballot_sync(0xffffffffu, my_nonempty && my_start < q0));
+  const uint32_t rel = my_start - q0;
+  const uint32_t H = __reduce_or_sync(0xffffffffu, (my_nonempty && rel < 32u) ? (1u << rel) : 0u);
+  return (int)(before + __popc(H & ((2u << lane) - 1u))) - 1;
+}
+
 // COUNT = true is a diagnostic instantiation that additionally tallies the executed
 // algorithmic work (non-zero weight x non-zero spectrum terms, kernel integrals, edge erfs);
 // it is never the timed kernel.  KIND >= 0: entry 0 of the kernel table -- the SPH kernel proper
 // of the reference's adaptive kernels; the other entries are its small-h fallbacks -- is that
 // tabulated kind, so the weight evaluation is the bare table look-up with compile-time zone
-// bounds and only particles on another entry take the closed forms; KIND = -1: general case.
+// bounds and only the lanes on another entry take the closed forms; KIND = -1: general case.
 template <bool COUNT, int KIND>
 __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel(const ProjArgs a) {
   MTN_DYN_SMEM(unsigned char, smem_raw);
   ProjSmem& sm = *reinterpret_cast<ProjSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ph = warp / N_CW, cw = warp % N_CW;  // this warp's pixel half and channel group
-  const int tpx = ph * (TILE_X / N_PH) + (lane >> 3), tpy = lane & 7;  // this thread's tile pixel
+  const int sub = warp;  // this warp's sub-block of the tile
   const Geo& g = a.geo;
   const bool gaussian_line = g.spectrum == MTN_SPECTRUM_GAUSSIAN;
   const double sgn = g.edges_increasing ? 1.0 : -1.0;
@@ -238,18 +270,14 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
     const int clo = max(0, -c0), nch = min(CB, g.C - c0);  // valid brick channels: [clo, nch)
     // pixels of the tile that exist in the slab / cube
     const int x_last = min(x0 + TILE_X, g.x_hi) - 1, y_last = min(y0 + TILE_Y, g.ny) - 1;
-    // rows of this warp's pixel half
-    const int hx0 = x0 + ph * (TILE_X / N_PH), hx1 = min(hx0 + TILE_X / N_PH - 1, x_last);
-    const int gx = x0 + tpx, gy = y0 + tpy;
-    const double gxd = (double)gx, gyd = (double)gy;
 
     for (int e = tid; e <= CB; e += PROJ_THREADS) sm.edge[e] = a.edges[min(max(c0 + e, 0), g.C)];
     for (int c = tid; c < CB; c += PROJ_THREADS)
       sm.inv_dv[c] = (c >= clo && c < nch) ? 1.0 / fabs(a.edges[c0 + c + 1] - a.edges[c0 + c]) : 0.0;
 
-    double acc[NCH];
+    double acc[SUB_PIX][2];
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) acc[k] = 0.0;
+    for (int j = 0; j < SUB_PIX; ++j) acc[j][0] = acc[j][1] = 0.0;
 
     const uint32_t n_part = it.end - it.begin;
     const uint32_t n_batch = (n_part + PBATCH - 1) / PBATCH;
@@ -264,198 +292,277 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
       if (tid == 0) mbar_arrive_expect_tx(&sm.bar[buf], nb * REC_BYTES);
     };
 
+    // ---- setup, lane = particle: the record carries the particle's footprint (candidate
+    // box in the slab, live channel window; computed once by the plan kernels with the exact
+    // predicates of martini.py:272-274), so the brick's share of it is integer clipping.
+    // Warp 0 turns the box areas into the enumeration prefix / owner list of the kernel
+    // integrals, warp 1 does the same for the edge runs; one barrier.
+    auto setup_from_records = [&](uint32_t bb) {
+      const int nbb = (int)min((uint32_t)PBATCH, n_part - bb * PBATCH);
+      SetupBuf& S = sm.sb[bb & 1u];
+      if (warp < 2) {
+        int bx0 = 0, bnx = 0, by0 = 0, bny = 0, cs = 0, ce = 0;
+        if (lane < nbb) {
+          const Record& r = sm.rec[bb & 1u][lane];
+          const int xa = max(r.i0, x0), xb = min(r.i1, x_last);
+          const int ya = max(r.j0, y0), yb = min(r.j1, y_last);
+          if (xa <= xb && ya <= yb) {
+            bx0 = xa - x0;
+            bnx = xb - xa + 1;
+            by0 = ya - y0;
+            bny = yb - ya + 1;
+          }
+          // live channels of the brick [cs, ce): the particle's window cut to the brick
+          cs = max((int)r.c_first - c0, clo);
+          ce = min((int)r.c_last + 1 - c0, nch);
+          if (cs >= ce) cs = ce = 0;
+        }
+        const uint32_t area = (ce > cs) ? (uint32_t)(bnx * bny) : 0u;
+        const uint32_t ne = (area && gaussian_line) ? (uint32_t)(ce - cs + 1) : 0u;
+        const uint32_t lt = (1u << lane) - 1u;
+        if (warp == 0) {
+          S.box[lane][0] = (uint8_t)bx0;
+          S.box[lane][1] = (uint8_t)bnx;
+          S.box[lane][2] = (uint8_t)by0;
+          S.box[lane][3] = (uint8_t)bny;
+          S.rny[lane] = bny ? 1.0f / (float)bny : 0.0f;
+          S.chan[lane][0] = (uint8_t)cs;
+          S.chan[lane][1] = (uint8_t)ce;
+          S.hlive[lane] = (uint8_t)(area ? 1u : 0u);
+          const uint32_t wi = warp_incl_scan_u32(area, lane);
+          S.wprefix[lane] = wi - area;
+          if (lane == 31) S.wprefix[32] = wi;
+          const uint32_t wm = __ballot_sync(0xffffffffu, area != 0);
+          if (area != 0) S.wowner[__popc(wm & lt)] = (uint8_t)lane;
+        }
+        if (warp == 1) {
+          S.erun[lane][0] = (uint8_t)cs;
+          S.erun[lane][1] = (uint8_t)ne;
+          const uint32_t ei = warp_incl_scan_u32(ne, lane);
+          S.eprefix[lane] = ei - ne;
+          if (lane == 31) S.eprefix[32] = ei;
+          const uint32_t em = __ballot_sync(0xffffffffu, ne != 0);
+          if (ne != 0) S.eowner[__popc(em & lt)] = (uint8_t)lane;
+        }
+      }
+    };
+
+    // Two barriers per batch: batch b+1 is set up (by warps 0 and 1, from the records that
+    // landed while batch b-1 was processed) during batch b's evaluation phase, into the other
+    // set-up buffer; the bulk copies of batch b+2 are issued once batch b has released rec[buf].
     issue(0);
     if (n_batch > 1) issue(1);
-    __syncthreads();  // edge table visible before the first spectrum step reads it
-
+    __syncthreads();  // edge table visible before the first setup step reads it
+    mbar_wait(&sm.bar[0], phase & 1u);
+    phase ^= 1u;
+    setup_from_records(0);
+    __syncthreads();
     for (uint32_t b = 0; b < n_batch; ++b) {
       const uint32_t buf = b & 1u;
       const int nb = (int)min((uint32_t)PBATCH, n_part - b * PBATCH);
-      // every thread observes the completion itself (visibility of rec[buf])
-      mbar_wait(&sm.bar[buf], (phase >> buf) & 1u);
-      phase ^= 1u << buf;
-      const Record* rec = sm.rec[buf];
-
-      // ---- S: line spectra, once per (particle, brick).  Warp w takes particles w, w + NW, ...
-      // The record carries the particle's live channel window (plan.cuh: channel_window, the
-      // exact predicates); its share of the brick is [cs, ce).  Lane l evaluates the edges
-      // cs + l and cs + 32 + l (two independent erf chains), the rare 65th edge is lane 0's.
-      for (int p = warp; p < nb; p += PROJ_WARPS) {
-        const Record& r = rec[p];
-        int cs = max((int)r.c_first - c0, clo), ce = min((int)r.c_last + 1 - c0, nch);
-        if (cs >= ce) {
-          if (lane == 0) sm.quads[p] = 0u;
-          continue;
-        }
-        const int c1 = cs + lane, c2 = cs + 32 + lane;  // this lane's channels (= their lower edges)
-        double s1 = 0.0, s2 = 0.0;
-        if (gaussian_line) {
-          const int ne = ce - cs + 1;  // edges cs .. ce
-          const double v = r.v, sc = sgn * r.inv_s;
-          // g orientation (sign folded in): S[c] = E[c+1] - E[c] >= 0; saturated edges at the
-          // ends of the window come out as exactly -1 / +1
-          const double t1 = (sm.edge[min(c1, CB)] - v) * sc;
-          double E1 = erf_tab(t1), E2 = 0.0, E3 = 0.0;
-          if (COUNT) n_erf += (lane < ne) && fabs(t1) < ERF_SAT;
-          if (ne > 32) {
-            const double t2 = (sm.edge[min(c2, CB)] - v) * sc;
-            E2 = erf_tab(t2);
-            if (COUNT) n_erf += (lane + 32 < ne) && fabs(t2) < ERF_SAT;
-            if (ne > 64) {  // the window covers the whole brick: edge 64 (cs == 0)
-              const double t3 = (sm.edge[CB] - v) * sc;
-              E3 = erf_tab(t3);
-              if (COUNT) n_erf += lane == 0 && fabs(t3) < ERF_SAT;
-            }
-          }
-          // upper edge of each channel: the next lane's value; lane 31 wraps into the next chain
-          double U1 = __shfl_down_sync(0xffffffffu, E1, 1);
-          double U2 = __shfl_down_sync(0xffffffffu, E2, 1);
-          const double E2_0 = __shfl_sync(0xffffffffu, E2, 0);
-          if (lane == 31) {
-            U1 = E2_0;
-            U2 = E3;
-          }
-          const double amp = r.amp;
-          if (c1 < ce) s1 = (U1 - E1) * (amp * sm.inv_dv[c1]);
-          if (c2 < ce) s2 = (U2 - E2) * (amp * sm.inv_dv[c2]);
-        } else {  // Dirac line: the live channels are exactly those with lo <= v <= hi
-          const double amp = r.amp;
-          if (c1 < ce) s1 = amp * sm.inv_dv[c1];
-          if (c2 < ce) s2 = amp * sm.inv_dv[c2];
-        }
-        // rotate into place: lane l holds channels cs + l and cs + 32 + l; the row is written
-        // whole (zeros outside the window), so phase C may read any group of four it visits
-        {
-          double* row = sm.S[p];
-          // channels below cs and from ce on: zero.  Lane l clears l (< cs) and the tail.
-          if (lane < cs) row[lane] = 0.0;
-          if (c1 < CB) row[c1] = s1;
-          if (c2 < CB) row[c2] = s2;
-          if (cs > 32 && lane + 32 < cs) row[lane + 32] = 0.0;
-        }
-        if (lane == 0) {
-          const uint32_t hi = ((ce + 3) >> 2) >= 32 ? 0xffffffffu : ((1u << ((ce + 3) >> 2)) - 1u);
-          sm.quads[p] = hi & ~((1u << (cs >> 2)) - 1u);
-        }
+      SetupBuf& S = sm.sb[buf];
+      if (b > 0) {  // every thread observes the completion itself (visibility of rec[buf])
+        mbar_wait(&sm.bar[buf], (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+      }
+      if (warp < 2 && b + 1 < n_batch) {
+        mbar_wait(&sm.bar[buf ^ 1u], (phase >> (buf ^ 1u)) & 1u);  // (parity toggled next iteration)
+        setup_from_records(b + 1);
       }
 
-      // ---- W: kernel integrals, once per (particle, pixel).  The channel warps of a pixel half
-      // share the particles out; two particles per step (two independent evaluation chains).
-      for (int p0 = cw; p0 < nb; p0 += 2 * N_CW) {
-        double wv[2];
-        bool live[2];
-        int kidv[2];
-        double dxv[2], dyv[2], R2v[2], ih2v[2];
+      // ---- phase A: kernel integrals (once per pair) and edge erfs (once per live edge) ---
+      // Items are enumerated through the prefix sums; a warp takes 2 x 32 consecutive items
+      // per step, so its lanes mostly share a particle (coherent branches, conflict-free
+      // rows) and every lane carries two independent dependency chains (the tabulated
+      // evaluators are straight-line code, so the two interleave).
+      {
+        const uint32_t total = S.wprefix[PBATCH];
+        const uint32_t my_start = S.wprefix[lane];
+        const bool my_nonempty = S.wprefix[lane + 1] > my_start;
+        constexpr int NW = 2;  // independent evaluation chains per lane
+        for (uint32_t q0 = warp * 32 * NW; q0 < total; q0 += PROJ_WARPS * 32 * NW) {
+          int ord[NW];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int p = p0 + u * N_CW;
-          live[u] = false;
-          kidv[u] = 0;
-          dxv[u] = dyv[u] = R2v[u] = ih2v[u] = 0.0;
-          if (p < nb) {
-            const Record& r = rec[p];
-            // the candidate box of martini.py:272-274 (computed once by the plan kernels with
-            // the exact predicate), cut to this pixel half; live channels in the brick
-            const bool any = max(r.i0, hx0) <= min(r.i1, hx1) && max(r.j0, y0) <= min(r.j1, y_last) &&
-                             max((int)r.c_first - c0, clo) < min((int)r.c_last + 1 - c0, nch);
-            if (any) {
-              live[u] = true;
-              kidv[u] = r.kid;
-              // dij = pixcoords - ij (martini.py:276)
-              dxv[u] = __dsub_rn(r.px, gxd);
-              dyv[u] = __dsub_rn(r.py, gyd);
-              ih2v[u] = r.inv_h2;
-              R2v[u] = sq_dist(dxv[u], dyv[u]) * ih2v[u];
-            } else if (lane == 0) {
-              sm.nz[ph][p] = 0u;
+          for (int u = 0; u < NW; ++u) ord[u] = owner_ordinal(q0 + 32 * u, my_start, my_nonempty, lane);
+          bool ok[NW];
+          int pp[NW], pix[NW], kind[NW], kid[NW];
+          double dx[NW], dy[NW], R2[NW], ih2[NW], tv[NW];
+#pragma unroll
+          for (int u = 0; u < NW; ++u) {
+            const uint32_t q = q0 + 32 * u + lane;
+            ok[u] = q < total;
+            const int p = ok[u] ? S.wowner[ord[u]] : S.wowner[0];
+            const uint32_t local = ok[u] ? q - S.wprefix[p] : 0u;
+            const int ix = (int)(((float)local + 0.5f) * S.rny[p]);
+            const int iy = (int)local - ix * S.box[p][3];
+            const int tpx = S.box[p][0] + ix, tpy = S.box[p][2] + iy;
+            const Record& r = sm.rec[buf][p];
+            pp[u] = p;
+            pix[u] = tpx * TILE_Y + tpy;
+            kid[u] = r.kid;
+            kind[u] = (KIND >= 0 && kid[u] == 0) ? KIND : a.table.kind[kid[u]];
+            // dij = pixcoords - ij (martini.py:276)
+            dx[u] = __dsub_rn(r.px, (double)(x0 + tpx));
+            dy[u] = __dsub_rn(r.py, (double)(y0 + tpy));
+            ih2[u] = r.inv_h2;
+            R2[u] = sq_dist(dx[u], dy[u]) * ih2[u];
+          }
+#pragma unroll
+          for (int u = 0; u < NW; ++u)  // straight-line, both chains in flight together
+            tv[u] = wtab_eval(KIND >= 0 ? KIND : (wtab_has(kind[u]) ? kind[u] : MTN_KERNEL_WENDLANDC2), R2[u]) * ih2[u];
+#pragma unroll
+          for (int u = 0; u < NW; ++u) {
+            if (ok[u]) {
+              double w = tv[u];
+              // closed form: kernels without a table; with KIND, every entry but the first
+              if (KIND >= 0 ? kid[u] != 0 : !wtab_has(kind[u])) {
+                const Record& r = sm.rec[buf][pp[u]];
+                w = kernel_weight_closed(kind[u], dx[u], dy[u], r.h, r.inv_h2, a.table.truncate[r.kid],
+                                         a.table.norm[r.kid]);
+              }
+              sm.W[pp[u]][pix[u]] = w;
+              if (COUNT) ++n_w;
             }
           }
         }
-        if (!live[0] && !live[1]) continue;
+      }
+      if (gaussian_line) {
+        const uint32_t total = S.eprefix[PBATCH];
+        const uint32_t my_start = S.eprefix[lane];
+        const bool my_nonempty = S.eprefix[lane + 1] > my_start;
+        for (uint32_t q0 = warp * 64; q0 < total; q0 += PROJ_WARPS * 64) {
+          const int ord[2] = {owner_ordinal(q0, my_start, my_nonempty, lane),
+                              owner_ordinal(q0 + 32, my_start, my_nonempty, lane)};
+          bool ok[2];
+          int pp[2], ee[2];
+          double t[2], ev[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {  // straight-line, both chains in flight together
-          const int kind = (KIND >= 0 && kidv[u] == 0) ? KIND : a.table.kind[kidv[u]];
-          wv[u] = wtab_eval(KIND >= 0 ? KIND : (wtab_has(kind) ? kind : MTN_KERNEL_WENDLANDC2), R2v[u]) * ih2v[u];
-        }
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t q = q0 + 32 * u + lane;
+            ok[u] = q < total;
+            const int p = ok[u] ? S.eowner[ord[u]] : S.eowner[0];
+            const int e = ok[u] ? S.erun[p][0] + (int)(q - S.eprefix[p]) : 0;
+            const Record& r = sm.rec[buf][p];
+            pp[u] = p;
+            ee[u] = e;
+            // g orientation (sign folded in): S[c] = E[c+1] - E[c] >= 0; saturated edges at
+            // the ends of the run come out as exactly -1 / +1
+            t[u] = (sm.edge[e] - r.v) * (sgn * r.inv_s);
+          }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (!live[u]) continue;  // (warp-uniform)
-          const int p = p0 + u * N_CW;
-          const Record& r = rec[p];
-          const int kind = (KIND >= 0 && kidv[u] == 0) ? KIND : a.table.kind[kidv[u]];
-          double w = wv[u];
-          // closed form: kernels without a table; with KIND, every entry but the first
-          if (KIND >= 0 ? kidv[u] != 0 : !wtab_has(kind))
-            w = kernel_weight_closed(kind, dxv[u], dyv[u], r.h, r.inv_h2, a.table.truncate[kidv[u]],
-                                     a.table.norm[kidv[u]]);
-          const bool inbox = gx >= r.i0 && gx <= r.i1 && gy >= r.j0 && gy <= r.j1;
-          w = inbox ? w : 0.0;
-          sm.W[ph][p][lane] = w;
-          const uint32_t m = __ballot_sync(0xffffffffu, w != 0.0);
-          if (lane == 0) sm.nz[ph][p] = m;
-          if (COUNT) n_w += inbox && cw == (p % N_CW);
+          for (int u = 0; u < 2; ++u) ev[u] = erf_tab(t[u]);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (ok[u]) {
+              sm.ES[pp[u]][ee[u]] = ev[u];
+              if (COUNT) n_erf += fabs(t[u]) < ERF_SAT;
+            }
+          }
         }
       }
       __syncthreads();
 
-      // ---- C: acc[c] += W * S for the particles that reach this warp's pixels and channels ---
-      {
-        constexpr uint32_t QMASK = (NQ >= 32) ? 0xffffffffu : ((1u << NQ) - 1u);
-        bool mine = false;
-        if (lane < nb) mine = sm.nz[ph][lane] != 0u && ((sm.quads[lane] >> (cw * NQ)) & QMASK) != 0u;
-        uint32_t act = __ballot_sync(0xffffffffu, mine);
-        if (act) {
-          int p = __ffs(act) - 1;
-          act &= act - 1;
-          double w = sm.W[ph][p][lane];
-          uint32_t qm = (sm.quads[p] >> (cw * NQ)) & QMASK;
-          for (;;) {
-            const bool more = act != 0;
-            const int pn = more ? __ffs(act) - 1 : p;
-            act &= act - 1;
-            // the next particle's loads go out ahead of this one's FMAs
-            const double wn = sm.W[ph][pn][lane];
-            const uint32_t qn = (sm.quads[pn] >> (cw * NQ)) & QMASK;
-            const double* Sp = &sm.S[p][cw * NCH];
+      // ---- warp-private list: which particles touch my sub-block, and on which pixels -----
+      uint32_t mymask = 0;
+      if (lane < nb && S.hlive[lane]) {
+        const int bx0 = S.box[lane][0], bx1 = bx0 + S.box[lane][1];
+        const int by0 = S.box[lane][2], by1 = by0 + S.box[lane][3];
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-              if (qm & (1u << q)) {
-                const double2 sa = *reinterpret_cast<const double2*>(Sp + 4 * q);
-                const double2 sb = *reinterpret_cast<const double2*>(Sp + 4 * q + 2);
-                acc[4 * q + 0] = fma(w, sa.x, acc[4 * q + 0]);
-                acc[4 * q + 1] = fma(w, sa.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = fma(w, sb.x, acc[4 * q + 2]);
-                acc[4 * q + 3] = fma(w, sb.y, acc[4 * q + 3]);
-                if (COUNT)
-                  n_upd += w != 0.0 ? (sa.x != 0.0) + (sa.y != 0.0) + (sb.x != 0.0) + (sb.y != 0.0) : 0;
-              }
-            }
-            if (!more) break;
-            p = pn;
-            w = wn;
-            qm = qn;
-          }
+        for (int j = 0; j < SUB_PIX; ++j) {
+          const int tpx = sub_x(sub, j), tpy = sub_y(sub, j);
+          // (the W != 0 test drops the box pixels outside the kernel's support: measured 6 %
+          // faster than box-only masks, which make more warps visit a particle for nothing)
+          if (tpx >= bx0 && tpx < bx1 && tpy >= by0 && tpy < by1 &&
+              sm.W[lane][tpx * TILE_Y + tpy] != 0.0)
+            mymask |= 1u << j;
         }
       }
-      __syncthreads();  // W, S, masks and rec[buf] are free again
+      uint32_t rel = __ballot_sync(0xffffffffu, mymask != 0);
+
+      // ---- phase C: acc[pixel][2 channels] += W * S for the masked pixels -----------------
+      // Software-pipelined: the next particle's mask shuffle, shared-memory loads and spectrum
+      // arithmetic are issued before the current particle's FMAs, so their ~110-cycle chain
+      // (bit scan, shuffle, load) overlaps the FMA stream instead of preceding it.
+      const int c = 2 * lane;
+      const double2 idv = *reinterpret_cast<const double2*>(&sm.inv_dv[c]);
+      // this lane's two channels of particle p's line spectrum, from the shared edge erfs
+      // (adjacent channels share an edge):  S = 0.5 [erf(hi) - erf(lo)] A / dv / 2.36e5, the
+      // 0.5 and 2.36e5 live in amp; channels outside the live range are exactly zero
+      struct RawSpec {  // what spectrum_of needs from shared memory, loaded ahead of time
+        uint32_t chan;
+        double amp, ec;
+        double2 eab;
+      };
+      auto load_spec = [&](int p) {
+        RawSpec r;
+        r.chan = *reinterpret_cast<const uint16_t*>(S.chan[p]);
+        r.amp = sm.rec[buf][p].amp;
+        r.eab = *reinterpret_cast<const double2*>(&sm.ES[p][c]);
+        r.ec = sm.ES[p][c + 2];
+        return r;
+      };
+      auto spectrum_of = [&](const RawSpec& r) {
+        const uint32_t cs = r.chan & 0xffu, span = (r.chan >> 8) - cs;
+        const bool in0 = (uint32_t)c - cs < span, in1 = (uint32_t)c + 1u - cs < span;
+        double2 s2;
+        if (gaussian_line) {
+          s2.x = in0 ? (r.eab.y - r.eab.x) * (r.amp * idv.x) : 0.0;
+          s2.y = in1 ? (r.ec - r.eab.y) * (r.amp * idv.y) : 0.0;
+        } else {  // Dirac line: the live channels are exactly those with lo <= v <= hi
+          s2.x = in0 ? r.amp * idv.x : 0.0;
+          s2.y = in1 ? r.amp * idv.y : 0.0;
+        }
+        return s2;
+      };
+      if (rel) {
+        int p = __ffs(rel) - 1;
+        rel &= rel - 1;
+        uint32_t m = __shfl_sync(0xffffffffu, mymask, p);
+        double2 s2 = spectrum_of(load_spec(p));
+        for (;;) {
+          const bool more = rel != 0;
+          const int pn = more ? __ffs(rel) - 1 : p;
+          rel &= rel - 1;
+          // loads for the next particle go out now, their arithmetic comes after the FMAs
+          const uint32_t mn = __shfl_sync(0xffffffffu, mymask, pn);
+          const RawSpec rn = load_spec(pn);
+          const double* Wp = sm.W[p];
+#pragma unroll
+          for (int j = 0; j < SUB_PIX; ++j) {
+            if (m & (1u << j)) {
+              const double w = Wp[sub_x(sub, j) * TILE_Y + sub_y(sub, j)];
+              acc[j][0] = fma(w, s2.x, acc[j][0]);
+              acc[j][1] = fma(w, s2.y, acc[j][1]);
+              if (COUNT) n_upd += (s2.x != 0.0) + (s2.y != 0.0);
+            }
+          }
+          if (!more) break;
+          p = pn;
+          m = mn;
+          s2 = spectrum_of(rn);
+        }
+      }
+      __syncthreads();  // W, ES, boxes and rec[buf] are free again
       if (b + 2 < n_batch) issue(b + 2);
     }
 
-    // ---- one store per voxel: NCH consecutive channels of this thread's pixel ---------------
-    const int cl0 = cw * NCH;  // first brick channel of this thread
+    // ---- one store per voxel -------------------------------------------------------------
+    const int cl = 2 * lane;  // this lane's first channel within the brick
+    const int nvalid = cl < clo ? 0 : max(0, min(2, nch - cl));
     if (it.slot >= 0) {
-      double* dst = a.partials + ((size_t)it.slot * TILE_PIX + tpx * TILE_Y + tpy) * CB + cl0;
+      double* dst = a.partials + (size_t)it.slot * TILE_PIX * CB + cl;
 #pragma unroll
-      for (int k = 0; k < NCH; k += 2)
-        *reinterpret_cast<double2*>(dst + k) = make_double2(acc[k], acc[k + 1]);
-    } else if (gx <= x_last && gy <= y_last) {
-      double* dst = a.slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + cl0;
-      const bool vec_ok = (g.C & 1) == 0;
+      for (int j = 0; j < SUB_PIX; ++j)
+        *reinterpret_cast<double2*>(dst + (size_t)(sub_x(sub, j) * TILE_Y + sub_y(sub, j)) * CB) =
+            make_double2(acc[j][0], acc[j][1]);
+    } else if (nvalid > 0) {
 #pragma unroll
-      for (int k = 0; k < NCH; k += 2) {
-        const int cl = cl0 + k;
-        const int nvalid = cl < clo ? 0 : max(0, min(2, nch - cl));  // (clo, c0 are even)
-        if (nvalid > 0) store2(dst + k, acc[k], acc[k + 1], nvalid, a.px_area, !a.zeroed, vec_ok);
+      for (int j = 0; j < SUB_PIX; ++j) {
+        const int gx = x0 + sub_x(sub, j), gy = y0 + sub_y(sub, j);
+        if (gx < g.x_hi && gy < g.ny) {
+          double* dst = a.slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + cl;
+          store2(dst, acc[j][0], acc[j][1], nvalid, a.px_area, !a.zeroed, (g.C & 1) == 0);
+        }
       }
     }
   }
@@ -466,50 +573,53 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
   }
 }
 
-// Sum the partial bricks of a multi-chunk brick in chunk order, then store.  One block per
-// (multi-chunk brick, 1/REDUCE_PARTS of its voxels): thread = one channel pair of one pixel,
-// so the hottest brick (most partials) is spread over REDUCE_PARTS blocks.
-constexpr int REDUCE_THREADS = 128;
-constexpr int REDUCE_PARTS = TILE_PIX * CB / 2 / REDUCE_THREADS;
-__global__ void __launch_bounds__(REDUCE_THREADS) reduce_partials_kernel(
+// Sum the partial bricks of a multi-chunk brick in chunk order, then store.
+__global__ void __launch_bounds__(PROJ_THREADS) reduce_partials_kernel(
     Geo g, const MultiBrick* __restrict__ multis, const uint32_t* __restrict__ n_multi,
     const double* __restrict__ partials, double* __restrict__ slab, double px_area, int zeroed) {
   if (blockIdx.x >= *n_multi) return;
   const MultiBrick m = multis[blockIdx.x];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cb = m.brick % g.ncb, tile = m.brick / g.ncb;
   const int x0 = g.x_lo + (tile / g.nty) * TILE_X, y0 = (tile % g.nty) * TILE_Y;
   const int c0 = g.phase[tile] + (cb - 1) * CB;
-  const int e = blockIdx.y * REDUCE_THREADS + threadIdx.x;  // double2 index within the brick
-  const int pix = e / (CB / 2), cl = 2 * (e % (CB / 2));
+  const int sub = warp, cl = 2 * lane;
   const int nvalid = c0 + cl < 0 ? 0 : max(0, min(2, min(CB, g.C - c0) - cl));
-  const double* src = partials + ((size_t)m.slot0 * TILE_PIX + pix) * CB + cl;
-  double a0 = 0.0, a1 = 0.0;
+  {
+    const int j = blockIdx.y;  // one pixel of every sub-block per grid row: the hottest brick
+                               // (most partials) is spread over SUB_PIX blocks
+    const int tpx = sub_x(sub, j), tpy = sub_y(sub, j);
+    const double* src = partials + ((size_t)m.slot0 * TILE_PIX + tpx * TILE_Y + tpy) * CB + cl;
+    double a0 = 0.0, a1 = 0.0;
 #pragma unroll 8
-  for (uint32_t k = 0; k < m.n; ++k) {  // chunk order: deterministic
-    const double2 v = *reinterpret_cast<const double2*>(src + (size_t)k * TILE_PIX * CB);
-    a0 += v.x;
-    a1 += v.y;
-  }
-  const int gx = x0 + pix / TILE_Y, gy = y0 + pix % TILE_Y;
-  if (nvalid > 0 && gx < g.x_hi && gy < g.ny) {
-    double* dst = slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + cl;
-    store2(dst, a0, a1, nvalid, px_area, !zeroed, (g.C & 1) == 0);
+    for (uint32_t k = 0; k < m.n; ++k) {  // chunk order: deterministic
+      const double2 v = *reinterpret_cast<const double2*>(src + (size_t)k * TILE_PIX * CB);
+      a0 += v.x;
+      a1 += v.y;
+    }
+    const int gx = x0 + tpx, gy = y0 + tpy;
+    if (nvalid > 0 && gx < g.x_hi && gy < g.ny) {
+      double* dst = slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + cl;
+      store2(dst, a0, a1, nvalid, px_area, !zeroed, (g.C & 1) == 0);
+    }
   }
 }
 
 // Accumulate mode only: voxels of bricks no particle reaches still get in / px_area.
-__global__ void __launch_bounds__(REDUCE_THREADS) empty_brick_kernel(
+__global__ void __launch_bounds__(PROJ_THREADS) empty_brick_kernel(
     Geo g, const uint32_t* __restrict__ brick_count, double* __restrict__ slab, double px_area) {
   const uint32_t brick = blockIdx.x;
   if (brick_count[brick] != 0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cb = brick % g.ncb, tile = brick / g.ncb;
   const int x0 = g.x_lo + (tile / g.nty) * TILE_X, y0 = (tile % g.nty) * TILE_Y;
   const int c0 = g.phase[tile] + (cb - 1) * CB;
-  for (int e = threadIdx.x; e < TILE_PIX * CB / 2; e += REDUCE_THREADS) {
-    const int pix = e / (CB / 2), cl = 2 * (e % (CB / 2));
-    const int nvalid = c0 + cl < 0 ? 0 : max(0, min(2, min(CB, g.C - c0) - cl));
-    const int gx = x0 + pix / TILE_Y, gy = y0 + pix % TILE_Y;
-    if (nvalid > 0 && gx < g.x_hi && gy < g.ny) {
+  const int sub = warp, cl = 2 * lane;
+  const int nvalid = c0 + cl < 0 ? 0 : max(0, min(2, min(CB, g.C - c0) - cl));
+  if (nvalid == 0) return;
+  for (int j = 0; j < SUB_PIX; ++j) {
+    const int gx = x0 + sub_x(sub, j), gy = y0 + sub_y(sub, j);
+    if (gx < g.x_hi && gy < g.ny) {
       double* dst = slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + cl;
       store2(dst, 0.0, 0.0, nvalid, px_area, true, (g.C & 1) == 0);
     }
