@@ -13,7 +13,7 @@
  *  - the library never owns device memory: scratch comes from caller-provided workspaces
  *    whose sizes are queried first, so the caller's allocator (torch) owns everything;
  *  - all work is enqueued on the caller's CUDA stream; only mtn_plan synchronises (it
- *    returns three counters to the host);
+ *    returns its counters to the host);
  *  - functions return 0 on success, a negative MTN_ERR_* code otherwise, and
  *    mtn_last_error() then returns a thread-local message;
  *  - units: positions / smoothing lengths in pixels (pad included, 0-indexed pixel
@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MTN_VERSION 100 /* 0.1.0 */
+#define MTN_VERSION 200 /* 0.2.0 */
 
 /* error codes */
 #define MTN_OK 0
@@ -114,6 +114,10 @@ typedef struct MtnCube {
   double px_size_arcsec;      /* datacube.px_size: final Jy/pix^2 -> Jy/arcsec^2 */
   const double* edges;        /* n_channels+1 velocity_channel_edges [km/s], monotone */
   double* slab;               /* (x_hi-x_lo, ny, n_channels) float64, in/out */
+  int32_t edges_direction;    /* +1: edges increase with channel index, -1: decrease (the usual
+                                 velocity-mode cube, datacube.py:469-475), 0: unknown -- the
+                                 library then reads two edges back and synchronises */
+  int32_t reserved;
 } MtnCube;
 
 /* What mtn_plan reports back (host memory). */
@@ -124,8 +128,13 @@ typedef struct MtnPlan {
   int64_t updates_dense;   /* U_dense: (particle,pixel,channel) terms the reference loop
                               executes for this slab = C * sum_p n_x(p) n_y(p) */
   int64_t chunk;           /* particles per work item chosen for mtn_project */
+  int64_t n_pairs2;        /* pairs of the second stream: (particle, pixel x channel superblock)
+                              for DiracDelta-kernel particles under a Gaussian line (column
+                              kernel), (particle, tile x channel) for every particle under a
+                              DiracDelta spectrum (splat kernel); 0 if the insertion has none */
+  int64_t chunk2;          /* particles per work item of the second stream */
   int32_t edges_increasing;/* 1 if channel edges increase with channel index */
-  int32_t reserved;
+  int32_t route2;          /* 0: none, 1: column kernel, 2: splat kernel */
   size_t workspace_bytes;  /* device workspace mtn_project needs */
 } MtnPlan;
 
@@ -172,11 +181,14 @@ size_t mtn_plan_scratch_bytes(int64_t n, const MtnCube* cube);
  * Plan the projection of `p` into `cube`: footprints, live channel windows, brick
  * overlap counts.  Synchronises the stream and fills *plan_host.  Replaces the
  * O(n_pix * N) candidate scan of _evaluate_pixel_spectrum (martini.py:272-274) by an
- * O(N) footprint pass.  Limits (MTN_ERR_LIMIT): fewer than 2^32 - 1 (particle, brick)
- * pairs and kept particles per slab, at most 65535 channels.
+ * O(N) footprint pass that also routes every particle to the kernel that computes it (the
+ * brick kernel; the column kernel for DiracDelta-kernel particles, which reach one pixel; the
+ * splat kernel under a DiracDelta spectrum, where a particle reaches one channel) -- which is
+ * why it needs the kernel table.  Limits (MTN_ERR_LIMIT): fewer than 2^32 - 1 pairs per stream
+ * and kept particles per slab, at most 65535 channels.
  */
-int mtn_plan(const MtnParticles* p, const MtnCube* cube, void* scratch, size_t scratch_bytes,
-             MtnPlan* plan_host, void* stream);
+int mtn_plan(const MtnParticles* p, const MtnKernelTable* table, const MtnCube* cube, void* scratch,
+             size_t scratch_bytes, MtnPlan* plan_host, void* stream);
 
 /*
  * Project.  Replaces spectral_model.init_spectra (spectral_models.py:63-147), the pixel

@@ -85,6 +85,8 @@ class MtnCube(C.Structure):
         ("px_size_arcsec", C.c_double),
         ("edges", C.c_void_p),
         ("slab", C.c_void_p),
+        ("edges_direction", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -95,8 +97,10 @@ class MtnPlan(C.Structure):
         ("n_bricks", C.c_int64),
         ("updates_dense", C.c_int64),
         ("chunk", C.c_int64),
+        ("n_pairs2", C.c_int64),
+        ("chunk2", C.c_int64),
         ("edges_increasing", C.c_int32),
-        ("reserved", C.c_int32),
+        ("route2", C.c_int32),
         ("workspace_bytes", C.c_size_t),
     ]
 
@@ -121,8 +125,8 @@ SYMBOLS = {
     "mtn_plan_scratch_bytes": (C.c_size_t, [C.c_int64, C.POINTER(MtnCube)]),
     "mtn_plan": (
         C.c_int,
-        [C.POINTER(MtnParticles), C.POINTER(MtnCube), C.c_void_p, C.c_size_t, C.POINTER(MtnPlan),
-         C.c_void_p],
+        [C.POINTER(MtnParticles), C.POINTER(MtnKernelTable), C.POINTER(MtnCube), C.c_void_p, C.c_size_t,
+         C.POINTER(MtnPlan), C.c_void_p],
     ),
     "mtn_project": (
         C.c_int,

@@ -10,6 +10,7 @@
 #include "project.cuh"
 #include "scan.cuh"
 #include "sort.cuh"
+#include "streams.cuh"
 #include "tables_host.hpp"
 
 namespace mtn {
@@ -134,12 +135,43 @@ static int launch_project_count(const ProjArgs& a, int primary_kind, int64_t max
   }
 }
 
+// The column / splat kernel of an insertion's second stream.
+static int launch_stream(const StreamArgs& a, int route, bool count, unsigned grid, cudaStream_t st) {
+  if (route == ROUTE_COLUMN) {
+    static bool attr_set[MAX_DEVICES][2] = {{false, false}};
+    const int dev = current_device();
+    const int smem = (int)(STREAM_WARPS * CSB * sizeof(double));
+    {
+      std::lock_guard<std::mutex> lock(g_once_mutex);
+      if (!attr_set[dev][count]) {
+        if (count)
+          MTN_CUDA(cudaFuncSetAttribute(column_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else
+          MTN_CUDA(cudaFuncSetAttribute(column_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[dev][count] = true;
+      }
+    }
+    if (count) {
+      MTN_LAUNCH(column_kernel<true>, grid, STREAM_THREADS, smem, st, a);
+    } else {
+      MTN_LAUNCH(column_kernel<false>, grid, STREAM_THREADS, smem, st, a);
+    }
+  } else {
+    if (count) {
+      MTN_LAUNCH(splat_kernel<true>, grid, STREAM_THREADS, 0, st, a);
+    } else {
+      MTN_LAUNCH(splat_kernel<false>, grid, STREAM_THREADS, 0, st, a);
+    }
+  }
+  return MTN_OK;
+}
+
 static int launch_project(const ProjArgs& a, int primary_kind, bool count, int64_t max_items, cudaStream_t st) {
   return count ? launch_project_count<true>(a, primary_kind, max_items, st)
                : launch_project_count<false>(a, primary_kind, max_items, st);
 }
 
-static int make_geo(const MtnCube* c, Geo* g, int edges_increasing) {
+static int make_geo(const MtnCube* c, const MtnKernelTable* table, Geo* g, int edges_increasing) {
   if (!c || c->nx <= 0 || c->ny <= 0 || c->n_channels <= 0)
     return fail(MTN_ERR_INVALID, "cube: bad shape%s", "");
   if (c->x_lo < 0 || c->x_hi > c->nx || c->x_lo >= c->x_hi)
@@ -160,6 +192,31 @@ static int make_geo(const MtnCube* c, Geo* g, int edges_increasing) {
   g->n_bricks = (int)nb;
   g->spectrum = c->spectrum;
   g->edges_increasing = edges_increasing;
+  g->nsb = (c->n_channels + CSB - 1) / CSB;
+  // the second stream (common.cuh: Route): a DiracDelta spectrum sends every particle to the
+  // splat kernel; otherwise the particles on a DiracDelta SPH kernel go to the column kernel.
+  // Keys must fit the sort's 32-bit key; if they do not, everything stays with the bricks.
+  g->route2 = ROUTE_BRICK;
+  g->n_keys2 = 0;
+  for (int i = 0; i < MTN_MAX_KERNELS; ++i) g->kind[i] = (table && i < table->n) ? table->k[i].kind : -1;
+  static int streams = -1;  // MTN_STREAMS=0: developer switch, everything through the brick kernel
+  if (streams < 0) {
+    const char* e = getenv("MTN_STREAMS");
+    streams = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (table && streams) {
+    const int64_t n_tiles = (int64_t)g->ntx * g->nty;
+    const int64_t n_pix = (int64_t)(c->x_hi - c->x_lo) * c->ny;
+    bool dirac_kernel = false;
+    for (int i = 0; i < table->n; ++i) dirac_kernel |= table->k[i].kind == MTN_KERNEL_DIRACDELTA;
+    if (c->spectrum == MTN_SPECTRUM_DIRACDELTA && n_tiles * c->n_channels < (1ll << 31)) {
+      g->route2 = ROUTE_SPLAT;
+      g->n_keys2 = n_tiles * c->n_channels;
+    } else if (c->spectrum == MTN_SPECTRUM_GAUSSIAN && dirac_kernel && n_pix * g->nsb < (1ll << 31)) {
+      g->route2 = ROUTE_COLUMN;
+      g->n_keys2 = n_pix * g->nsb;
+    }
+  }
   return MTN_OK;
 }
 
@@ -183,11 +240,12 @@ static PlanIn make_plan_in(const MtnParticles* p, const MtnCube* c) {
   return in;
 }
 
-// plan scratch: [blk_kept | blk_pairs | totals(8 x u64) | tile_sum | tile_cnt | tile_phase]
+// plan scratch: [blk_kept | blk_pairs | blk_pairs2 | totals(8 x u64) | tile_sum | tile_cnt | tile_phase]
 struct PlanScratch {
   int64_t nblk;
   int64_t* blk_kept;
   int64_t* blk_pairs;
+  int64_t* blk_pairs2;
   unsigned long long* totals;
   unsigned long long* tile_sum;
   unsigned int* tile_cnt;
@@ -207,6 +265,7 @@ static size_t plan_scratch_layout(int64_t n, int64_t n_tiles, void* base, PlanSc
   };
   char* a = take(nblk * sizeof(int64_t));
   char* b = take(nblk * sizeof(int64_t));
+  char* b2 = take(nblk * sizeof(int64_t));
   char* t = take(8 * sizeof(unsigned long long));
   char* ts = take((size_t)n_tiles * sizeof(unsigned long long));
   char* tc = take((size_t)n_tiles * sizeof(unsigned int));
@@ -215,6 +274,7 @@ static size_t plan_scratch_layout(int64_t n, int64_t n_tiles, void* base, PlanSc
     s->nblk = nblk;
     s->blk_kept = (int64_t*)a;
     s->blk_pairs = (int64_t*)b;
+    s->blk_pairs2 = (int64_t*)b2;
     s->totals = (unsigned long long*)t;
     s->tile_sum = (unsigned long long*)ts;
     s->tile_cnt = (unsigned int*)tc;
@@ -223,25 +283,31 @@ static size_t plan_scratch_layout(int64_t n, int64_t n_tiles, void* base, PlanSc
   return off;
 }
 
-// project workspace
-struct Workspace {
-  Record* records;
+// project workspace.  A "stream" is one sorted pair array with its work items: the bricks
+// (stream 0) and, if the insertion has one, the column or splat stream (stream 1).
+struct StreamWs {
   uint64_t* pairs_a;
   uint64_t* pairs_b;
-  uint32_t* hist;
-  void* scan_temp;
-  uint32_t* brick_count;
-  uint32_t* brick_start;
+  uint32_t* key_count;  // per key: particles (brick_bounds writes one-past-last, item_count a count)
+  uint32_t* key_start;
   uint32_t* counts;
   uint32_t* multi;
   uint32_t* ismulti;
-  uint32_t* scalars;  // [n_items, n_slots, n_multi, counter]
+  uint32_t* scalars;  // [n_items, n_slots, n_multi, counter, ...exec counts from +8]
   Item* items;
   MultiBrick* multis;
   double* partials;
   int64_t max_items, max_multi, max_slots;
 };
-static size_t workspace_layout(int64_t n_kept, int64_t n_pairs, int64_t n_bricks, int64_t chunk,
+struct Workspace {
+  Record* records;
+  double* inv_dv;
+  uint32_t* hist;
+  void* scan_temp;
+  StreamWs s[2];
+};
+static size_t workspace_layout(int64_t n_kept, const int64_t n_pairs[2], const int64_t n_keys[2],
+                               const int64_t chunk[2], const int64_t slot_doubles[2], int n_channels,
                                void* base, Workspace* w) {
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -249,31 +315,49 @@ static size_t workspace_layout(int64_t n_kept, int64_t n_pairs, int64_t n_bricks
     off += align_up(bytes ? bytes : 1);
     return p;
   };
-  const int64_t max_multi = n_pairs / chunk + 1;
-  const int64_t max_slots = 2 * (n_pairs / chunk) + 2;
-  const int64_t max_items = std::min<int64_t>(n_bricks, n_pairs) + n_pairs / chunk + 1;
   Workspace ws;
   ws.records = (Record*)take((size_t)n_kept * sizeof(Record));
-  ws.pairs_a = (uint64_t*)take((size_t)n_pairs * 8);
-  ws.pairs_b = (uint64_t*)take((size_t)n_pairs * 8);
-  ws.hist = (uint32_t*)take(sort_hist_bytes(n_pairs));
-  const size_t st = std::max(scan_temp_bytes(sort_num_chunks(n_pairs) * RADIX, 4),
-                             scan_temp_bytes(n_bricks, 4));
-  ws.scan_temp = take(st);
-  ws.brick_count = (uint32_t*)take((size_t)n_bricks * 4);
-  ws.brick_start = (uint32_t*)take((size_t)n_bricks * 4);
-  ws.counts = (uint32_t*)take((size_t)n_bricks * 4);
-  ws.multi = (uint32_t*)take((size_t)n_bricks * 4);
-  ws.ismulti = (uint32_t*)take((size_t)n_bricks * 4);
-  ws.scalars = (uint32_t*)take(64);
-  ws.items = (Item*)take((size_t)max_items * sizeof(Item));
-  ws.multis = (MultiBrick*)take((size_t)max_multi * sizeof(MultiBrick));
-  ws.partials = (double*)take((size_t)max_slots * TILE_PIX * CB * sizeof(double));
-  ws.max_items = max_items;
-  ws.max_multi = max_multi;
-  ws.max_slots = max_slots;
+  ws.inv_dv = (double*)take((size_t)n_channels * sizeof(double));
+  const int64_t np_max = std::max(n_pairs[0], n_pairs[1]), nk_max = std::max(n_keys[0], n_keys[1]);
+  ws.hist = (uint32_t*)take(sort_hist_bytes(np_max));
+  ws.scan_temp = take(std::max(scan_temp_bytes(sort_num_chunks(np_max) * RADIX, 4), scan_temp_bytes(nk_max, 4)));
+  for (int k = 0; k < 2; ++k) {
+    StreamWs& t = ws.s[k];
+    const int64_t np = n_pairs[k], nk = np > 0 || k == 0 ? n_keys[k] : 0, ch = std::max<int64_t>(1, chunk[k]);
+    t.max_multi = np / ch + 1;
+    t.max_slots = 2 * (np / ch) + 2;
+    t.max_items = std::min<int64_t>(nk, np) + np / ch + 1;
+    t.pairs_a = (uint64_t*)take((size_t)np * 8);
+    t.pairs_b = (uint64_t*)take((size_t)np * 8);
+    t.key_count = (uint32_t*)take((size_t)nk * 4);
+    t.key_start = (uint32_t*)take((size_t)nk * 4);
+    t.counts = (uint32_t*)take((size_t)nk * 4);
+    t.multi = (uint32_t*)take((size_t)nk * 4);
+    t.ismulti = (uint32_t*)take((size_t)nk * 4);
+    t.scalars = (uint32_t*)take(64);
+    t.items = (Item*)take((size_t)t.max_items * sizeof(Item));
+    t.multis = (MultiBrick*)take((size_t)t.max_multi * sizeof(MultiBrick));
+    t.partials = (double*)take((size_t)t.max_slots * slot_doubles[k] * sizeof(double));
+  }
   if (w) *w = ws;
   return off;
+}
+
+// The plan's sizes in the form workspace_layout wants them.
+struct PlanSizes {
+  int64_t n_pairs[2], n_keys[2], chunk[2], slot_doubles[2];
+};
+static PlanSizes plan_sizes(const MtnPlan* plan, const Geo& g) {
+  PlanSizes z;
+  z.n_pairs[0] = plan->n_pairs;
+  z.n_pairs[1] = plan->n_pairs2;
+  z.n_keys[0] = g.n_bricks;
+  z.n_keys[1] = g.n_keys2;
+  z.chunk[0] = plan->chunk;
+  z.chunk[1] = plan->chunk2;
+  z.slot_doubles[0] = (int64_t)TILE_PIX * CB;
+  z.slot_doubles[1] = g.route2 == ROUTE_COLUMN ? CSB : TILE_PIX;
+  return z;
 }
 
 static int64_t choose_chunk(int64_t n_pairs) {
@@ -284,6 +368,14 @@ static int64_t choose_chunk(int64_t n_pairs) {
     rounds = e ? std::max(1, atoi(e)) : 8;
   }
   const int64_t target = (int64_t)sm_count() * PROJ_CTAS_PER_SM * rounds;
+  int64_t chunk = std::max<int64_t>(8 * PBATCH, (n_pairs + target - 1) / target);
+  return (chunk + PBATCH - 1) / PBATCH * PBATCH;
+}
+
+// Work items of the column / splat kernels are taken by warps: ~8 rounds over the resident
+// warps, never smaller than 8 batches.
+static int64_t choose_chunk2(int64_t n_pairs) {
+  const int64_t target = (int64_t)sm_count() * 16 * 8;
   int64_t chunk = std::max<int64_t>(8 * PBATCH, (n_pairs + target - 1) / target);
   return (chunk + PBATCH - 1) / PBATCH * PBATCH;
 }
@@ -399,7 +491,11 @@ static int check_particles(const MtnParticles* p) {
 
 static int edges_direction(const MtnCube* cube, cudaStream_t st, int* increasing) {
   // the host mirror validates monotonicity (spectral_models.py:180-187); here only the
-  // direction is needed
+  // direction is needed.  A caller that knows it says so (no device read-back, no sync).
+  if (cube->edges_direction > 0 || cube->edges_direction < 0) {
+    *increasing = cube->edges_direction > 0 ? 1 : 0;
+    return MTN_OK;
+  }
   double e[2];
   MTN_CUDA(cudaMemcpyAsync(e, cube->edges, sizeof(e), cudaMemcpyDeviceToHost, st));
   MTN_CUDA(cudaStreamSynchronize(st));
@@ -407,10 +503,10 @@ static int edges_direction(const MtnCube* cube, cudaStream_t st, int* increasing
   return MTN_OK;
 }
 
-int mtn_plan(const MtnParticles* p, const MtnCube* cube, void* scratch, size_t scratch_bytes,
-             MtnPlan* plan, void* stream) {
+int mtn_plan(const MtnParticles* p, const MtnKernelTable* table, const MtnCube* cube, void* scratch,
+             size_t scratch_bytes, MtnPlan* plan, void* stream) {
   if (int rc = check_particles(p)) return rc;
-  if (!cube || !cube->edges || !plan) return fail(MTN_ERR_INVALID, "plan: bad arguments%s", "");
+  if (!cube || !cube->edges || !plan || !table) return fail(MTN_ERR_INVALID, "plan: bad arguments%s", "");
   cudaStream_t st = (cudaStream_t)stream;
   PlanScratch ps;
   if (plan_scratch_layout(p->n, num_tiles(cube), scratch, &ps) > scratch_bytes || !scratch)
@@ -418,13 +514,14 @@ int mtn_plan(const MtnParticles* p, const MtnCube* cube, void* scratch, size_t s
   int inc = 0;
   if (int rc = edges_direction(cube, st, &inc)) return rc;
   Geo g;
-  if (int rc = make_geo(cube, &g, inc)) return rc;
+  if (int rc = make_geo(cube, table, &g, inc)) return rc;
+  if (cube->n_channels > 65535) return fail(MTN_ERR_LIMIT, "plan: more than 65535 channels%s", "");
   g.phase = ps.tile_phase;
   const int n_tiles = g.ntx * g.nty;
   MTN_CUDA(cudaMemsetAsync(ps.totals, 0, 8 * sizeof(unsigned long long), st));
   MTN_CUDA(cudaMemsetAsync(ps.tile_sum, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
   MTN_CUDA(cudaMemsetAsync(ps.tile_cnt, 0, (size_t)n_tiles * sizeof(unsigned int), st));
-  if (p->n > 0) {
+  if (p->n > 0 && g.route2 != ROUTE_SPLAT) {  // (the splat stream has no channel blocks to phase)
     MTN_LAUNCH(tile_stats_kernel, (unsigned)((ps.nblk + TILE_STAT_STRIDE - 1) / TILE_STAT_STRIDE),
                PLAN_THREADS, 0, st, make_plan_in(p, cube), g, ps.tile_sum, ps.tile_cnt);
     MTN_LAUNCH_CHECK();
@@ -434,30 +531,54 @@ int mtn_plan(const MtnParticles* p, const MtnCube* cube, void* scratch, size_t s
   MTN_LAUNCH_CHECK();
   if (p->n > 0) {
     MTN_LAUNCH(plan_count_kernel, (unsigned)ps.nblk, PLAN_THREADS, 0, st, make_plan_in(p, cube), g,
-               ps.blk_kept, ps.blk_pairs, ps.totals + 2);
+               ps.blk_kept, ps.blk_pairs, ps.blk_pairs2, ps.totals + 3);
     MTN_LAUNCH_CHECK();
-    MTN_LAUNCH(scan_sums_inplace<int64_t>, 1, 1024, 0, st, ps.blk_kept, ps.nblk, (int64_t*)ps.totals);
-    MTN_LAUNCH_CHECK();
-    MTN_LAUNCH(scan_sums_inplace<int64_t>, 1, 1024, 0, st, ps.blk_pairs, ps.nblk, (int64_t*)ps.totals + 1);
+    MTN_LAUNCH(scan3_sums_inplace, 3, 1024, 0, st, ps.blk_kept, ps.blk_pairs, ps.blk_pairs2, ps.nblk,
+               (int64_t*)ps.totals);
     MTN_LAUNCH_CHECK();
   }
-  unsigned long long tot[3];
+  unsigned long long tot[4];
   MTN_CUDA(cudaMemcpyAsync(tot, ps.totals, sizeof(tot), cudaMemcpyDeviceToHost, st));
   MTN_CUDA(cudaStreamSynchronize(st));
   plan->n_kept = (int64_t)tot[0];
   plan->n_pairs = (int64_t)tot[1];
-  plan->updates_dense = (int64_t)tot[2];
+  plan->n_pairs2 = (int64_t)tot[2];
+  plan->updates_dense = (int64_t)tot[3];
   plan->n_bricks = g.n_bricks;
-  if (cube->n_channels > 65535)
-    return fail(MTN_ERR_LIMIT, "plan: more than 65535 channels%s", "");
-  if (plan->n_pairs >= (1ll << 32) - 1 || plan->n_kept >= (1ll << 32) - 1)
+  plan->route2 = g.route2;
+  if (std::max(plan->n_pairs, plan->n_pairs2) >= (1ll << 32) - 1 || plan->n_kept >= (1ll << 32) - 1)
     return fail(MTN_ERR_LIMIT, "plan: %s%lld pairs exceed the 32-bit sort index; split the slab", "",
-                (long long)plan->n_pairs);
+                (long long)std::max(plan->n_pairs, plan->n_pairs2));
   plan->chunk = choose_chunk(plan->n_pairs);
+  plan->chunk2 = choose_chunk2(plan->n_pairs2);
   plan->edges_increasing = inc;
-  plan->reserved = 0;
-  plan->workspace_bytes =
-      workspace_layout(plan->n_kept, plan->n_pairs, plan->n_bricks, plan->chunk, nullptr, nullptr);
+  const PlanSizes z = plan_sizes(plan, g);
+  plan->workspace_bytes = workspace_layout(plan->n_kept, z.n_pairs, z.n_keys, z.chunk, z.slot_doubles,
+                                           cube->n_channels, nullptr, nullptr);
+  return MTN_OK;
+}
+
+// Sort one stream's pairs by key and cut the sorted runs into work items.
+static int build_items(StreamWs& t, int64_t n_pairs, int64_t n_keys, int64_t chunk, uint32_t* hist,
+                       void* scan_temp, uint64_t** sorted, cudaStream_t st) {
+  int key_bits = 1;
+  while ((1ll << key_bits) < n_keys) ++key_bits;
+  if (int rc = radix_sort_pairs(t.pairs_a, t.pairs_b, n_pairs, key_bits, hist, scan_temp, sorted, st)) return rc;
+  mark(2, st);
+  MTN_LAUNCH(brick_bounds_kernel, (unsigned)((n_pairs + 255) / 256), 256, 0, st, *sorted, n_pairs, t.key_start,
+             t.key_count);
+  MTN_LAUNCH_CHECK();
+  const unsigned bgrid = (unsigned)((n_keys + 255) / 256);
+  MTN_LAUNCH(item_count_kernel, bgrid, 256, 0, st, t.key_count, t.key_start, (int)n_keys, (uint32_t)chunk,
+             t.counts, t.multi, t.ismulti);
+  MTN_LAUNCH_CHECK();
+  if (int rc = exclusive_scan<uint32_t, uint32_t>(t.counts, t.counts, n_keys, scan_temp, t.scalars + 0, st)) return rc;
+  if (int rc = exclusive_scan<uint32_t, uint32_t>(t.multi, t.multi, n_keys, scan_temp, t.scalars + 1, st)) return rc;
+  if (int rc = exclusive_scan<uint32_t, uint32_t>(t.ismulti, t.ismulti, n_keys, scan_temp, t.scalars + 2, st))
+    return rc;
+  MTN_LAUNCH(item_fill_kernel, bgrid, 256, 0, st, t.key_count, t.key_start, (int)n_keys, (uint32_t)chunk, t.counts,
+             t.multi, t.ismulti, t.items, t.multis);
+  MTN_LAUNCH_CHECK();
   return MTN_OK;
 }
 
@@ -476,91 +597,116 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
   PlanScratch ps;
   if (plan_scratch_layout(p->n, num_tiles(cube), scratch, &ps) > scratch_bytes || !scratch)
     return fail(MTN_ERR_WORKSPACE, "project: scratch too small%s", "");
+  Geo g;
+  if (int rc = make_geo(cube, table, &g, plan->edges_increasing)) return rc;
+  if (g.n_bricks != plan->n_bricks || g.route2 != plan->route2)
+    return fail(MTN_ERR_INVALID, "project: plan/cube mismatch%s", "");
+  g.phase = ps.tile_phase;  // written by mtn_plan into the caller's scratch
+  const PlanSizes z = plan_sizes(plan, g);
   Workspace ws;
-  if (workspace_layout(plan->n_kept, plan->n_pairs, plan->n_bricks, plan->chunk, workspace, &ws) >
-          workspace_bytes ||
+  if (workspace_layout(plan->n_kept, z.n_pairs, z.n_keys, z.chunk, z.slot_doubles, cube->n_channels, workspace,
+                       &ws) > workspace_bytes ||
       !workspace)
     return fail(MTN_ERR_WORKSPACE, "project: workspace too small%s", "");
-  Geo g;
-  if (int rc = make_geo(cube, &g, plan->edges_increasing)) return rc;
-  if (g.n_bricks != plan->n_bricks) return fail(MTN_ERR_INVALID, "project: plan/cube mismatch%s", "");
-  g.phase = ps.tile_phase;  // written by mtn_plan into the caller's scratch
   const double px_area = cube->px_size_arcsec * cube->px_size_arcsec;
   const int zeroed = (cube->flags & MTN_CUBE_ZEROED) ? 1 : 0;
+  const bool stream2 = plan->n_pairs2 > 0;
 
-  MTN_CUDA(cudaMemsetAsync(ws.brick_count, 0, (size_t)g.n_bricks * 4, st));
-  MTN_CUDA(cudaMemsetAsync(ws.scalars, 0, 64, st));
+  MTN_CUDA(cudaMemsetAsync(ws.s[0].key_count, 0, (size_t)g.n_bricks * 4, st));
+  MTN_CUDA(cudaMemsetAsync(ws.s[0].scalars, 0, 64, st));
+  if (stream2) {
+    MTN_CUDA(cudaMemsetAsync(ws.s[1].key_count, 0, (size_t)g.n_keys2 * 4, st));
+    MTN_CUDA(cudaMemsetAsync(ws.s[1].scalars, 0, 64, st));
+  }
   g_ev_valid = false;
   mark(0, st);
   for (int k = 1; k <= N_STAGES; ++k) mark(k, st);  // stages skipped below read as 0 ms
+  for (int k = 0; k < 3; ++k) g_exec_counts[k] = 0;
 
-  if (plan->n_pairs > 0) {
+  if (plan->n_pairs + plan->n_pairs2 > 0) {
     MTN_LAUNCH(plan_emit_kernel, (unsigned)ps.nblk, PLAN_THREADS, 0, st, make_plan_in(p, cube), g,
-               ps.blk_kept, ps.blk_pairs, ws.records, ws.pairs_a);
+               ps.blk_kept, ps.blk_pairs, ps.blk_pairs2, ws.records, ws.s[0].pairs_a, ws.s[1].pairs_a);
     MTN_LAUNCH_CHECK();
-
-    mark(1, st);
-    int key_bits = 1;
-    while ((1ll << key_bits) < g.n_bricks) ++key_bits;
-    uint64_t* sorted = nullptr;
-    if (int rc = radix_sort_pairs(ws.pairs_a, ws.pairs_b, plan->n_pairs, key_bits, ws.hist,
-                                  ws.scan_temp, &sorted, st))
+  }
+  mark(1, st);
+  uint64_t* sorted[2] = {nullptr, nullptr};
+  if (plan->n_pairs > 0)
+    if (int rc = build_items(ws.s[0], plan->n_pairs, g.n_bricks, plan->chunk, ws.hist, ws.scan_temp, &sorted[0], st))
       return rc;
-
-    mark(2, st);
-    MTN_LAUNCH(brick_bounds_kernel, (unsigned)((plan->n_pairs + 255) / 256), 256, 0, st, sorted,
-               plan->n_pairs, ws.brick_start, ws.brick_count);
+  if (stream2) {
+    if (int rc = build_items(ws.s[1], plan->n_pairs2, g.n_keys2, plan->chunk2, ws.hist, ws.scan_temp, &sorted[1], st))
+      return rc;
+    MTN_LAUNCH(inv_dv_kernel, (unsigned)((g.C + 255) / 256), 256, 0, st, cube->edges, g.C, ws.inv_dv);
     MTN_LAUNCH_CHECK();
-    const unsigned bgrid = (unsigned)((g.n_bricks + 255) / 256);
-    MTN_LAUNCH(item_count_kernel, bgrid, 256, 0, st, ws.brick_count, ws.brick_start, g.n_bricks,
-               (uint32_t)plan->chunk, ws.counts, ws.multi, ws.ismulti);
-    MTN_LAUNCH_CHECK();
-    if (int rc = exclusive_scan<uint32_t, uint32_t>(ws.counts, ws.counts, g.n_bricks, ws.scan_temp,
-                                                    ws.scalars + 0, st))
-      return rc;
-    if (int rc = exclusive_scan<uint32_t, uint32_t>(ws.multi, ws.multi, g.n_bricks, ws.scan_temp,
-                                                    ws.scalars + 1, st))
-      return rc;
-    if (int rc = exclusive_scan<uint32_t, uint32_t>(ws.ismulti, ws.ismulti, g.n_bricks, ws.scan_temp,
-                                                    ws.scalars + 2, st))
-      return rc;
-    MTN_LAUNCH(item_fill_kernel, bgrid, 256, 0, st, ws.brick_count, ws.brick_start, g.n_bricks,
-               (uint32_t)plan->chunk, ws.counts, ws.multi, ws.ismulti, ws.items, ws.multis);
-    MTN_LAUNCH_CHECK();
-
+  }
+  mark(3, st);
+  if (plan->n_pairs > 0) {
     ProjArgs a;
     a.geo = g;
     a.table = t;
     a.records = ws.records;
-    a.pairs = sorted;
-    a.items = ws.items;
-    a.n_items = ws.scalars + 0;
-    a.counter = ws.scalars + 3;
+    a.pairs = sorted[0];
+    a.items = ws.s[0].items;
+    a.n_items = ws.s[0].scalars + 0;
+    a.counter = ws.s[0].scalars + 3;
     a.edges = cube->edges;
     a.slab = cube->slab;
-    a.partials = ws.partials;
+    a.partials = ws.s[0].partials;
     a.px_area = px_area;
     a.zeroed = zeroed;
-    a.exec_counts = (unsigned long long*)(ws.scalars + 8);  // zeroed with the scalars
+    a.exec_counts = (unsigned long long*)(ws.s[0].scalars + 8);  // zeroed with the scalars
     // the instantiation specialised on the kind of table entry 0 (if that kind is tabulated)
-    mark(3, st);
-    if (int rc = launch_project(a, t.kind[0], g_count_exec != 0, ws.max_items, st)) return rc;
+    if (int rc = launch_project(a, t.kind[0], g_count_exec != 0, ws.s[0].max_items, st)) return rc;
     MTN_LAUNCH_CHECK();
     mark(4, st);
-    MTN_LAUNCH(reduce_partials_kernel, dim3((unsigned)ws.max_multi, SUB_PIX), PROJ_THREADS, 0, st, g,
-               ws.multis, ws.scalars + 2, ws.partials, cube->slab, px_area, zeroed);
+    MTN_LAUNCH(reduce_partials_kernel, dim3((unsigned)ws.s[0].max_multi, SUB_PIX), PROJ_THREADS, 0, st, g,
+               ws.s[0].multis, ws.s[0].scalars + 2, ws.s[0].partials, cube->slab, px_area, zeroed);
     MTN_LAUNCH_CHECK();
-    if (g_count_exec) {
-      MTN_CUDA(cudaMemcpyAsync(g_exec_counts, a.exec_counts, sizeof(g_exec_counts),
-                               cudaMemcpyDeviceToHost, st));
-      MTN_CUDA(cudaStreamSynchronize(st));
-    }
+  } else {
+    mark(4, st);
   }
   mark(5, st);
-  if (!zeroed) {
-    MTN_LAUNCH(empty_brick_kernel, (unsigned)g.n_bricks, PROJ_THREADS, 0, st, g, ws.brick_count, cube->slab,
+  if (!zeroed) {  // voxels of bricks no brick-kernel particle reaches still get in / px_area
+    MTN_LAUNCH(empty_brick_kernel, (unsigned)g.n_bricks, PROJ_THREADS, 0, st, g, ws.s[0].key_count, cube->slab,
                px_area);
     MTN_LAUNCH_CHECK();
+  }
+  if (stream2) {  // the column / splat kernel adds onto what the brick kernel has written
+    StreamArgs a;
+    a.geo = g;
+    a.table = t;
+    a.records = ws.records;
+    a.pairs = sorted[1];
+    a.items = ws.s[1].items;
+    a.n_items = ws.s[1].scalars + 0;
+    a.counter = ws.s[1].scalars + 3;
+    a.edges = cube->edges;
+    a.inv_dv = ws.inv_dv;
+    a.slab = cube->slab;
+    a.partials = ws.s[1].partials;
+    a.px_area = px_area;
+    a.exec_counts = (unsigned long long*)(ws.s[1].scalars + 8);
+    // resident CTAs per SM: column 48 registers + 32 KB of shared memory, splat 96 registers
+    const unsigned grid = (unsigned)std::min<int64_t>((ws.s[1].max_items + STREAM_WARPS - 1) / STREAM_WARPS,
+                                                      (int64_t)sm_count() * (g.route2 == ROUTE_COLUMN ? 6 : 5));
+    if (int rc = launch_stream(a, g.route2, g_count_exec != 0, grid, st)) return rc;
+    MTN_LAUNCH_CHECK();
+    if (g.route2 == ROUTE_COLUMN) {
+      MTN_LAUNCH(column_reduce_kernel, (unsigned)ws.s[1].max_multi, 256, 0, st, g, ws.s[1].multis,
+                 ws.s[1].scalars + 2, ws.s[1].partials, cube->slab, px_area);
+    } else {
+      MTN_LAUNCH(splat_reduce_kernel, (unsigned)ws.s[1].max_multi, TILE_PIX, 0, st, g, ws.s[1].multis,
+                 ws.s[1].scalars + 2, ws.s[1].partials, cube->slab, px_area);
+    }
+    MTN_LAUNCH_CHECK();
+  }
+  if (g_count_exec) {
+    unsigned long long c[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    if (plan->n_pairs > 0)
+      MTN_CUDA(cudaMemcpyAsync(c[0], ws.s[0].scalars + 8, sizeof(c[0]), cudaMemcpyDeviceToHost, st));
+    if (stream2) MTN_CUDA(cudaMemcpyAsync(c[1], ws.s[1].scalars + 8, sizeof(c[1]), cudaMemcpyDeviceToHost, st));
+    MTN_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < 3; ++k) g_exec_counts[k] = c[0][k] + c[1][k];
   }
   mark(6, st);
   g_ev_valid = g_timing != 0;

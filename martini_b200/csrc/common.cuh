@@ -55,6 +55,18 @@ constexpr int REC_BYTES = REC_DOUBLES * 8;
 // reference (scipy) and here, so skipping them is bit-safe.
 constexpr double ERF_SAT = 6.0;
 
+// Where a particle's contributions are computed (plan.cuh: footprint).  The general case is
+// the brick kernel (project.cuh).  Two degenerate shapes get kernels of their own
+// (streams.cuh), each with the lanes of a warp laid along the one axis that is left:
+//   COLUMN  DiracDelta SPH kernel (sph_kernels.py:1136-1165): the particle reaches exactly one
+//           pixel, so it is a line profile added to one voxel column -- key = (pixel, channel
+//           superblock), lanes = channels;
+//   SPLAT   DiracDelta spectrum (spectral_models.py:510-570): the particle reaches one channel
+//           (two if it sits on a channel edge), so it is a kernel image added to one channel
+//           map -- key = (tile, channel), lanes = pixels.
+enum Route { ROUTE_BRICK = 0, ROUTE_COLUMN = 1, ROUTE_SPLAT = 2 };
+constexpr int CSB = 1024;  // channels per superblock of the column kernel (8 KB of shared memory per warp)
+
 struct Geo {
   int nx, ny, C;        // full cube
   int x_lo, x_hi;       // slab rows
@@ -63,6 +75,10 @@ struct Geo {
   const int* phase;     // per-tile channel phase in [0, CB): block k = [ph + (k-1) CB, ph + k CB)
   int spectrum;         // MTN_SPECTRUM_*
   int edges_increasing; // 1 if edges[c+1] > edges[c]
+  int nsb;              // channel superblocks of the column kernel: ceil(C / CSB)
+  int route2;           // ROUTE_COLUMN / ROUTE_SPLAT: the second stream of this insertion; 0: none
+  int64_t n_keys2;      // keys of the second stream
+  int kind[MTN_MAX_KERNELS];  // MTN_KERNEL_* of each kernel-table entry
 };
 
 // One staged particle: everything the projection kernel needs.  The footprint (candidate box

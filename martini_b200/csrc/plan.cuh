@@ -91,7 +91,9 @@ struct Foot {
   int i0, i1, j0, j1;  // inclusive pixel bounds (full-cube coordinates), clipped to the slab
   int c0, c1;          // inclusive live-channel window
   bool box;            // candidate box reaches the slab (counts towards U_dense)
-  bool live;           // box && a live channel exists
+  bool live;           // box && a live channel exists (&& a pixel with non-zero weight, COLUMN)
+  int route;           // Route: which kernel computes this particle
+  int nbx, nby;        // extent of the reference's candidate box in the slab (U_dense)
 };
 
 // Smallest and largest integer i in [lim_lo, lim_hi] with |i - p| <= r, the candidate test
@@ -176,17 +178,45 @@ __device__ __forceinline__ double inv_sqrt2_sigma(const PlanIn& in, int64_t i) {
   return 1.0 / (1.4142135623730951 * sg);
 }
 
+// The one pixel a DiracDelta-kernel particle reaches: |p - i| < 0.5 on both axes, strict
+// (sph_kernels.py:1165), evaluated as numpy does (fl(p - i)); false if there is none (a
+// particle exactly on a pixel edge lands nowhere) or it lies outside [lo, hi].
+__device__ __forceinline__ bool dirac_pixel(double p, int lo, int hi, int& i) {
+  if (!(fabs(p) < 1.0e9)) return false;
+  const int k = (int)rint(p);
+  if (k < lo || k > hi || !(fabs(__dsub_rn(p, (double)k)) < 0.5)) return false;
+  i = k;
+  return true;
+}
+
 __device__ __forceinline__ Foot footprint(const PlanIn& in, const Geo& g, int64_t i) {
   Foot f;
   f.box = f.live = false;
+  f.route = ROUTE_BRICK;
   if (in.accept && !in.accept[i]) return f;
   const double r = in.sm_range[i];
   if (!pixel_bounds(in.px[i], r, g.x_lo, g.x_hi - 1, f.i0, f.i1)) return f;
   if (!pixel_bounds(in.py[i], r, 0, g.ny - 1, f.j0, f.j1)) return f;
   f.box = true;
+  f.nbx = f.i1 - f.i0 + 1;
+  f.nby = f.j1 - f.j0 + 1;
   const double inv_s = g.spectrum == MTN_SPECTRUM_GAUSSIAN ? inv_sqrt2_sigma(in, i) : 1.0;
   f.live = channel_window(in.edges, g.C, g.edges_increasing ? 1 : -1, g.spectrum, in.v[i], inv_s,
                           f.c0, f.c1);
+  if (!f.live) return f;
+  if (g.route2 == ROUTE_SPLAT) {
+    f.route = ROUTE_SPLAT;
+  } else if (g.route2 == ROUTE_COLUMN && g.kind[in.kernel_id ? in.kernel_id[i] : 0] == MTN_KERNEL_DIRACDELTA) {
+    // the candidate box shrinks to the single pixel with non-zero weight (or to nothing)
+    f.route = ROUTE_COLUMN;
+    int x, y;
+    if (dirac_pixel(in.px[i], f.i0, f.i1, x) && dirac_pixel(in.py[i], f.j0, f.j1, y)) {
+      f.i0 = f.i1 = x;
+      f.j0 = f.j1 = y;
+    } else {
+      f.live = false;
+    }
+  }
   return f;
 }
 
@@ -215,7 +245,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) tile_stats_kernel(
   const int64_t i = ((int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x) * TILE_STAT_STRIDE;
   if (i >= in.n) return;
   const Foot f = footprint(in, g, i);
-  if (!f.live) return;
+  if (!f.live || f.route != ROUTE_BRICK) return;
   int tx0, tx1, ty0, ty1;
   tile_range(f, g, tx0, tx1, ty0, ty1);
   const unsigned long long centre2 = (unsigned long long)(f.c0 + f.c1 + 1);
@@ -241,9 +271,13 @@ __global__ void __launch_bounds__(256) tile_phase_kernel(int n_tiles,
   phase[t] = ph;
 }
 
+// Pairs a particle contributes to its stream: (particle, brick) for the brick kernel,
+// (particle, pixel x channel superblock) for COLUMN, (particle, tile x channel) for SPLAT.
 __device__ __forceinline__ int64_t count_pairs(const Foot& f, const Geo& g) {
+  if (f.route == ROUTE_COLUMN) return f.c1 / CSB - f.c0 / CSB + 1;
   int tx0, tx1, ty0, ty1;
   tile_range(f, g, tx0, tx1, ty0, ty1);
+  if (f.route == ROUTE_SPLAT) return (int64_t)(tx1 - tx0 + 1) * (ty1 - ty0 + 1) * (f.c1 - f.c0 + 1);
   int64_t n = 0;
   for (int tx = tx0; tx <= tx1; ++tx)
     for (int ty = ty0; ty <= ty1; ++ty) {
@@ -257,25 +291,28 @@ __device__ __forceinline__ int64_t count_pairs(const Foot& f, const Geo& g) {
 // Pass 1: per-block totals of (kept particles, bricks overlapped) and the slab's U_dense.
 __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(
     PlanIn in, Geo g, int64_t* __restrict__ blk_kept, int64_t* __restrict__ blk_pairs,
-    unsigned long long* __restrict__ updates) {
+    int64_t* __restrict__ blk_pairs2, unsigned long long* __restrict__ updates) {
   __shared__ int64_t sm[33];
   const int64_t i = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
-  int64_t kept = 0, pairs = 0, upd = 0;
+  int64_t kept = 0, pairs = 0, pairs2 = 0, upd = 0;
   if (i < in.n) {
     const Foot f = footprint(in, g, i);
-    if (f.box) upd = (int64_t)(f.i1 - f.i0 + 1) * (f.j1 - f.j0 + 1) * g.C;
+    // U_dense counts the reference's candidate box, whatever kernel computes the particle
+    if (f.box) upd = (int64_t)f.nbx * f.nby * g.C;
     if (f.live) {
       kept = 1;
-      pairs = count_pairs(f, g);
+      (f.route == ROUTE_BRICK ? pairs : pairs2) = count_pairs(f, g);
     }
   }
-  int64_t tk, tp, tu;
+  int64_t tk, tp, tq, tu;
   block_excl_scan(kept, sm, &tk);
   block_excl_scan(pairs, sm, &tp);
+  block_excl_scan(pairs2, sm, &tq);
   block_excl_scan(upd, sm, &tu);
   if (threadIdx.x == 0) {
     blk_kept[blockIdx.x] = tk;
     blk_pairs[blockIdx.x] = tp;
+    blk_pairs2[blockIdx.x] = tq;
     if (tu) atomicAdd(updates, (unsigned long long)tu);
   }
 }
@@ -284,22 +321,25 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(
 // and one (brick key << 32 | record index) pair per brick it overlaps, in particle order.
 __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
     PlanIn in, Geo g, const int64_t* __restrict__ blk_kept, const int64_t* __restrict__ blk_pairs,
-    Record* __restrict__ records, uint64_t* __restrict__ pairs_out) {
+    const int64_t* __restrict__ blk_pairs2, Record* __restrict__ records,
+    uint64_t* __restrict__ pairs_out, uint64_t* __restrict__ pairs2_out) {
   __shared__ int64_t sm[33];
   const int64_t i = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
-  int64_t kept = 0, npair = 0;
+  int64_t kept = 0, npair = 0, npair2 = 0;
   Foot f;
   f.live = false;
+  f.route = ROUTE_BRICK;
   if (i < in.n) {
     f = footprint(in, g, i);
     if (f.live) {
       kept = 1;
-      npair = count_pairs(f, g);
+      (f.route == ROUTE_BRICK ? npair : npair2) = count_pairs(f, g);
     }
   }
   int64_t tk, tp;
   const int64_t ridx = blk_kept[blockIdx.x] + block_excl_scan(kept, sm, &tk);
   int64_t off = blk_pairs[blockIdx.x] + block_excl_scan(npair, sm, &tp);
+  int64_t off2 = blk_pairs2[blockIdx.x] + block_excl_scan(npair2, sm, &tp);
   if (!f.live) return;
   Record rec;
   rec.px = in.px[i];
@@ -328,11 +368,22 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
   rec.kid = in.kernel_id ? in.kernel_id[i] : (uint8_t)0;
   for (int k = 0; k < 3; ++k) rec.pad[k] = 0;
   records[ridx] = rec;
+  if (f.route == ROUTE_COLUMN) {
+    const int64_t pixel = (int64_t)(f.i0 - g.x_lo) * g.ny + f.j0;
+    for (int sb = f.c0 / CSB; sb <= f.c1 / CSB; ++sb)
+      pairs2_out[off2++] = ((uint64_t)(uint32_t)(pixel * g.nsb + sb) << 32) | (uint64_t)(uint32_t)ridx;
+    return;
+  }
   int tx0, tx1, ty0, ty1;
   tile_range(f, g, tx0, tx1, ty0, ty1);
   for (int tx = tx0; tx <= tx1; ++tx)
     for (int ty = ty0; ty <= ty1; ++ty) {
       const int tile = tx * g.nty + ty;
+      if (f.route == ROUTE_SPLAT) {
+        for (int c = f.c0; c <= f.c1; ++c)
+          pairs2_out[off2++] = ((uint64_t)(uint32_t)((int64_t)tile * g.C + c) << 32) | (uint64_t)(uint32_t)ridx;
+        continue;
+      }
       int k0, k1;
       block_range(f, g.phase[tile], k0, k1);
       for (int k = k0; k <= k1; ++k) {

@@ -78,6 +78,25 @@ __global__ void __launch_bounds__(1024) scan_sums_inplace(T* __restrict__ sums, 
   if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 
+// Three arrays of block sums scanned by the three CTAs of ONE launch (mtn_plan's kept /
+// pairs / second-stream pairs); totals to total_out[blockIdx.x].
+__global__ void __launch_bounds__(1024) scan3_sums_inplace(int64_t* __restrict__ a, int64_t* __restrict__ b,
+                                                           int64_t* __restrict__ c, int64_t m,
+                                                           int64_t* __restrict__ total_out) {
+  __shared__ int64_t sm[33];
+  int64_t* sums = blockIdx.x == 0 ? a : (blockIdx.x == 1 ? b : c);
+  int64_t carry = 0;
+  for (int64_t base = 0; base < m; base += blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    const int64_t x = i < m ? sums[i] : 0;
+    int64_t total;
+    const int64_t ex = block_excl_scan(x, sm, &total);
+    if (i < m) sums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) total_out[blockIdx.x] = carry;
+}
+
 template <typename TIn, typename T>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply(const TIn* in, int64_t n,
                                                            const T* __restrict__ sums, T* out) {

@@ -141,7 +141,7 @@ class Engine:
     def insert(self, *, px, py, h_eff, sm_range, v, kernel_id=None, sigma=None, mHI=None, D=None,
                accept=None, table: KernelTable, spectrum: int, edges: torch.Tensor,
                cube: torch.Tensor, px_size_arcsec: float, x_lo: int = 0, x_hi: int | None = None,
-               nx_full: int | None = None, zeroed: bool = False):
+               nx_full: int | None = None, zeroed: bool = False, edges_increasing: bool | None = None):
         """Project particles into ``cube`` (a (x_hi-x_lo, ny, C) float64 device tensor holding
         rows [x_lo, x_hi) of the full cube), in place:  cube = (cube + inserted) / px_size^2.
 
@@ -173,20 +173,22 @@ class Engine:
         c.flags = L.CUBE_ZEROED if zeroed else L.CUBE_ACCUMULATE
         c.px_size_arcsec = float(px_size_arcsec)
         c.edges, c.slab = _ptr(edges), _ptr(cube)
+        # the caller usually knows the direction of its (host-made) edges: saves a read-back + sync
+        c.edges_direction = 0 if edges_increasing is None else (1 if edges_increasing else -1)
         tc = table.to_c()
         stream = self._stream()
 
         sbytes = self.lib.mtn_plan_scratch_bytes(n, C.byref(c))
         scratch = self._grow("_scratch", sbytes)
         plan = L.MtnPlan()
-        self._check(self.lib.mtn_plan(C.byref(p), C.byref(c), _ptr(scratch), scratch.numel(),
+        self._check(self.lib.mtn_plan(C.byref(p), C.byref(tc), C.byref(c), _ptr(scratch), scratch.numel(),
                                   C.byref(plan), stream), "mtn_plan")
         ws = self._grow("_workspace", plan.workspace_bytes)
         self._check(self.lib.mtn_project(C.byref(p), C.byref(tc), C.byref(c), C.byref(plan),
                                      _ptr(scratch), scratch.numel(), _ptr(ws), ws.numel(), stream),
                 "mtn_project")
         self.last_plan = plan
-        self.last_launches = self.lib.mtn_last_launch_count() + 5  # + mtn_plan's five kernels
+        self.last_launches = self.lib.mtn_last_launch_count() + 4  # + mtn_plan's four kernels
         del keep
         return plan
 

@@ -123,13 +123,15 @@ class _BaseMartini:
             cube = torch.zeros((nx, ny, dc.n_channels), dtype=torch.float64, device=eng.device)
         else:
             cube = dc._device_array(eng)
-        edges = eng.to_device(dc.velocity_channel_edges)
+        edges_host = np.asarray(dc.velocity_channel_edges)
+        edges = eng.to_device(edges_host)
         gauss = self._spectrum == L.SPECTRUM_GAUSSIAN
         plan = eng.insert(px=d["px"], py=d["py"], h_eff=d["h_eff"], sm_range=d["sm_range"], v=d["v"],
                           kernel_id=d["kernel_id"], sigma=d["sigma"] if gauss else 1.0,
                           mHI=d["mHI"], D=d["D"], accept=d["accept"], table=self._table,
                           spectrum=self._spectrum, edges=edges, cube=cube,
-                          px_size_arcsec=dc.px_size, zeroed=zero)
+                          px_size_arcsec=dc.px_size, zeroed=zero,
+                          edges_increasing=bool(edges_host[1] > edges_host[0]))
         dc._set_device_array(cube)  # stays on the GPU until someone reads datacube._array
         dc.array_unit = "Jy/arcsec2"
         self.last_plan = plan

@@ -36,6 +36,7 @@ class CaseContext:
     max_abs_dv: float
     shape: tuple
     px_size: float
+    edges_increasing: bool = False
 
 
 def prepare(case) -> CaseContext:
@@ -46,6 +47,7 @@ def prepare(case) -> CaseContext:
         max_abs_dv=float(np.max(np.abs(np.diff(case["edges"])))),
         shape=tuple(int(s) for s in case["shape"]),
         px_size=float(case["px_size"]),
+        edges_increasing=bool(case["edges"][1] > case["edges"][0]),
     )
 
 
@@ -105,6 +107,7 @@ def run_hot_path(engine, case, dev=None, cube=None, x_lo=0, x_hi=None, prune=(Tr
         sigma=dev["sigma"] if gauss else 1.0, mHI=dev["mHI"], D=dev["D"], accept=accept,
         table=ctx.table, spectrum=ctx.spectrum, edges=dev["edges"], cube=cube,
         px_size_arcsec=ctx.px_size, x_lo=x_lo, x_hi=x_hi, nx_full=nx, zeroed=bool(zeroed),
+        edges_increasing=ctx.edges_increasing,
     )
     return {"cube": cube, "accept": accept, "n_accept": n_accept, "plan": plan, "kernel_id": kid,
             "valid": valid, "sm_range": sm_range, "h_eff": h_eff,
@@ -146,7 +149,8 @@ def run_hot_path_to_host(engine, case, host_rows, dev, ctx: CaseContext, slab, x
             px=dev["px"], py=dev["py"], h_eff=h_eff, sm_range=sm_range, v=dev["v"], kernel_id=kid,
             sigma=dev["sigma"] if gauss else 1.0, mHI=dev["mHI"], D=dev["D"], accept=accept,
             table=ctx.table, spectrum=ctx.spectrum, edges=dev["edges"], cube=part,
-            px_size_arcsec=ctx.px_size, x_lo=x_lo + a, x_hi=x_lo + b, nx_full=nx, zeroed=True))
+            px_size_arcsec=ctx.px_size, x_lo=x_lo + a, x_hi=x_lo + b, nx_full=nx, zeroed=True,
+            edges_increasing=ctx.edges_increasing))
         launches += engine.last_launches
         done = torch.cuda.Event()
         done.record(main)

@@ -34,17 +34,35 @@ def test_header_and_binding_agree(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.mtn_version() == 100
+    assert lib.mtn_version() == 200
     assert isinstance(lib.mtn_last_error(), bytes)
 
 
-def test_struct_layouts_match_header():
-    # sizes the C compiler gives the same declarations (x86-64 SysV)
-    assert ctypes.sizeof(L.MtnKernelEntry) == 48
-    assert ctypes.sizeof(L.MtnKernelTable) == 8 + 8 * 48
-    assert ctypes.sizeof(L.MtnParticles) == 14 * 8
-    assert ctypes.sizeof(L.MtnCube) == 7 * 4 + 4 + 8 + 8 + 8
-    assert ctypes.sizeof(L.MtnPlan) == 5 * 8 + 8 + 8
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every struct as gcc lays out include/martini_b200.h against the
+    ctypes mirrors in martini_b200/_lib.py."""
+    import shutil
+    import subprocess
+
+    structs = {"MtnKernelEntry": L.MtnKernelEntry, "MtnKernelTable": L.MtnKernelTable,
+               "MtnParticles": L.MtnParticles, "MtnCube": L.MtnCube, "MtnPlan": L.MtnPlan}
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "martini_b200.h"', "int main(void) {"]
+    for name, cls in structs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(out[name]) == ctypes.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(out[f"{name}.{field}"]) == getattr(cls, field).offset, (name, field)
 
 
 def test_invalid_arguments_are_reported_not_crashed(lib):

@@ -53,7 +53,7 @@ def eng():
 def test_device_is_blackwell(eng):
     info = eng.device_info()
     assert info["cc"][0] == 10, info  # sm_100a code only runs on compute capability 10.x
-    assert eng.lib.mtn_version() == 100
+    assert eng.lib.mtn_version() == 200
 
 
 def test_erf_saturation(eng):
