@@ -372,7 +372,12 @@ def roofline_block(eng, name, plan, ex, stage, slab_voxels, n_gpus):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     p64 = eng.fp64_peak_tflops()
-    t_proj = float(np.mean(stage["project"])) * 1e-3
+    # the kernels that compute the sum: the brick kernel and, if the insertion has one, the
+    # column / splat kernel of its second stream (executed-work counts cover both)
+    t_brick, t_stream2 = float(np.mean(stage["project"])) * 1e-3, float(np.mean(stage.get("stream2", [0.0]))) * 1e-3
+    t_proj = t_brick + t_stream2
+    route2 = {0: None, 1: "column_kernel", 2: "splat_kernel"}[int(getattr(plan, "route2", 0))]
+    dominant = "project_kernel" if t_brick >= t_stream2 else route2
     flops_fma = 2.0 * ex["updates"]
     # F_alg = 2 U_exec + K_w P_exec + K_s N (C_live + 1) with the flop counts of the
     # evaluations as implemented here: one kernel integral = a degree-9 Horner (18) + R^2 and
@@ -380,10 +385,11 @@ def roofline_block(eng, name, plan, ex, stage, slab_voxels, n_gpus):
     # evaluations); one edge erf = a degree-9 Horner (18) + argument (3) = 21 flops
     kw, ks = 24.0, 21.0
     flops_full = flops_fma + kw * ex["weights"] + ks * ex["erfs"]
-    bytes_alg = 88.0 * plan.n_pairs + 8.0 * slab_voxels
+    bytes_alg = 88.0 * (plan.n_pairs + plan.n_pairs2) + 8.0 * slab_voxels
     traffic, src = profiled_traffic(name) if n_gpus == 1 else (None, "N > 1: not profiled per rank")
     return {
-        "kernel": "project_kernel", "bound": "fp64",
+        "kernel": dominant, "kernels_ms": {"project_kernel": t_brick * 1e3, **({route2: t_stream2 * 1e3} if route2 else {})},
+        "bound": "fp64",
         "achieved": flops_fma / t_proj / 1e12, "peak": p64, "unit": "TFLOP/s",
         "frac": flops_fma / t_proj / 1e12 / p64,
         "achieved_full": flops_full / t_proj / 1e12, "frac_full": flops_full / t_proj / 1e12 / p64,
@@ -393,7 +399,8 @@ def roofline_block(eng, name, plan, ex, stage, slab_voxels, n_gpus):
         "peak_source": "FP64 FMA microbenchmark run on this GPU in this process (mtn_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 entry",
         "algorithmic": {"fma_updates": ex["updates"], "kernel_integrals": ex["weights"],
-                        "edge_erfs": ex["erfs"], "pairs": int(plan.n_pairs), "kept": int(plan.n_kept),
+                        "edge_erfs": ex["erfs"], "pairs": int(plan.n_pairs), "pairs2": int(plan.n_pairs2),
+                        "kept": int(plan.n_kept),
                         "note": "rank 0 slab, one launch"},
         "kernel_ms": t_proj * 1e3,
         "hbm": {"achieved": bytes_alg / t_proj / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -607,8 +614,9 @@ def measure_strong(eng, name, args, timer, world, rank, local, case=None, dev=No
         del slab_e2e
     clocks = sampler.stop() if sampler else None
     plan = out["plan"]
-    stats = torch.tensor([float(plan.updates_dense), float(plan.n_pairs), float(plan.n_kept),
-                          float(np.mean(stage["project"]))], dtype=torch.float64, device=dev_t)
+    stats = torch.tensor([float(plan.updates_dense), float(plan.n_pairs + plan.n_pairs2), float(plan.n_kept),
+                          float(np.mean(stage["project"]) + np.mean(stage["stream2"]))], dtype=torch.float64,
+                         device=dev_t)
     per_rank = [torch.zeros_like(stats) for _ in range(world)]
     dist.all_gather(per_rank, stats)
     u_dense = float(sum(p[0] for p in per_rank))

@@ -207,8 +207,9 @@ int mtn_last_launch_count(void);
 
 /*
  * Measurement hooks (bench.py).  With timing enabled, mtn_project records CUDA events on
- * the caller's stream at its stage boundaries; mtn_last_timing then returns the six stage
- * durations in ms: [emit, sort, items, project kernel, partial reduce, finalize].
+ * the caller's stream at its stage boundaries; mtn_last_timing then returns the seven stage
+ * durations in ms: [emit, sort, items, project kernel, partial reduce, finalize, second stream
+ * (column / splat kernel + its reduce)].
  * With exec counting enabled, mtn_project launches a diagnostic instantiation of the
  * projection kernel that also tallies the algorithmic work actually executed
  * (mtn_last_exec_counts: [particle-channel updates with non-zero weight and spectrum,

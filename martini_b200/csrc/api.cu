@@ -18,7 +18,7 @@ thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 
 // optional per-stage timing of mtn_project (CUDA events on the caller's stream)
-constexpr int N_STAGES = 6;  // emit, sort, items, project, reduce, finalize
+constexpr int N_STAGES = 7;  // emit, sort, items, project, reduce, finalize, stream2
 thread_local int g_timing = 0;
 thread_local int g_count_exec = 0;
 thread_local cudaEvent_t g_ev[N_STAGES + 1];
@@ -671,6 +671,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
                px_area);
     MTN_LAUNCH_CHECK();
   }
+  mark(6, st);
   if (stream2) {  // the column / splat kernel adds onto what the brick kernel has written
     StreamArgs a;
     a.geo = g;
@@ -708,7 +709,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
     MTN_CUDA(cudaStreamSynchronize(st));
     for (int k = 0; k < 3; ++k) g_exec_counts[k] = c[0][k] + c[1][k];
   }
-  mark(6, st);
+  mark(7, st);
   g_ev_valid = g_timing != 0;
   return MTN_OK;
 }
@@ -730,7 +731,7 @@ int mtn_last_exec_counts(int64_t* out3) {
 }
 
 int mtn_last_timing(float* ms_out, int n) {
-  if (!ms_out || n < N_STAGES) return fail(MTN_ERR_INVALID, "timing: need room for 6 stages%s", "");
+  if (!ms_out || n < N_STAGES) return fail(MTN_ERR_INVALID, "timing: need room for 7 stages%s", "");
   if (!g_ev_valid) return fail(MTN_ERR_INVALID, "timing: enable with mtn_set_timing first%s", "");
   MTN_CUDA(cudaEventSynchronize(g_ev[N_STAGES]));
   for (int k = 0; k < N_STAGES; ++k) MTN_CUDA(cudaEventElapsedTime(ms_out + k, g_ev[k], g_ev[k + 1]));

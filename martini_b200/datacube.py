@@ -40,9 +40,8 @@ class DataCube:
         self.dec = float(_value(dec, "deg"))
         self.padx = self.pady = 0
         self._dev = None  # device copy (torch, 3-D); authoritative while _host is None
-        self._host = np.zeros((self.n_px_x, self.n_px_y, self.n_channels))
-        if stokes_axis:
-            self._host = self._host[..., np.newaxis]
+        self._host = None  # host array; a cube that is known to be all zeros has neither copy
+        self._known_zero = True
         #: "Jy/pix2" until insert_source_in_cube converts to "Jy/arcsec2" (martini.py:364-366)
         self.array_unit = "Jy/pix2"
 
@@ -51,34 +50,52 @@ class DataCube:
     # host array of the reference (`DataCube._array`) is materialised on first access.  A
     # host access also drops the device copy, because the caller may modify the array in
     # place (the reference's own tests do).
+    def _shape(self):
+        return (self.n_px_x + 2 * self.padx, self.n_px_y + 2 * self.pady, self.n_channels) + (
+            (1,) if self.stokes_axis else ())
+
     @property
     def _array(self):
         if self._host is None:
-            a = self._dev.cpu().numpy()
-            self._host = a[..., np.newaxis] if self.stokes_axis else a
+            if self._dev is None:
+                self._host = np.zeros(self._shape())
+            else:
+                a = self._dev.cpu().numpy()
+                self._host = a[..., np.newaxis] if self.stokes_axis else a
         self._dev = None
+        self._known_zero = False  # the caller holds a writable reference from here on
         return self._host
 
     @_array.setter
     def _array(self, value):
         self._host = value
         self._dev = None
+        self._known_zero = False
 
     def _device_array(self, engine):
         """The cube as a 3-D device tensor (uploaded from the host copy if needed)."""
         if self._dev is None:
-            h = self._host
-            self._dev = engine.to_device(np.ascontiguousarray(h.reshape(h.shape[:3])))
+            if self._host is None:
+                import torch
+
+                self._dev = torch.zeros(self._shape()[:3], dtype=torch.float64, device=engine.device)
+            else:
+                h = self._host
+                self._dev = engine.to_device(np.ascontiguousarray(h.reshape(h.shape[:3])))
         return self._dev
 
     def _set_device_array(self, tensor):
         """Make ``tensor`` (3-D, on the device) the cube's contents; the host copy is stale."""
         self._dev = tensor
         self._host = None
+        self._known_zero = False
 
     @property
     def _array_is_zero(self):
-        """True if the cube holds only zeros (checked where the data lives)."""
+        """True if the cube holds only zeros (checked where the data lives; a cube nobody has
+        touched since construction / reset is known to be zero without looking)."""
+        if self._known_zero:
+            return True
         if self._host is None:
             return not bool(self._dev.any())
         return not self._host.any()
@@ -102,6 +119,10 @@ class DataCube:
         if self.padx > 0 or self.pady > 0:
             raise RuntimeError("Tried to add padding to already padded datacube array.")
         px, py = int(pad[0]), int(pad[1])
+        if self._known_zero:  # nothing to copy: the padded cube is all zeros too
+            self._host = self._dev = None
+            self.padx, self.pady = px, py
+            return
         shape = (self.n_px_x + 2 * px, self.n_px_y + 2 * py, self.n_channels)
         new = np.zeros(shape + ((1,) if self.stokes_axis else ()))
         new[px:px + self.n_px_x, py:py + self.n_px_y, ...] = self._array

@@ -199,7 +199,11 @@ def insert_sharded(engine, case, dev=None, ctx=None, bounds=None, gather=True, f
     if dev is None:
         dev = pipeline.upload(engine, case)
     slab = torch.zeros((x_hi - x_lo, ny, nc), dtype=torch.float64, device=engine.device)
-    out = pipeline.run_hot_path(engine, case, dev=dev, cube=slab, x_lo=x_lo, x_hi=x_hi, zeroed=True, ctx=ctx)
+    # slab_bounds keeps the cuts on brick boundaries, so a narrow cube can leave a rank without
+    # rows: it projects nothing but still takes part in the gather
+    out = None
+    if x_hi > x_lo:
+        out = pipeline.run_hot_path(engine, case, dev=dev, cube=slab, x_lo=x_lo, x_hi=x_hi, zeroed=True, ctx=ctx)
     cube = None
     if gather:
         if rank == 0 and full is None:

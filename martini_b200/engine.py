@@ -8,7 +8,9 @@ include/martini_b200.h).  Nothing here computes on the CPU: every method enqueue
 
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import functools
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -59,6 +61,19 @@ def _scalar_or_tensor(x, device):
     return torch.from_numpy(np.ascontiguousarray(a)).to(device), 0.0
 
 
+def _on_device(method):
+    """Run an Engine method with the engine's GPU as the current CUDA device: the C ABI
+    launches on the current device and keeps per-device state (tables, function attributes),
+    so two engines on different GPUs may share a host thread."""
+
+    @functools.wraps(method)
+    def wrapped(self, *args, **kwargs):
+        with self._device_ctx():
+            return method(self, *args, **kwargs)
+
+    return wrapped
+
+
 class Engine:
     """One CUDA device's projection engine (owns grow-only scratch tensors)."""
 
@@ -80,10 +95,15 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _device_ctx(self):
+        return torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()
+
     def to_device(self, x, dtype=torch.float64):
         if isinstance(x, torch.Tensor):
             return x.to(device=self.device, dtype=dtype).contiguous()
         a = np.ascontiguousarray(np.asarray(x))
+        if not a.flags.writeable:  # (broadcast views: torch refuses to alias read-only memory)
+            a = a.copy()
         t = torch.from_numpy(a)
         if a.dtype != np.dtype("uint8") or dtype != torch.uint8:
             t = t.to(dtype)
@@ -98,12 +118,14 @@ class Engine:
             setattr(self, name, buf)
         return buf
 
+    @_on_device
     def device_info(self):
         sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
         self._check(self.lib.mtn_device_info(C.byref(sm), C.byref(ma), C.byref(mi)), "mtn_device_info")
         return {"sm_count": sm.value, "cc": (ma.value, mi.value)}
 
     # ------------------------------------------------------------------ K0 / K1
+    @_on_device
     def smoothing_setup(self, sm_length: torch.Tensor, table: KernelTable):
         """-> (kernel_id u8, valid u8, sm_range f64, h_eff f64); see mtn_smoothing_setup."""
         n = sm_length.numel()
@@ -119,6 +141,7 @@ class Engine:
         )
         return kid, valid, rng, heff
 
+    @_on_device
     def prune(self, px, py, pz, sm_range, mHI, half_width, max_abs_dv, nx_tot, ny_tot, n_channels,
               spatial=True, spectral=True, mass=True):
         """-> (accept u8 tensor, n_accept 0-d int64 tensor); see mtn_prune."""
@@ -138,6 +161,7 @@ class Engine:
         return accept, count
 
     # ------------------------------------------------------------------ plan + project
+    @_on_device
     def insert(self, *, px, py, h_eff, sm_range, v, kernel_id=None, sigma=None, mHI=None, D=None,
                accept=None, table: KernelTable, spectrum: int, edges: torch.Tensor,
                cube: torch.Tensor, px_size_arcsec: float, x_lo: int = 0, x_hi: int | None = None,
@@ -193,6 +217,7 @@ class Engine:
         return plan
 
     # ------------------------------------------------------------------ beam convolution
+    @_on_device
     def convolve_beam(self, cube: torch.Tensor, kernel: torch.Tensor, scale: float = 1.0):
         """out[x,y,c] = scale * (cube[:, :, c] (*) kernel)[x, y], 'same' size; see mtn_convolve_beam."""
         assert cube.ndim == 3 and cube.dtype == torch.float64 and cube.is_contiguous()
@@ -204,15 +229,16 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ diagnostics
-    STAGES = ("emit", "sort", "items", "project", "reduce", "finalize")
+    STAGES = ("emit", "sort", "items", "project", "reduce", "finalize", "stream2")
 
     def set_timing(self, enable: bool):
         self._check(self.lib.mtn_set_timing(int(enable)), "mtn_set_timing")
 
+    @_on_device
     def last_timing_ms(self):
         """Stage durations [ms] of the last insert() (needs set_timing(True)); synchronises."""
-        arr = (C.c_float * 6)()
-        self._check(self.lib.mtn_last_timing(arr, 6), "mtn_last_timing")
+        arr = (C.c_float * 7)()
+        self._check(self.lib.mtn_last_timing(arr, 7), "mtn_last_timing")
         return dict(zip(self.STAGES, (float(x) for x in arr)))
 
     def set_count_exec(self, enable: bool):
@@ -223,11 +249,13 @@ class Engine:
         self._check(self.lib.mtn_last_exec_counts(arr), "mtn_last_exec_counts")
         return {"updates": int(arr[0]), "weights": int(arr[1]), "erfs": int(arr[2])}
 
+    @_on_device
     def fp64_peak_tflops(self):
         t, ms = C.c_double(), C.c_double()
         self._check(self.lib.mtn_fp64_peak(C.byref(t), C.byref(ms), self._stream()), "mtn_fp64_peak")
         return t.value
 
+    @_on_device
     def probe_kernel_integral(self, entry: dict, dx, dy, h, closed_form=False):
         e = KernelTable([entry]).to_c().k[0]
         dx, dy, h = (self.to_device(a) for a in (dx, dy, h))
@@ -237,11 +265,13 @@ class Engine:
                 "mtn_probe_kernel_integral")
         return out
 
+    @_on_device
     def table_error(self, kind: int) -> float:
         err = C.c_double()
         self._check(self.lib.mtn_table_error(int(kind), C.byref(err)), "mtn_table_error")
         return err.value
 
+    @_on_device
     def probe_spectra(self, spectrum, v, sigma, amp, edges):
         v, amp, edges = (self.to_device(a) for a in (v, amp, edges))
         st, ss = _scalar_or_tensor(sigma, self.device)

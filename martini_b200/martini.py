@@ -60,46 +60,52 @@ class _BaseMartini:
 
     # ------------------------------------------------------------------ device state
     def _init_device_particles(self):
-        """Upload the seam arrays and run K0 (sph_kernels.py:235-262, 1241-1274)."""
+        """Upload the seam arrays and run K0 (sph_kernels.py:235-262, 1241-1274).  Everything the
+        projection needs stays on the device from here on."""
         eng, src = self.engine, self.source
-        n = src.npart
+        scalar_or_dev = lambda x: eng.to_device(x) if np.ndim(x) > 0 else float(x)  # noqa: E731
         self._dev = {
             "px": eng.to_device(src.pixcoords[0]), "py": eng.to_device(src.pixcoords[1]),
             "pz": eng.to_device(src.pixcoords[2]),
             "sm_length": eng.to_device(src.sm_lengths_px(self._datacube)),
             "v": eng.to_device(src.radial_velocity),
-            "D": eng.to_device(np.broadcast_to(src.distance_p, (n,))),
+            "D": scalar_or_dev(src.distance_p), "mHI": scalar_or_dev(src.mHI_g),
+            "sigma": scalar_or_dev(self.spectral_model.half_width(src)),
         }
-        self._dev["mHI"] = (eng.to_device(src.mHI_g) if np.ndim(src.mHI_g) > 0 else float(src.mHI_g))
-        hw = self.spectral_model.half_width(src)
-        self._dev["sigma"] = eng.to_device(hw) if np.ndim(hw) > 0 else float(hw)
         kid, valid, sm_range, h_eff = eng.smoothing_setup(self._dev["sm_length"], self._table)
         self._dev.update(kernel_id=kid, valid=valid, sm_range=sm_range, h_eff=h_eff)
-        self.sph_kernel._set_device_state(
-            self._dev["sm_length"].cpu().numpy(), sm_range.cpu().numpy(),
-            kid.cpu().numpy(), valid.cpu().numpy())
+        # host copies of the kernel state are fetched when somebody reads them (sph_kernels.py)
+        self.sph_kernel._set_device_state(self._dev["sm_length"], sm_range, kid, valid)
+
+    def _mass_on_device(self, accept=None):
+        m = self._dev["mHI"]
+        n = self._dev["px"].numel()
+        if not isinstance(m, torch.Tensor):
+            return m * (n if accept is None else int(accept.sum()))
+        return float(m.sum() if accept is None else (m * accept).sum())
 
     def _prune_particles(self, spatial=True, spectral=True, mass=True, obj_type_str="data cube"):
-        """martini.py:168-241; the accept mask is computed on the GPU and applied to the host
-        objects exactly like the reference (:233-234)."""
+        """martini.py:168-241; the accept mask is computed on the GPU and stays there for the
+        projection.  The host objects are pruned exactly like the reference's (:233-234), but
+        lazily: ``source`` and ``sph_kernel`` apply the mask when their arrays are first read."""
         if not self.quiet:
             print(f"Source module contained {self.source.npart} particles with total HI mass of "
-                  f"{np.sum(np.broadcast_to(self.source.mHI_g, (self.source.npart,))):.2e} Msun.")
+                  f"{self._mass_on_device():.2e} Msun.")
         dc, d = self._datacube, self._dev
         edges = dc.velocity_channel_edges
         check_monotonic(edges)
         nx_tot, ny_tot = dc.n_px_x + 2 * dc.padx, dc.n_px_y + 2 * dc.pady
-        accept, _ = self.engine.prune(d["px"], d["py"], d["pz"], d["sm_range"], d["mHI"], d["sigma"],
-                                      float(np.max(np.abs(np.diff(edges)))), nx_tot, ny_tot,
-                                      dc.n_channels, spatial, spectral, mass)
+        accept, n_accept = self.engine.prune(d["px"], d["py"], d["pz"], d["sm_range"], d["mHI"], d["sigma"],
+                                             float(np.max(np.abs(np.diff(edges)))), nx_tot, ny_tot,
+                                             dc.n_channels, spatial, spectral, mass)
         self._dev["accept"] = accept
-        mask = accept.cpu().numpy().astype(bool)
-        self.source.apply_mask(mask)       # raises RuntimeError if nothing is left
-        self.sph_kernel._apply_mask(mask)
+        n_kept = int(n_accept)  # the one scalar that comes back; raises below if nothing is left
+        self.source._defer_mask(lambda: accept.cpu().numpy().astype(bool), n_kept)
+        self.sph_kernel._apply_mask(accept)
         if not self.quiet:
             print(f"Pruned particles that will not contribute to {obj_type_str}, "
-                  f"{self.source.npart} particles remaining with total HI mass of "
-                  f"{np.sum(np.broadcast_to(self.source.mHI_g, (self.source.npart,))):.2e} Msun.")
+                  f"{n_kept} particles remaining with total HI mass of "
+                  f"{self._mass_on_device(accept):.2e} Msun.")
 
     # ------------------------------------------------------------------ public methods
     def init_spectra(self):
@@ -139,23 +145,23 @@ class _BaseMartini:
             self._print_summary()
 
     def _print_summary(self):
-        """martini.py:367-406."""
+        """martini.py:367-406, evaluated where the cube lives (no device -> host copy)."""
         dc = self._datacube
-        a = dc._array
+        a = dc._device_array(self.engine)
+        full = a
         if dc.padx > 0 and dc.pady > 0:
-            a = a[dc.padx:-dc.padx, dc.pady:-dc.pady, ...]
-        flux = np.sum(a) * dc.px_size**2
-        dv = np.abs(np.diff(dc.velocity_channel_edges))
-        mass = 2.36e5 * self.source.distance**2 * np.sum(
-            (a * dc.px_size**2).sum((0, 1)).squeeze() * dv)
-        nz = dc._array[dc._array > 0]
+            a = a[dc.padx:-dc.padx, dc.pady:-dc.pady]
+        flux = float(a.sum()) * dc.px_size**2
+        dv = torch.as_tensor(np.abs(np.diff(dc.velocity_channel_edges)), device=a.device)
+        mass = 2.36e5 * self.source.distance**2 * float((a.sum(dim=(0, 1)) * dc.px_size**2 * dv).sum())
+        nz = full[full > 0]
         print("Source inserted.",
               f"  Flux density in cube: {flux:.2e} Jy",
               f"  Mass in cube (assuming distance {self.source.distance:.2f} Mpc and a spatially"
               f" resolved source): {mass:.2e} Msun",
               f"    [{mass / self.source.input_mass * 100:.0f}% of initial source mass]",
-              f"  Maximum pixel: {dc._array.max():.2e} Jy / arcsec2",
-              f"  Median non-zero pixel: {np.median(nz) if nz.size else 0.0:.2e} Jy / arcsec2",
+              f"  Maximum pixel: {float(full.max()):.2e} Jy / arcsec2",
+              f"  Median non-zero pixel: {float(nz.median()) if nz.numel() else 0.0:.2e} Jy / arcsec2",
               sep="\n")
 
     def reset(self):

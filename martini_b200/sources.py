@@ -61,8 +61,33 @@ def L_align(xyz, vxyz, m, frac=0.3, Laxis="x"):
     return np.roll(rotmat, shift, axis=0)  # rows = new basis vectors: x' = rotmat . x
 
 
+def _lazy(name):
+    """A per-particle attribute that a deferred prune mask (``_defer_mask``) is applied to on
+    first access."""
+    key = "_lz_" + name
+
+    def get(self):
+        if self.__dict__.get("_pending_mask") is not None:
+            self._flush_mask()
+        return self.__dict__.get(key)
+
+    def set(self, value):
+        if self.__dict__.get("_pending_mask") is not None:
+            self._flush_mask()
+        self.__dict__[key] = value
+
+    return property(get, set)
+
+
 class SPHSource:
-    """Generic particle source (sph_source.py:171-263)."""
+    """Generic particle source (sph_source.py:171-263).
+
+    Pruning (``apply_mask``, sph_source.py:364-393) can be deferred: ``Martini`` computes the
+    accept mask on the GPU and the projection uses it there, so the host copies of the
+    per-particle arrays are only compacted when somebody reads them (``_defer_mask``);
+    ``npart`` is known at once from the device-side count."""
+
+    _pending_mask = None
 
     def __init__(self, *, distance, vpeculiar=0.0, rotation=None, L_coords=None, ra=0.0, dec=0.0,
                  h=0.7, T_g=None, mHI_g, xyz_g, vxyz_g, hsm_g=None, coordinate_axis=None,
@@ -167,8 +192,46 @@ class SPHSource:
         return np.arctan(hsm / self.distance_p * 1.0e-3) * (1.0 / (datacube.px_size * (np.pi / 648000.0)))
 
     # ------------------------------------------------------------------ pruning
+    @property
+    def npart(self):
+        return self._pending_n if self.__dict__.get("_pending_mask") is not None else self._npart
+
+    @npart.setter
+    def npart(self, value):
+        self._npart = value
+
+    def _defer_mask(self, fetch_mask, n_kept):
+        """Like ``apply_mask(fetch_mask())``, but the host arrays are compacted on first access.
+        ``n_kept`` is the number of True entries (raises like apply_mask if it is 0)."""
+        if self.__dict__.get("_pending_mask") is not None:
+            self._flush_mask()
+        if int(n_kept) == 0:
+            raise RuntimeError("No non-zero mHI source particles in target region.")
+        self._pending_n = int(n_kept)
+        self._pending_mask = fetch_mask
+
+    def _flush_mask(self):
+        fetch, self._pending_mask = self._pending_mask, None
+        if fetch is not None:
+            self.apply_mask(fetch())
+
+    def pin_memory(self):
+        """Move the arrays the projection uploads into page-locked host memory, so that
+        ``Martini``'s host -> device copies run at full PCIe rate and asynchronously (optional:
+        pageable arrays work, the driver then stages them itself)."""
+        import torch
+
+        for key in ("pixcoords", "radial_velocity", "distance_p", "mHI_g", "T_g", "hsm_g", "_sm_lengths"):
+            a = getattr(self, key, None)
+            if isinstance(a, np.ndarray) and a.ndim > 0 and a.size:
+                t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+                setattr(self, key, t.numpy())  # (the view keeps the pinned tensor alive)
+        return self
+
     def apply_mask(self, mask):
         """sph_source.py:364-393."""
+        if self.__dict__.get("_pending_mask") is not None:
+            self._flush_mask()
         mask = np.asarray(mask, dtype=bool)
         if mask.size != self.npart:
             raise ValueError("Mask must have same length as particle arrays.")
@@ -230,6 +293,11 @@ class PixelSource(SPHSource):
         return cls(pixcoords=np.vstack((case["px"], case["py"], case["pz"])),
                    sm_lengths=case["sm_length"], radial_velocity=case["v"], distance_p=case["D"],
                    mHI_g=case["mHI"], T_g=case.get("T"))
+
+
+for _name in ("T_g", "mHI_g", "xyz_g", "vxyz_g", "skycoords", "radial_velocity", "distance_p", "pixcoords",
+              "hsm_g", "_sm_lengths"):
+    setattr(SPHSource, _name, _lazy(_name))
 
 
 def demo_source(N=500):

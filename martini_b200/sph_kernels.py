@@ -28,6 +28,35 @@ def find_fwhm(f):
     return 2 * fsolve(lambda q: f(q) - f(np.zeros(1)) / 2, 0.5)[0]
 
 
+def _to_host(x):
+    """Device tensor or array-like -> host numpy array."""
+    return x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
+
+
+class _LazyValid:
+    """What ``_validate`` returns: the per-particle validity array of the reference, fetched
+    from the device only if somebody looks at it."""
+
+    def __init__(self, kernel):
+        self._k = kernel
+
+    def __array__(self, dtype=None, copy=None):
+        a = np.asarray(self._k._valid, dtype=bool)
+        return a if dtype is None else a.astype(dtype)
+
+    def all(self):
+        return self._k._all_valid()
+
+    def __getattr__(self, name):
+        return getattr(np.asarray(self), name)
+
+    def __getitem__(self, i):
+        return np.asarray(self)[i]
+
+    def __len__(self):
+        return len(np.asarray(self))
+
+
 class _BaseSPHKernel:
     """Attributes shared by all kernels (sph_kernels.py:51-337)."""
 
@@ -38,8 +67,6 @@ class _BaseSPHKernel:
     def __init__(self):
         self._rescale = 1.0
         self.size_in_fwhm = None
-        self.sm_lengths = None  # pixels, set by Martini.__init__
-        self.sm_ranges = None
         self._engine = None  # set by Martini; used by _px_weight
 
     # -- 3-D kernel value -------------------------------------------------------------
@@ -75,25 +102,72 @@ class _BaseSPHKernel:
         return KernelTable([self._entry()], adaptive=False)
 
     # -- per-particle state --------------------------------------------------------------
+    # Martini keeps the per-particle kernel state (smoothing lengths and ranges in pixels,
+    # kernel choice, validity -- the outputs of mtn_smoothing_setup) and the prune mask on the
+    # device; the host copies the reference exposes as attributes (sm_lengths, sm_ranges,
+    # kernel_indices ...) are made, and compacted by the mask, on first access.
+    _state = None     # dict of device tensors / host arrays: sm_lengths, sm_ranges, kernel_ids, valid
+    _mask = None      # pending prune mask (device tensor or host array), applied on access
+    _host = None      # materialised host arrays
+
     def _set_device_state(self, sm_lengths, sm_ranges, kernel_ids, valid):
-        """Called by Martini after mtn_smoothing_setup; arrays are host numpy copies."""
-        self.sm_lengths = sm_lengths
-        self.sm_ranges = sm_ranges
-        self._valid = valid
+        """Called by Martini after mtn_smoothing_setup (device tensors or host arrays)."""
+        self._state = {"sm_lengths": sm_lengths, "sm_ranges": sm_ranges, "kernel_ids": kernel_ids, "valid": valid}
+        self._mask = None
+        self._host = None
 
     def _apply_mask(self, mask):
-        self.sm_lengths = self.sm_lengths[mask]
-        self.sm_ranges = self.sm_ranges[mask]
-        self._valid = self._valid[mask]
+        if self._host is not None:
+            m = _to_host(mask).astype(bool)
+            self._host = {k: v[m] for k, v in self._host.items()}
+        elif self._mask is None:
+            self._mask = mask
+        else:  # a second mask refers to the already compacted arrays
+            self._materialise()
+            self._apply_mask(mask)
+
+    def _materialise(self):
+        if self._host is None and self._state is not None:
+            h = {k: _to_host(v) for k, v in self._state.items()}
+            if self._mask is not None:
+                m = _to_host(self._mask).astype(bool)
+                h = {k: v[m] for k, v in h.items()}
+            self._host, self._mask = self._derive(h), None
+        return self._host
+
+    def _derive(self, h):
+        return h
+
+    def _get(self, key, default=None):
+        h = self._materialise()
+        return default if h is None else h.get(key, default)
+
+    sm_lengths = property(lambda self: self._get("sm_lengths"), lambda self, v: self._set("sm_lengths", v))
+    sm_ranges = property(lambda self: self._get("sm_ranges"), lambda self, v: self._set("sm_ranges", v))
+    _valid = property(lambda self: self._get("valid"))
+
+    def _set(self, key, value):
+        if self._materialise() is None:
+            self._host = {}
+        self._host[key] = value
+
+    def _all_valid(self):
+        """Whether every kept particle passes the kernel's accuracy check -- on the device if
+        the state still lives there (one scalar comes back)."""
+        if self._host is None and self._state is not None and hasattr(self._state["valid"], "device"):
+            ok = self._state["valid"].bool()
+            if self._mask is not None and hasattr(self._mask, "device"):
+                ok = ok | ~self._mask.bool()
+                return bool(ok.all())
+        return bool(np.asarray(self._valid, dtype=bool).all())
 
     def _validate(self, sm_lengths=None, noraise=False, quiet=False):
-        valid = np.asarray(self._valid, dtype=bool)
-        if not valid.all() and not noraise:
+        if not self._all_valid() and not noraise:
             raise RuntimeError(self._validation_message())
-        return valid
+        return _LazyValid(self)
 
     def _confirm_validation(self, noraise=False, quiet=False):
-        return self._validate(self.sm_lengths, noraise=noraise, quiet=quiet)
+        return self._validate(None, noraise=noraise, quiet=quiet)
 
     def _validation_message(self):
         name = type(self).__name__
@@ -242,7 +316,6 @@ class _AdaptiveKernel(_BaseSPHKernel):
     def __init__(self, kernels):
         self.kernels = tuple(kernels)
         super().__init__()
-        self.kernel_indices = None
 
     def kernel(self, q):
         return self.kernels[0].kernel(q)
@@ -253,20 +326,17 @@ class _AdaptiveKernel(_BaseSPHKernel):
     def _table(self) -> KernelTable:
         return KernelTable([k._entry() for k in self.kernels], adaptive=True)
 
-    def _set_device_state(self, sm_lengths, sm_ranges, kernel_ids, valid):
-        super()._set_device_state(sm_lengths, sm_ranges, kernel_ids, valid)
+    def _derive(self, h):
         # the reference keeps -1 for "no kernel validated" (:1254) and maps it to entry 0
-        self.kernel_indices = np.where(valid.astype(bool), kernel_ids.astype(int), -1)
-        sizes = np.array([k.size_in_fwhm for k in self.kernels])
-        rescales = np.array([k._rescale for k in self.kernels])
-        self.size_in_fwhm = sizes[kernel_ids]
-        self._rescale = rescales[kernel_ids]
+        kid = h["kernel_ids"].astype(int)
+        h["kernel_indices"] = np.where(h["valid"].astype(bool), kid, -1)
+        h["size_in_fwhm"] = np.array([k.size_in_fwhm for k in self.kernels])[kid]
+        h["rescale"] = np.array([k._rescale for k in self.kernels])[kid]
+        return h
 
-    def _apply_mask(self, mask):
-        self.size_in_fwhm = self.size_in_fwhm[mask]
-        self._rescale = self._rescale[mask]
-        self.kernel_indices = self.kernel_indices[mask]
-        super()._apply_mask(mask)
+    kernel_indices = property(lambda self: self._get("kernel_indices"), lambda self, v: self._set("kernel_indices", v))
+    size_in_fwhm = property(lambda self: self._get("size_in_fwhm"), lambda self, v: self._set("size_in_fwhm", v))
+    _rescale = property(lambda self: self._get("rescale", 1.0), lambda self, v: self._set("rescale", v))
 
     def _validation_message(self):
         return (

@@ -2,7 +2,7 @@
 # ncu --set full capture of one project_kernel launch of $1 (workload) -> gpurun_out/$2.ncu-rep
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-W=${1:-cfg2}; OUT=${2:-r2_kB_$W}
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:project_kernel -c 1 -s 4 \
+W=${1:-cfg2}; OUT=${2:-r2_$W}; KRN=${3:-project_kernel}
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KRN -c 1 -s 4 \
   -o gpurun_out/$OUT -f python bench.py --workload $W --others none --steps 2 --warmup 3 --no-cpu-baseline --no-class > gpurun_out/$OUT.log 2>&1
 tail -3 gpurun_out/$OUT.log

@@ -126,3 +126,46 @@ def test_host_cube_is_shared_between_ranks():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert ok
+
+
+def _sharded_worker(rank, world, port, nx, q):
+    """dist.insert_sharded end to end on two ranks: the kernels run under the SIMT emulator
+    (tests/emu, CPU tensors), the gather over gloo."""
+    import torch.distributed as dist
+
+    from martini_b200 import dist as mdist
+    from martini_b200 import synthetic
+    from martini_b200.pipeline import run_hot_path
+    from tests.emu import EmuEngine
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        eng = EmuEngine()
+        case = synthetic.make_case("cfg2", n=1500, nx=nx, ny=24, nc=32, seed=11)
+        bounds = mdist.slab_bounds(nx, world)
+        out, cube = mdist.insert_sharded(eng, case, bounds=bounds)
+        if rank == 0:
+            want = run_hot_path(eng, case)["cube"]
+            ok = bool((cube - want).abs().max() <= 1e-13 * want.abs().max())
+            q.put((ok, bounds))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nx", (40, 8))
+def test_insert_sharded_world2_gloo(nx):
+    """Two ranks, one cube: each projects its x-slab, rank 0 gathers.  nx = 8 leaves rank 0 or 1
+    without rows (cuts stay on brick boundaries): it must still take part in the gather."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, nx, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, bounds = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok
+    if nx == 8:
+        assert 0 in [b - a for a, b in zip(bounds[:-1], bounds[1:])]
