@@ -140,7 +140,7 @@ static int launch_stream(const StreamArgs& a, int route, bool count, unsigned gr
   if (route == ROUTE_COLUMN) {
     static bool attr_set[MAX_DEVICES][2] = {{false, false}};
     const int dev = current_device();
-    const int smem = (int)(STREAM_WARPS * CSB * sizeof(double));
+    const int smem = (int)((STREAM_WARPS * CSB + ERF_NINT * ERF_NCOEF) * sizeof(double));
     {
       std::lock_guard<std::mutex> lock(g_once_mutex);
       if (!attr_set[dev][count]) {
@@ -687,9 +687,9 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
     a.partials = ws.s[1].partials;
     a.px_area = px_area;
     a.exec_counts = (unsigned long long*)(ws.s[1].scalars + 8);
-    // resident CTAs per SM: column 48 registers + 32 KB of shared memory, splat 96 registers
+    // resident CTAs per SM: column 40 KB of shared memory, splat 96 registers
     const unsigned grid = (unsigned)std::min<int64_t>((ws.s[1].max_items + STREAM_WARPS - 1) / STREAM_WARPS,
-                                                      (int64_t)sm_count() * (g.route2 == ROUTE_COLUMN ? 6 : 5));
+                                                      (int64_t)sm_count() * 5);
     if (int rc = launch_stream(a, g.route2, g_count_exec != 0, grid, st)) return rc;
     MTN_LAUNCH_CHECK();
     if (g.route2 == ROUTE_COLUMN) {

@@ -67,13 +67,15 @@ __device__ __forceinline__ bool next_item(const StreamArgs& a, int lane, Item& i
 // ------------------------------------------------------------------------------- column
 template <bool COUNT>
 __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs a) {
-  MTN_DYN_SMEM(double, col_acc);  // [STREAM_WARPS][CSB]
+  MTN_DYN_SMEM(double, col_smem);  // [STREAM_WARPS][CSB] accumulators, then a copy of the erf table
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* acc = col_acc + warp * CSB;
+  double* acc = col_smem + warp * CSB;
+  double* erf_table = col_smem + STREAM_WARPS * CSB;
   const Geo& g = a.geo;
   const double sgn = g.edges_increasing ? 1.0 : -1.0;
   for (int c = lane; c < CSB; c += 32) acc[c] = 0.0;
-  __syncwarp();
+  for (int k = threadIdx.x; k < ERF_NINT * ERF_NCOEF; k += STREAM_THREADS) erf_table[k] = g_erf_table[k];
+  __syncthreads();
   unsigned long long n_upd = 0, n_w = 0, n_erf = 0;
   Item it;
   while (next_item(a, lane, it)) {
@@ -113,17 +115,23 @@ __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs
           const int c1 = e0 + lane, c2 = e0 + 32 + lane;
           // g orientation (sign folded in): S[c] = E[c+1] - E[c] >= 0; saturated edges at the
           // ends of the window come out as exactly -1 / +1
-          const double t1 = (__ldg(edge + min(c1, nchs)) - v) * sc;
-          const double E1 = erf_tab(t1);
-          double E2 = 0.0, E3 = 0.0;
-          if (COUNT) n_erf += (lane <= n_here) && fabs(t1) < ERF_SAT;
+          // (lanes beyond the window's edges skip the evaluation: their table reads would
+          // cost data-pipe wavefronts for nothing)
+          double E1 = 0.0, E2 = 0.0, E3 = 0.0;
+          if (lane <= n_here) {
+            const double t1 = (__ldg(edge + min(c1, nchs)) - v) * sc;
+            E1 = erf_tab_from(erf_table, t1);
+            if (COUNT) n_erf += fabs(t1) < ERF_SAT;
+          }
           if (n_here >= 32) {
-            const double t2 = (__ldg(edge + min(c2, nchs)) - v) * sc;
-            E2 = erf_tab(t2);
-            if (COUNT) n_erf += (lane + 32 <= n_here) && fabs(t2) < ERF_SAT;
+            if (lane + 32 <= n_here) {
+              const double t2 = (__ldg(edge + min(c2, nchs)) - v) * sc;
+              E2 = erf_tab_from(erf_table, t2);
+              if (COUNT) n_erf += fabs(t2) < ERF_SAT;
+            }
             if (n_here == 64) {
               const double t3 = (__ldg(edge + e0 + 64) - v) * sc;
-              E3 = erf_tab(t3);
+              E3 = erf_tab_from(erf_table, t3);
               if (COUNT) n_erf += lane == 0 && fabs(t3) < ERF_SAT;
             }
           }
@@ -195,15 +203,15 @@ __global__ void __launch_bounds__(256) column_reduce_kernel(
 // pixels share an edge.  ez = erf(zmax / sqrt 2), zmax^2 = t^2 - (d / h / sig)^2, vanishes
 // where the reference's truncation predicates zero the weight, continuously -- values agree
 // with the closed form (kernel_integrals.cuh: w_gaussian) to a few ulp of the kernel's peak.
-__device__ __forceinline__ void gaussian_pair(const Record& r, double truncate, double norm, double gx0,
-                                              double gy, double x0d, double y0d, int lane, double& wA,
-                                              double& wB) {
+__device__ __forceinline__ void gaussian_pair(const double* __restrict__ erf_table, const Record& r,
+                                              double truncate, double norm, double gx0, double gy,
+                                              double x0d, double y0d, int lane, double& wA, double& wB) {
   const double sig = 0.42466090014400953;  // 1 / (2 sqrt(2 ln 2))
   const double c = 1.0 / (r.h * 1.4142135623730951 * sig);
   // edge k of an axis sits at pixel-centre k - 1/2: E_k = erf((p - (o + k) + 1/2) c)
   const int k = lane & 15;
   const double o = lane < 16 ? x0d : y0d, p = lane < 16 ? r.px : r.py;
-  const double E = erf_tab((p - (o + (double)k) + 0.5) * c);
+  const double E = erf_tab_from(erf_table, (p - (o + (double)k) + 0.5) * c);
   const double F = E - __shfl_down_sync(0xffffffffu, E, 1);  // lanes 0-7: columns, 16-23: rows
   const double exA = __shfl_sync(0xffffffffu, F, lane >> 3);
   const double exB = __shfl_sync(0xffffffffu, F, (lane >> 3) + 4);
@@ -214,17 +222,18 @@ __device__ __forceinline__ void gaussian_pair(const Record& r, double truncate, 
   {
     const double dx = __dsub_rn(r.px, gx0);
     const double z2 = t2 - sq_dist(dx, dy) * k2;
-    wA = z2 > 0.0 ? erf_tab(sqrt(0.5 * z2)) * exA * ey * q : 0.0;
+    wA = z2 > 0.0 ? erf_tab_from(erf_table, sqrt(0.5 * z2)) * exA * ey * q : 0.0;
   }
   {
     const double dx = __dsub_rn(r.px, gx0 + 4.0);
     const double z2 = t2 - sq_dist(dx, dy) * k2;
-    wB = z2 > 0.0 ? erf_tab(sqrt(0.5 * z2)) * exB * ey * q : 0.0;
+    wB = z2 > 0.0 ? erf_tab_from(erf_table, sqrt(0.5 * z2)) * exB * ey * q : 0.0;
   }
 }
 
 struct SplatSmem {
   Record rec[STREAM_WARPS][PBATCH];
+  double erf_table[ERF_NINT * ERF_NCOEF];  // (shared-memory copy: see tables.cuh, erf_tab_from)
 };
 
 template <bool COUNT>
@@ -233,6 +242,8 @@ __global__ void __launch_bounds__(STREAM_THREADS) splat_kernel(const StreamArgs 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Record* rec = sm.rec[warp];
   const Geo& g = a.geo;
+  for (int k = threadIdx.x; k < ERF_NINT * ERF_NCOEF; k += STREAM_THREADS) sm.erf_table[k] = g_erf_table[k];
+  __syncthreads();
   unsigned long long n_upd = 0, n_w = 0;
   Item it;
   while (next_item(a, lane, it)) {
@@ -261,7 +272,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) splat_kernel(const StreamArgs 
         const bool inA = inY && gxA >= r.i0 && gxA <= r.i1, inB = inY && gxB >= r.i0 && gxB <= r.i1;
         double wA, wB;
         if (kind == MTN_KERNEL_GAUSSIAN) {
-          gaussian_pair(r, a.table.truncate[r.kid], a.table.norm[r.kid], gxd, gyd, (double)x0, (double)y0,
+          gaussian_pair(sm.erf_table, r, a.table.truncate[r.kid], a.table.norm[r.kid], gxd, gyd, (double)x0, (double)y0,
                         lane, wA, wB);
         } else {
           // dij = pixcoords - ij (martini.py:276)
