@@ -109,8 +109,10 @@ class PeerCube:
     bytes per warp) -- the access pattern NVLink peer stores like.  Use with MTN_CUBE_ZEROED
     only (accumulate mode would read the cube back over the link).
 
-    Per insertion: ``begin()`` (dst zeroes its buffer, then a barrier so no store can overtake
-    the memset), the ranks project, ``end()`` (barrier: all stores have landed)."""
+    Per insertion: ``begin()`` (every rank zeroes ITS OWN rows of the destination through the
+    peer mapping -- same stream as the projection that follows, so nothing can overtake it, and
+    no rank touches another rank's rows), the ranks project, ``end()`` (one barrier: all stores
+    have landed).  The previous insertion's ``end()`` is what makes the next ``begin()`` safe."""
 
     def __init__(self, shape, bounds, device, dst=0, group=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -124,10 +126,7 @@ class PeerCube:
         self.rows = self.hdl.get_buffer(dst, (hi - lo, ny, nc), torch.float64, storage_offset=lo * ny * nc)
 
     def begin(self):
-        if self.rank == self.dst:
-            self.buf.zero_()
-        torch.cuda.current_stream().synchronize()
-        dist.barrier(group=self.group)
+        self.rows.zero_()
 
     def end(self):
         torch.cuda.current_stream().synchronize()
@@ -210,3 +209,58 @@ def insert_sharded(engine, case, dev=None, ctx=None, bounds=None, gather=True, f
             full = torch.empty((nx, ny, nc), dtype=torch.float64, device=engine.device)
         cube = gather_slabs(slab, bounds, full, dst=0)
     return out, cube
+
+
+# --------------------------------------------------------------------------------------------
+# Particle routing: the one exchange step of the input side.
+#
+# Every rank starts with a contiguous 1 / world share of the particle list (uploaded from its
+# own host buffers over its own PCIe link).  A particle is needed by every rank whose slab its
+# candidate box [px - r, px + r] reaches, so each rank buckets its share by destination slab
+# (halo particles go to both neighbours) and the buckets are exchanged with one all-to-all over
+# NVLink.  Received buckets are concatenated in source-rank order and every bucket keeps its
+# particles in index order, so a rank sees its particles in ascending global index -- the
+# summation order of the single-GPU run.  The destination test is conservative (one pixel of
+# slack on both sides); the exact candidate-box predicate is applied afterwards by mtn_plan on
+# the receiving rank, exactly as in the single-GPU path.
+# --------------------------------------------------------------------------------------------
+ROUTED_KEYS = ("px", "py", "pz", "sm_length", "v", "mHI", "D", "sigma")
+
+
+def route_particles(dev, sm_range, bounds, group=None):
+    """``dev``: dict of this rank's per-particle device tensors (any subset of ROUTED_KEYS that
+    are tensors; scalars are passed through), ``sm_range`` their candidate-box half widths in
+    pixels (K0's output).  Returns the dict of the particles whose box may reach this rank's
+    slab ``[bounds[rank], bounds[rank + 1])``."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    keys = [k for k in ROUTED_KEYS if isinstance(dev.get(k), torch.Tensor)]
+    out = {k: v for k, v in dev.items() if k not in keys}
+    if world == 1:
+        out.update({k: dev[k] for k in keys})
+        return out
+    px = dev["px"]
+    device = px.device
+    b = torch.as_tensor(bounds, dtype=torch.float64, device=device)
+    r = torch.nan_to_num(sm_range, nan=0.0, posinf=float(bounds[-1]) + 2.0)
+    lo = torch.floor(px - r) - 1.0   # first / last cube row the box may reach (one pixel of slack)
+    hi = torch.ceil(px + r) + 1.0
+    ok = ~torch.isnan(px)
+    # rank d is a destination iff its slab [b[d], b[d+1]) intersects [lo, hi] and is not empty
+    x_lo, x_hi = b[:-1].unsqueeze(1), b[1:].unsqueeze(1)
+    want = (lo.unsqueeze(0) < x_hi) & (hi.unsqueeze(0) >= x_lo) & (x_hi > x_lo) & ok.unsqueeze(0)  # (world, n)
+    dest, idx = torch.nonzero(want, as_tuple=True)  # sorted by destination, then particle index
+    send_counts = torch.bincount(dest, minlength=world)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    payload = torch.stack([dev[k] for k in keys], dim=1).index_select(0, idx)  # (n_send, F), bucketed
+    recv = torch.empty((sum(rc), len(keys)), dtype=torch.float64, device=device)
+    dist.all_to_all_single(recv, payload, output_split_sizes=rc, input_split_sizes=sc, group=group)
+    cols = recv.t().contiguous()  # (F, n_recv): one contiguous array per quantity for the C ABI
+    out.update({k: cols[i] for i, k in enumerate(keys)})
+    return out
+
+
+def chunk_of(n, rank, world):
+    """The contiguous share [a, b) of an n-particle list that rank ``rank`` uploads."""
+    return (n * rank) // world, (n * (rank + 1)) // world

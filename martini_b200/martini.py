@@ -138,7 +138,7 @@ class _BaseMartini:
                           spectrum=self._spectrum, edges=edges, cube=cube,
                           px_size_arcsec=dc.px_size, zeroed=zero,
                           edges_increasing=bool(edges_host[1] > edges_host[0]))
-        dc._set_device_array(cube)  # stays on the GPU until someone reads datacube._array
+        dc._set_device_array(cube, eng)  # stays on the GPU until someone reads datacube._array
         dc.array_unit = "Jy/arcsec2"
         self.last_plan = plan
         if (quiet is None and not self.quiet) or (quiet is not None and not quiet):
@@ -168,9 +168,9 @@ class _BaseMartini:
         """martini.py:409-425."""
         dc = self._datacube
         new = DataCube(n_px_x=dc.n_px_x, n_px_y=dc.n_px_y, n_channels=dc.n_channels,
-                       px_size=dc.px_size, channel_width=dc.channel_width,
-                       spectral_centre=dc.spectral_centre, ra=dc.ra, dec=dc.dec,
-                       stokes_axis=dc.stokes_axis)
+                       px_size=dc.px_size, channel_width=dc.channel_width, channel_unit=dc.channel_unit,
+                       spectral_centre=dc.spectral_centre, spectral_centre_unit=dc.channel_unit,
+                       ra=dc.ra, dec=dc.dec, stokes_axis=dc.stokes_axis)
         if self.beam is not None:
             # the reference re-pads with the beam's own requirement (martini.py:423-424), not
             # with the current pad: convolve_beam() has dropped that one
@@ -256,10 +256,12 @@ class GlobalProfile(_BaseMartini):
     at pixel (0, 0), ``DiracDeltaKernel(size_in_fwhm=inf)``; pruning by velocity only."""
 
     def __init__(self, *, source, spectral_model, n_channels=64, channel_width=4.0,
-                 spectral_centre=0.0, quiet=False, device="cuda:0", engine=None):
+                 spectral_centre=0.0, quiet=False, device="cuda:0", engine=None, channel_unit=None,
+                 spectral_centre_unit=None):
         self._source_in = source
         dc = DataCube(n_px_x=1, n_px_y=1, n_channels=n_channels, px_size=1.0,
-                      channel_width=channel_width, spectral_centre=spectral_centre,
+                      channel_width=channel_width, spectral_centre=spectral_centre, channel_unit=channel_unit,
+                      spectral_centre_unit=spectral_centre_unit,
                       ra=source.ra if hasattr(source, "ra") else 0.0,
                       dec=source.dec if hasattr(source, "dec") else 0.0)
         self._inserted = False

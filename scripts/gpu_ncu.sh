@@ -5,4 +5,5 @@ mkdir -p gpurun_out
 W=${1:-cfg2}; OUT=${2:-r2_$W}; KRN=${3:-project_kernel}
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KRN -c 1 -s 4 \
   -o gpurun_out/$OUT -f python bench.py --workload $W --others none --steps 2 --warmup 3 --no-cpu-baseline --no-class > gpurun_out/$OUT.log 2>&1
+python -c "import bench; print(bench.csrc_hash())" > gpurun_out/$OUT.hash
 tail -3 gpurun_out/$OUT.log

@@ -169,3 +169,65 @@ def test_insert_sharded_world2_gloo(nx):
     assert ok
     if nx == 8:
         assert 0 in [b - a for a, b in zip(bounds[:-1], bounds[1:])]
+
+
+def _route_worker(rank, world, port, q):
+    """dist.route_particles over gloo: every rank starts with a contiguous share of the
+    particles and ends with exactly those whose box can reach its slab, in global index order;
+    the slab cubes computed from the routed sets concatenate to the single-engine cube."""
+    import torch.distributed as dist
+
+    from martini_b200 import dist as mdist
+    from martini_b200 import pipeline, synthetic
+    from tests.emu import EmuEngine
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        eng = EmuEngine()
+        case = synthetic.make_case("cfg3", n=3000, nx=48, ny=24, nc=32, seed=5)
+        case["px"][7] = np.nan  # a NaN coordinate goes nowhere
+        n = case["px"].size
+        ctx = pipeline.prepare(case)
+        bounds = [0, 16, 48]
+        a, b = mdist.chunk_of(n, rank, world)
+        share = dict(case, **{k: case[k][a:b] for k in pipeline.particle_keys(case)})
+        dev = pipeline.upload(eng, share)
+        _, _, sm_range, _ = eng.smoothing_setup(dev["sm_length"], ctx.table)
+        routed = mdist.route_particles(dev, sm_range, bounds)
+        # expected set: conservative superset test evaluated on the whole list
+        _, _, r_all, _ = eng.smoothing_setup(eng.to_device(case["sm_length"]), ctx.table)
+        r_all, px = r_all.numpy(), case["px"]
+        must = (np.floor(px + r_all) >= bounds[rank]) & (np.ceil(px - r_all) <= bounds[rank + 1] - 1) & ~np.isnan(px)
+        got_px = routed["px"].numpy()
+        full_px = px[~np.isnan(px)]
+        pos = np.searchsorted(np.sort(full_px), got_px)  # every routed particle is a real one
+        ok = bool(np.all(np.isin(px[must], got_px))) and bool(np.all(np.isin(got_px, full_px)))
+        # ascending global index: positions of the routed particles in the original list increase
+        order = np.array([np.flatnonzero(px == x)[0] for x in got_px])
+        ok = ok and bool(np.all(np.diff(order) > 0)) and pos.size == got_px.size
+        x_lo, x_hi = bounds[rank], bounds[rank + 1]
+        slab = torch.zeros((x_hi - x_lo, 24, 32), dtype=torch.float64)
+        rcase = dict(case, **{k: routed[k].numpy() for k in pipeline.particle_keys(case)})
+        pipeline.run_hot_path(eng, rcase, dev=routed, cube=slab, x_lo=x_lo, x_hi=x_hi, zeroed=True, ctx=ctx)
+        full = torch.empty((48, 24, 32), dtype=torch.float64) if rank == 0 else None
+        cube = mdist.gather_slabs(slab, bounds, full, dst=0)
+        if rank == 0:
+            want = pipeline.run_hot_path(eng, case)["cube"]
+            ok = ok and bool((cube - want).abs().max() <= 1e-13 * want.abs().max())
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_route_particles_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_route_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert results == {0: True, 1: True}

@@ -82,6 +82,42 @@ def test_mass_accuracy(kernel, hsm, spectrum):
     assert np.isclose(mass_in_cube(m), 4e6, rtol=1e-2)
 
 
+@pytest.mark.parametrize("kernel,hsm", ((_WendlandC2Kernel, 2.0), (DiracDeltaKernel, 0.3), (GaussianKernel, 0.7)))
+@pytest.mark.parametrize("spectrum", (GaussianSpectrum, DiracDeltaSpectrum))
+def test_mass_accuracy_frequency_channels(kernel, hsm, spectrum):
+    """The reference's mass-accuracy matrix also runs frequency-mode cubes (test_martini.py:205-241
+    with dc_zeros in Hz, datacube.py:196-207): channels of equal frequency width, the spectral
+    centre given as a velocity.  Mass within 1 %, and the cube equals the velocity-mode cube of
+    the same channels (v = c (1 - f / f_HI) is linear, so the edges agree to rounding)."""
+    from martini_b200.datacube import C_KMS, HI_FREQ_HZ
+
+    def build(**channels):
+        source = SPHSource(distance=3.0, mHI_g=np.ones(4) * 1e6, T_g=np.ones(4) * 1e4,
+                           xyz_g=np.array([[0, 0.3, 0.2], [0, 1.3, 0.1], [0, 0.2, 1.4], [0, -1.3, -1.1]]),
+                           vxyz_g=np.array([[0, 0, 0], [5, 0, 0], [-5, 0, 0], [10.0, 0, 0]]),
+                           hsm_g=np.ones(4) * hsm)
+        dc = DataCube(n_px_x=32, n_px_y=32, n_channels=32, px_size=68.75493542, spectral_centre=source.vsys,
+                      **channels)
+        m = Martini(source=source, datacube=dc, sph_kernel=kernel(), spectral_model=spectrum(), quiet=True)
+        m.insert_source_in_cube()
+        return m
+
+    mf = build(channel_width=HI_FREQ_HZ * 4.0 / C_KMS, channel_unit="Hz")
+    dc = mf.datacube
+    assert dc._freq_channel_mode and dc.channel_unit == "Hz"
+    assert np.all(np.diff(dc.channel_edges) > 0) and np.all(np.diff(dc.velocity_channel_edges) < 0)
+    assert np.isclose(mass_in_cube(mf), 4e6, rtol=1e-2)
+    mv = build(channel_width=4.0)
+    assert np.allclose(dc.velocity_channel_edges, mv.datacube.velocity_channel_edges, rtol=0, atol=1e-9)
+    a, b = mf.datacube._array, mv.datacube._array
+    if spectrum is GaussianSpectrum:
+        assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max()
+    else:  # a Dirac line may flip channel when an edge moves by an ulp: compare the moment-0 maps
+        assert np.abs(a.sum(2) - b.sum(2)).max() <= 1e-9 * np.abs(b.sum(2)).max()
+    mf.reset()  # reset keeps the channel mode
+    assert mf.datacube._freq_channel_mode and np.allclose(mf.datacube.channel_edges, dc.channel_edges)
+
+
 def test_kernel_validation_raises_unless_skipped():
     """reference test_sph_kernels.py:209-278: 'use this with care'."""
     def build():
