@@ -80,6 +80,7 @@ def parse():
                     help="also run config 2 on the CPU in full, once (minutes) and record it under profiles/")
     ap.add_argument("--no-cfg5", action="store_true", help="N = 8: skip the config-5 target run")
     ap.add_argument("--cfg5-particles", type=int, default=100_000_000)
+    ap.add_argument("--force-cfg5", action="store_true", help="run the config-5 block at any N > 1 (testing)")
     ap.add_argument("--no-class", action="store_true", help="skip the Martini-class wall time")
     return ap.parse_args()
 
@@ -805,7 +806,7 @@ def run_b200(args):
     line["gpu_launches"] = blk["gpu_launches_per_step"] * args.steps
     del cube, dev, peer
     torch.cuda.empty_cache()
-    if world == 8 and not args.no_cfg5 and args.particles is None:
+    if (world == 8 or args.force_cfg5) and not args.no_cfg5 and args.particles is None:
         try:
             line["extra"] = {"cfg5": cfg5_block(eng, args, timer, world, rank, local)}
         except Exception as exc:  # noqa: BLE001 -- the headline line must survive

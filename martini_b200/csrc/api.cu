@@ -240,7 +240,7 @@ static PlanIn make_plan_in(const MtnParticles* p, const MtnCube* c) {
   return in;
 }
 
-// plan scratch: [blk_kept | blk_pairs | blk_pairs2 | totals(8 x u64) | tile_sum | tile_cnt | tile_phase]
+// plan scratch: [blk_kept | blk_pairs | blk_pairs2 | totals(8 x u64) | tile_sum | tile_cnt | tile_phase | feet]
 struct PlanScratch {
   int64_t nblk;
   int64_t* blk_kept;
@@ -250,6 +250,7 @@ struct PlanScratch {
   unsigned long long* tile_sum;
   unsigned int* tile_cnt;
   int* tile_phase;
+  PackedFoot* feet;
 };
 static int64_t num_tiles(const MtnCube* c) {
   if (!c || c->x_hi <= c->x_lo || c->ny <= 0) return 1;
@@ -270,6 +271,7 @@ static size_t plan_scratch_layout(int64_t n, int64_t n_tiles, void* base, PlanSc
   char* ts = take((size_t)n_tiles * sizeof(unsigned long long));
   char* tc = take((size_t)n_tiles * sizeof(unsigned int));
   char* tp = take((size_t)n_tiles * sizeof(int));
+  char* ft = take((size_t)std::max<int64_t>(n, 1) * sizeof(PackedFoot));
   if (s) {
     s->nblk = nblk;
     s->blk_kept = (int64_t*)a;
@@ -279,6 +281,7 @@ static size_t plan_scratch_layout(int64_t n, int64_t n_tiles, void* base, PlanSc
     s->tile_sum = (unsigned long long*)ts;
     s->tile_cnt = (unsigned int*)tc;
     s->tile_phase = (int*)tp;
+    s->feet = (PackedFoot*)ft;
   }
   return off;
 }
@@ -531,7 +534,7 @@ int mtn_plan(const MtnParticles* p, const MtnKernelTable* table, const MtnCube* 
   MTN_LAUNCH_CHECK();
   if (p->n > 0) {
     MTN_LAUNCH(plan_count_kernel, (unsigned)ps.nblk, PLAN_THREADS, 0, st, make_plan_in(p, cube), g,
-               ps.blk_kept, ps.blk_pairs, ps.blk_pairs2, ps.totals + 3);
+               ps.blk_kept, ps.blk_pairs, ps.blk_pairs2, ps.totals + 3, ps.feet);
     MTN_LAUNCH_CHECK();
     MTN_LAUNCH(scan3_sums_inplace, 3, 1024, 0, st, ps.blk_kept, ps.blk_pairs, ps.blk_pairs2, ps.nblk,
                (int64_t*)ps.totals);
@@ -625,7 +628,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
 
   if (plan->n_pairs + plan->n_pairs2 > 0) {
     MTN_LAUNCH(plan_emit_kernel, (unsigned)ps.nblk, PLAN_THREADS, 0, st, make_plan_in(p, cube), g,
-               ps.blk_kept, ps.blk_pairs, ps.blk_pairs2, ws.records, ws.s[0].pairs_a, ws.s[1].pairs_a);
+               ps.blk_kept, ps.blk_pairs, ps.blk_pairs2, ps.feet, ws.records, ws.s[0].pairs_a, ws.s[1].pairs_a);
     MTN_LAUNCH_CHECK();
   }
   mark(1, st);
@@ -770,9 +773,11 @@ int mtn_convolve_beam(const double* cube_in, double* cube_out, int32_t nx, int32
                       const double* kernel, int32_t ka, int32_t kb, double scale, void* stream) {
   if (!cube_in || !cube_out || !kernel || cube_in == cube_out)
     return fail(MTN_ERR_INVALID, "convolve_beam: bad pointers (in-place is not supported)%s", "");
-  if (nx <= 0 || ny <= 0 || nc <= 0 || ka <= 0 || kb <= 0 || !(ka & 1) || !(kb & 1) ||
-      (int64_t)ka * kb > CONV_MAX_TAPS)
-    return fail(MTN_ERR_INVALID, "convolve_beam: bad shape (beam image must be odd x odd, <= 96 x 96)%s", "");
+  if (nx <= 0 || ny <= 0 || nc <= 0 || ka <= 0 || kb <= 0 || !(ka & 1) || !(kb & 1))
+    return fail(MTN_ERR_INVALID, "convolve_beam: bad shape (the beam image must be odd x odd)%s", "");
+  if ((int64_t)ka * kb > CONV_MAX_TAPS)
+    return fail(MTN_ERR_LIMIT, "convolve_beam: beam image of %s%lld taps exceeds the 28000 (e.g. 167 x 167) that fit "
+                "in shared memory", "", (long long)ka * kb);
   const size_t smem = (size_t)ka * kb * sizeof(double);
   static bool attr_set[MAX_DEVICES] = {false};
   {
@@ -784,8 +789,8 @@ int mtn_convolve_beam(const double* cube_in, double* cube_out, int32_t nx, int32
       attr_set[dev] = true;
     }
   }
-  const dim3 grid((nc + 31) / 32, (ny + 4 * CONV_TY - 1) / (4 * CONV_TY), nx);
-  MTN_LAUNCH(convolve_beam_kernel, grid, 128, smem, (cudaStream_t)stream, cube_in, cube_out, nx, ny, nc,
+  const dim3 grid((nc + 31) / 32, (ny + CONV_WARPS * CONV_TY - 1) / (CONV_WARPS * CONV_TY), (nx + CONV_TX - 1) / CONV_TX);
+  MTN_LAUNCH(convolve_beam_kernel, grid, CONV_WARPS * 32, smem, (cudaStream_t)stream, cube_in, cube_out, nx, ny, nc,
              kernel, ka, kb, scale);
   MTN_LAUNCH_CHECK();
   return MTN_OK;

@@ -78,9 +78,16 @@ __global__ void __launch_bounds__(256) prune_kernel(
     keep = !reject;
     accept[i] = keep ? 1 : 0;
   }
-  if (n_accept) {
+  if (n_accept) {  // one atomic per block (one per warp cost 0.3 ms of serialised L2 atomics at 1e7 particles)
+    __shared__ unsigned int warp_cnt[8];
     const unsigned b = __ballot_sync(0xffffffffu, keep);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_accept, (unsigned long long)__popc(b));
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int c = 0;
+      for (int w = 0; w < 8; ++w) c += warp_cnt[w];
+      if (c) atomicAdd(n_accept, (unsigned long long)c);
+    }
   }
 }
 
@@ -95,6 +102,36 @@ struct Foot {
   int route;           // Route: which kernel computes this particle
   int nbx, nby;        // extent of the reference's candidate box in the slab (U_dense)
 };
+
+// What the count pass leaves for the emit pass (24 bytes per particle), so the footprint --
+// two exact pixel-bound searches and two binary searches over the channel edges -- is
+// evaluated once.
+struct __align__(8) PackedFoot {
+  int32_t i0, i1, j0, j1;
+  uint16_t c0, c1;
+  uint8_t live, route;
+  uint16_t pad;
+};
+__device__ __forceinline__ PackedFoot pack_foot(const Foot& f) {
+  PackedFoot p;
+  p.i0 = f.i0; p.i1 = f.i1; p.j0 = f.j0; p.j1 = f.j1;
+  p.c0 = (uint16_t)(f.live ? f.c0 : 0);
+  p.c1 = (uint16_t)(f.live ? f.c1 : 0);
+  p.live = f.live ? 1 : 0;
+  p.route = (uint8_t)f.route;
+  p.pad = 0;
+  return p;
+}
+__device__ __forceinline__ Foot unpack_foot(const PackedFoot& p) {
+  Foot f;
+  f.i0 = p.i0; f.i1 = p.i1; f.j0 = p.j0; f.j1 = p.j1;
+  f.c0 = p.c0; f.c1 = p.c1;
+  f.live = p.live != 0;
+  f.box = f.live;
+  f.route = p.route;
+  f.nbx = f.nby = 0;
+  return f;
+}
 
 // Smallest and largest integer i in [lim_lo, lim_hi] with |i - p| <= r, the candidate test
 // of martini.py:272-274 evaluated exactly as numpy does (fl(i - p), then compare).
@@ -291,12 +328,14 @@ __device__ __forceinline__ int64_t count_pairs(const Foot& f, const Geo& g) {
 // Pass 1: per-block totals of (kept particles, bricks overlapped) and the slab's U_dense.
 __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(
     PlanIn in, Geo g, int64_t* __restrict__ blk_kept, int64_t* __restrict__ blk_pairs,
-    int64_t* __restrict__ blk_pairs2, unsigned long long* __restrict__ updates) {
+    int64_t* __restrict__ blk_pairs2, unsigned long long* __restrict__ updates,
+    PackedFoot* __restrict__ feet) {
   __shared__ int64_t sm[33];
   const int64_t i = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
   int64_t kept = 0, pairs = 0, pairs2 = 0, upd = 0;
   if (i < in.n) {
     const Foot f = footprint(in, g, i);
+    feet[i] = pack_foot(f);
     // U_dense counts the reference's candidate box, whatever kernel computes the particle
     if (f.box) upd = (int64_t)f.nbx * f.nby * g.C;
     if (f.live) {
@@ -321,8 +360,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(
 // and one (brick key << 32 | record index) pair per brick it overlaps, in particle order.
 __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
     PlanIn in, Geo g, const int64_t* __restrict__ blk_kept, const int64_t* __restrict__ blk_pairs,
-    const int64_t* __restrict__ blk_pairs2, Record* __restrict__ records,
-    uint64_t* __restrict__ pairs_out, uint64_t* __restrict__ pairs2_out) {
+    const int64_t* __restrict__ blk_pairs2, const PackedFoot* __restrict__ feet,
+    Record* __restrict__ records, uint64_t* __restrict__ pairs_out, uint64_t* __restrict__ pairs2_out) {
   __shared__ int64_t sm[33];
   const int64_t i = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
   int64_t kept = 0, npair = 0, npair2 = 0;
@@ -330,7 +369,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
   f.live = false;
   f.route = ROUTE_BRICK;
   if (i < in.n) {
-    f = footprint(in, g, i);
+    f = unpack_foot(feet[i]);  // (computed by plan_count_kernel)
     if (f.live) {
       kept = 1;
       (f.route == ROUTE_BRICK ? npair : npair2) = count_pairs(f, g);
@@ -345,7 +384,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
   rec.px = in.px[i];
   rec.py = in.py[i];
   rec.h = in.h_eff[i];
-  rec.inv_h2 = 1.0 / (rec.h * rec.h);
+  rec.inv_h2 = f.route == ROUTE_COLUMN ? 0.0 : 1.0 / (rec.h * rec.h);  // (a DiracDelta kernel has no scale)
   rec.v = in.v[i];
   const double m = in.mHI ? in.mHI[i] : in.mHI_scalar;
   const double d = in.D ? in.D[i] : in.D_scalar;

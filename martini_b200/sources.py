@@ -242,7 +242,8 @@ class SPHSource:
             self.T_g = self.T_g[mask]
         if self.mHI_g.ndim > 0:
             self.mHI_g = self.mHI_g[mask]
-        self.xyz_g, self.vxyz_g = self.xyz_g[mask], self.vxyz_g[mask]
+        if self.xyz_g.shape[0] == mask.size:  # (PixelSource carries no Cartesian coordinates)
+            self.xyz_g, self.vxyz_g = self.xyz_g[mask], self.vxyz_g[mask]
         if self.skycoords is not None:
             self.skycoords = {k: v[mask] for k, v in self.skycoords.items()}
             self.radial_velocity = self.radial_velocity[mask]
@@ -260,18 +261,35 @@ class PixelSource(SPHSource):
 
     def __init__(self, *, pixcoords, sm_lengths, radial_velocity, distance_p, mHI_g, T_g=None,
                  sigma=None):
+        # (arrays that are already float64 and contiguous are kept as they are -- no copies, so
+        # page-locked inputs stay page-locked)
         self.pixcoords = np.ascontiguousarray(pixcoords, dtype=np.float64)
         self.npart = self.pixcoords.shape[1]
         self._sm_lengths = np.ascontiguousarray(sm_lengths, dtype=np.float64)
         self.radial_velocity = np.ascontiguousarray(radial_velocity, dtype=np.float64)
-        self.distance_p = np.ascontiguousarray(np.broadcast_to(distance_p, (self.npart,)), dtype=np.float64)
+        d = np.asarray(distance_p, dtype=np.float64)
+        self.distance_p = np.ascontiguousarray(d) if d.shape == (self.npart,) else np.full(self.npart, float(d))
         self.mHI_g = np.asarray(mHI_g, dtype=np.float64)
         self.T_g = None if T_g is None else np.asarray(T_g, dtype=np.float64)
-        self.input_mass = np.broadcast_to(self.mHI_g, (self.npart,)).sum()
-        self.distance = float(np.mean(self.distance_p))
         self.hsm_g = None
         self.skycoords = {}
-        self.xyz_g = self.vxyz_g = np.zeros((self.npart, 3))
+        self.xyz_g = self.vxyz_g = np.zeros((0, 3))
+        self._mHI0, self._D0 = (self.mHI_g, self.npart), self.distance_p
+
+    # (summary quantities of the UNPRUNED source, as the constructor would have computed them,
+    # evaluated when somebody asks: the original arrays are kept by reference until then)
+    @property
+    def input_mass(self):
+        if "_input_mass" not in self.__dict__:
+            m0, n0 = self.__dict__.pop("_mHI0")
+            self._input_mass = np.broadcast_to(m0, (n0,)).sum()
+        return self._input_mass
+
+    @property
+    def distance(self):
+        if "_distance" not in self.__dict__:
+            self._distance = float(np.mean(self.__dict__.pop("_D0")))
+        return self._distance
 
     def _init_skycoords(self):
         pass
