@@ -85,10 +85,12 @@ static int ensure_tables() {
   std::lock_guard<std::mutex> lock(g_once_mutex);
   if (done[dev]) return MTN_OK;
   static double erf_tab_host[ERF_NINT * ERF_NCOEF];
+  static double erf_tabc_host[ERFC_NINT * ERFC_NCOEF];
   static HostTables T;
   static bool built = false;
   if (!built) {
     build_erf_table(erf_tab_host);
+    build_erf_table_compact(erf_tabc_host);
     T = build_kernel_tables();
     for (int k = 0; k < WT_KINDS; ++k) g_table_err[k] = T.max_err[k];
     built = true;
@@ -96,6 +98,7 @@ static int ensure_tables() {
   if (T.rows.size() > (size_t)WT_MAX_ROWS * WT_ROW)
     return fail(MTN_ERR_LIMIT, "kernel tables exceed WT_MAX_ROWS%s", "");
   MTN_CUDA(cudaMemcpyToSymbol(g_erf_table, erf_tab_host, sizeof(erf_tab_host)));
+  MTN_CUDA(cudaMemcpyToSymbol(g_erf_table_compact, erf_tabc_host, sizeof(erf_tabc_host)));
   MTN_CUDA(cudaMemcpyToSymbol(c_wzone, T.zone, sizeof(T.zone)));
   MTN_CUDA(cudaMemcpyToSymbol(c_wnz, T.nz, sizeof(T.nz)));
   MTN_CUDA(cudaMemcpyToSymbol(c_wscale, T.scale, sizeof(T.scale)));
@@ -140,7 +143,7 @@ static int launch_stream(const StreamArgs& a, int route, bool count, unsigned gr
   if (route == ROUTE_COLUMN) {
     static bool attr_set[MAX_DEVICES][2] = {{false, false}};
     const int dev = current_device();
-    const int smem = (int)((STREAM_WARPS * CSB + ERF_NINT * ERF_NCOEF) * sizeof(double));
+    const int smem = (int)((STREAM_WARPS * CSB + ERFC_NINT * ERFC_NCOEF) * sizeof(double));
     {
       std::lock_guard<std::mutex> lock(g_once_mutex);
       if (!attr_set[dev][count]) {

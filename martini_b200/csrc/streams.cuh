@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs
   const Geo& g = a.geo;
   const double sgn = g.edges_increasing ? 1.0 : -1.0;
   for (int c = lane; c < CSB; c += 32) acc[c] = 0.0;
-  for (int k = threadIdx.x; k < ERF_NINT * ERF_NCOEF; k += STREAM_THREADS) erf_table[k] = g_erf_table[k];
+  for (int k = threadIdx.x; k < ERFC_NINT * ERFC_NCOEF; k += STREAM_THREADS) erf_table[k] = g_erf_table_compact[k];
   __syncthreads();
   unsigned long long n_upd = 0, n_w = 0, n_erf = 0;
   Item it;
@@ -120,18 +120,18 @@ __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs
           double E1 = 0.0, E2 = 0.0, E3 = 0.0;
           if (lane <= n_here) {
             const double t1 = (__ldg(edge + min(c1, nchs)) - v) * sc;
-            E1 = erf_tab_from(erf_table, t1);
+            E1 = erf_tab_compact(erf_table, t1);
             if (COUNT) n_erf += fabs(t1) < ERF_SAT;
           }
           if (n_here >= 32) {
             if (lane + 32 <= n_here) {
               const double t2 = (__ldg(edge + min(c2, nchs)) - v) * sc;
-              E2 = erf_tab_from(erf_table, t2);
+              E2 = erf_tab_compact(erf_table, t2);
               if (COUNT) n_erf += fabs(t2) < ERF_SAT;
             }
             if (n_here == 64) {
               const double t3 = (__ldg(edge + e0 + 64) - v) * sc;
-              E3 = erf_tab_from(erf_table, t3);
+              E3 = erf_tab_compact(erf_table, t3);
               if (COUNT) n_erf += lane == 0 && fabs(t3) < ERF_SAT;
             }
           }
@@ -211,7 +211,7 @@ __device__ __forceinline__ void gaussian_pair(const double* __restrict__ erf_tab
   // edge k of an axis sits at pixel-centre k - 1/2: E_k = erf((p - (o + k) + 1/2) c)
   const int k = lane & 15;
   const double o = lane < 16 ? x0d : y0d, p = lane < 16 ? r.px : r.py;
-  const double E = erf_tab_from(erf_table, (p - (o + (double)k) + 0.5) * c);
+  const double E = erf_tab_compact(erf_table, (p - (o + (double)k) + 0.5) * c);
   const double F = E - __shfl_down_sync(0xffffffffu, E, 1);  // lanes 0-7: columns, 16-23: rows
   const double exA = __shfl_sync(0xffffffffu, F, lane >> 3);
   const double exB = __shfl_sync(0xffffffffu, F, (lane >> 3) + 4);
@@ -222,18 +222,18 @@ __device__ __forceinline__ void gaussian_pair(const double* __restrict__ erf_tab
   {
     const double dx = __dsub_rn(r.px, gx0);
     const double z2 = t2 - sq_dist(dx, dy) * k2;
-    wA = z2 > 0.0 ? erf_tab_from(erf_table, sqrt(0.5 * z2)) * exA * ey * q : 0.0;
+    wA = z2 > 0.0 ? erf_tab_compact(erf_table, sqrt(0.5 * z2)) * exA * ey * q : 0.0;
   }
   {
     const double dx = __dsub_rn(r.px, gx0 + 4.0);
     const double z2 = t2 - sq_dist(dx, dy) * k2;
-    wB = z2 > 0.0 ? erf_tab_from(erf_table, sqrt(0.5 * z2)) * exB * ey * q : 0.0;
+    wB = z2 > 0.0 ? erf_tab_compact(erf_table, sqrt(0.5 * z2)) * exB * ey * q : 0.0;
   }
 }
 
 struct SplatSmem {
   Record rec[STREAM_WARPS][PBATCH];
-  double erf_table[ERF_NINT * ERF_NCOEF];  // (shared-memory copy: see tables.cuh, erf_tab_from)
+  double erf_table[ERFC_NINT * ERFC_NCOEF];  // (shared-memory copy of the compact table, tables.cuh)
 };
 
 template <bool COUNT>
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) splat_kernel(const StreamArgs 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Record* rec = sm.rec[warp];
   const Geo& g = a.geo;
-  for (int k = threadIdx.x; k < ERF_NINT * ERF_NCOEF; k += STREAM_THREADS) sm.erf_table[k] = g_erf_table[k];
+  for (int k = threadIdx.x; k < ERFC_NINT * ERFC_NCOEF; k += STREAM_THREADS) sm.erf_table[k] = g_erf_table_compact[k];
   __syncthreads();
   unsigned long long n_upd = 0, n_w = 0;
   Item it;

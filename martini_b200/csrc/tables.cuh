@@ -19,26 +19,26 @@ namespace mtn {
 // ------------------------------------------------------------------------------------ erf
 __device__ double g_erf_table[ERF_NINT * ERF_NCOEF];
 
-// erf(t) to ~1 ulp: exactly +-1 for |t| >= ERF_SAT (where erf rounds to 1 in float64 anyway),
-// otherwise a degree-9 Taylor polynomial about the centre of the 1/16-wide interval holding
-// |t| (|u| <= 1/32: truncation < 5e-18).  Branch-free.  `table` is g_erf_table or a copy of it
-// in shared memory (the column kernel: every lane reads its own row, and the L1 / shared-memory
-// data pipe -- 128 B per cycle -- is what bounds it; a shared-memory row costs 4 wavefronts per
-// 16-byte load of a warp, a global one 5.4 and three times the latency).
-__device__ __forceinline__ double erf_tab_from(const double* __restrict__ table, double t) {
+// erf(t): exactly +-1 for |t| >= ERF_SAT (where erf rounds to 1 in float64 anyway), otherwise a
+// Taylor polynomial about the centre of the table interval holding |t|.  Branch-free.  Two tables:
+// g_erf_table (1/16-wide intervals, degree 9, truncation < 5e-18; read through L1 by the brick
+// kernel, where few rows matter more than few loads) and the compact one (common.cuh) that the
+// column / splat kernels copy into shared memory: every lane reads its own row there, and the
+// L1 / shared-memory data pipe -- 128 B per cycle -- is what bounds them (a shared-memory row
+// costs 4 wavefronts per 16-byte load of a warp, a global one 5.4 and three times the latency).
+__device__ double g_erf_table_compact[ERFC_NINT * ERFC_NCOEF];
+
+__device__ __forceinline__ double erf_tab_compact(const double* __restrict__ table, double t) {
   const double a = fmin(fabs(t), ERF_SAT);
-  const int i = (int)(a * ERF_INV_W);  // a = ERF_SAT lands in the last (saturated) interval
-  const double u = a - ((double)i + 0.5) * (1.0 / ERF_INV_W);
-  const double2* row = reinterpret_cast<const double2*>(table + i * ERF_NCOEF);
-  double2 c[ERF_NCOEF / 2];
-#pragma unroll
-  for (int k = ERF_NCOEF / 2 - 1; k >= 0; --k) c[k] = row[k];
-  double r = fma(c[ERF_NCOEF / 2 - 1].y, u, c[ERF_NCOEF / 2 - 1].x);
-#pragma unroll
-  for (int k = ERF_NCOEF / 2 - 2; k >= 0; --k) {
-    r = fma(r, u, c[k].y);
-    r = fma(r, u, c[k].x);
-  }
+  const int i = (int)(a * ERFC_INV_W);  // a = ERF_SAT lands in the last (saturated) interval
+  const double u = a - ((double)i + 0.5) * (1.0 / ERFC_INV_W);
+  const double2* row = reinterpret_cast<const double2*>(table + i * ERFC_NCOEF);
+  const double2 c45 = row[2], c23 = row[1], c01 = row[0];
+  double r = fma(c45.y, u, c45.x);
+  r = fma(r, u, c23.y);
+  r = fma(r, u, c23.x);
+  r = fma(r, u, c01.y);
+  r = fma(r, u, c01.x);
   r = fmin(r, 1.0);
   r = fabs(t) >= ERF_SAT ? 1.0 : r;
   return copysign(r, t);

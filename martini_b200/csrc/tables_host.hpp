@@ -300,22 +300,26 @@ static HostTables build_kernel_tables() {
 
 // erf: Taylor coefficients about the interval centres,
 // erf^(k)(x) = (2/sqrt(pi)) (-1)^(k-1) H_(k-1)(x) exp(-x^2), H = physicists' Hermite.
-static void build_erf_table(double* tab) {
+static void build_erf_table_generic(double* tab, int inv_w, int deg, int nint) {
   const ld two_over_sqrt_pi = 1.1283791670955125738961589031215452L;
-  for (int i = 0; i < ERF_NINT; ++i) {
-    const ld c = ((ld)i + 0.5L) / ERF_INV_W;
+  const int ncoef = deg + 1;
+  for (int i = 0; i < nint; ++i) {
+    const ld c = ((ld)i + 0.5L) / inv_w;
     const ld ex = expl(-c * c);
     ld h_prev = 0.0L, h = 1.0L, fact = 1.0L;  // H_(-1) := 0, H_0 = 1
-    tab[i * ERF_NCOEF + 0] = (double)erfl(c);
-    for (int k = 1; k <= ERF_DEG; ++k) {
+    tab[i * ncoef + 0] = (double)erfl(c);
+    for (int k = 1; k <= deg; ++k) {
       fact *= k;
       const ld sign = ((k - 1) & 1) ? -1.0L : 1.0L;
-      tab[i * ERF_NCOEF + k] = (double)(two_over_sqrt_pi * sign * h * ex / fact);
+      tab[i * ncoef + k] = (double)(two_over_sqrt_pi * sign * h * ex / fact);
       const ld h_next = 2.0L * c * h - 2.0L * (k - 1) * h_prev;
       h_prev = h;
       h = h_next;
     }
   }
 }
+static void build_erf_table(double* tab) { build_erf_table_generic(tab, ERF_INV_W, ERF_DEG, ERF_NINT); }
+// the compact table of the column / splat kernels (tables.cuh: erf_tab_compact)
+static void build_erf_table_compact(double* tab) { build_erf_table_generic(tab, ERFC_INV_W, ERFC_DEG, ERFC_NINT); }
 
 }  // namespace mtn

@@ -253,11 +253,14 @@ def route_particles(dev, sm_range, bounds, group=None):
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts, group=group)
     sc, rc = send_counts.tolist(), recv_counts.tolist()
-    payload = torch.stack([dev[k] for k in keys], dim=1).index_select(0, idx)  # (n_send, F), bucketed
-    recv = torch.empty((sum(rc), len(keys)), dtype=torch.float64, device=device)
-    dist.all_to_all_single(recv, payload, output_split_sizes=rc, input_split_sizes=sc, group=group)
-    cols = recv.t().contiguous()  # (F, n_recv): one contiguous array per quantity for the C ABI
-    out.update({k: cols[i] for i, k in enumerate(keys)})
+    n_recv = sum(rc)
+    # one gather + one all-to-all per quantity: the receive side is then already the contiguous
+    # array the C ABI wants (no packing into records, no transpose afterwards)
+    for k in keys:
+        send = dev[k].index_select(0, idx)
+        recv = torch.empty(n_recv, dtype=send.dtype, device=device)
+        dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc, group=group)
+        out[k] = recv
     return out
 
 
