@@ -85,7 +85,7 @@ static int ensure_tables() {
   std::lock_guard<std::mutex> lock(g_once_mutex);
   if (done[dev]) return MTN_OK;
   static double erf_tab_host[ERF_NINT * ERF_NCOEF];
-  static double erf_tabc_host[ERFC_NINT * ERFC_NCOEF];
+  static double erf_tabc_host[ERFC_DOUBLES];
   static HostTables T;
   static bool built = false;
   if (!built) {
@@ -139,27 +139,33 @@ static int launch_project_count(const ProjArgs& a, int primary_kind, int64_t max
 }
 
 // The column / splat kernel of an insertion's second stream.
-static int launch_stream(const StreamArgs& a, int route, bool count, unsigned grid, cudaStream_t st) {
+static int launch_stream(const StreamArgs& a, int route, bool count, int64_t max_items, cudaStream_t st) {
+  const int64_t want = (max_items + STREAM_WARPS - 1) / STREAM_WARPS;
   if (route == ROUTE_COLUMN) {
     static bool attr_set[MAX_DEVICES][2] = {{false, false}};
     const int dev = current_device();
-    const int smem = (int)((STREAM_WARPS * CSB + ERFC_NINT * ERFC_NCOEF) * sizeof(double));
+    const size_t smem = column_smem_bytes(a.geo.C);
     {
       std::lock_guard<std::mutex> lock(g_once_mutex);
       if (!attr_set[dev][count]) {
+        const int smem_max = (int)column_smem_bytes(CSB);
         if (count)
-          MTN_CUDA(cudaFuncSetAttribute(column_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+          MTN_CUDA(cudaFuncSetAttribute(column_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         else
-          MTN_CUDA(cudaFuncSetAttribute(column_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+          MTN_CUDA(cudaFuncSetAttribute(column_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         attr_set[dev][count] = true;
       }
     }
+    // resident CTAs per SM: shared memory (227 KB per SM, 1 KB reserved per CTA), at most 12 (48 warps)
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(12, (227 * 1024) / (smem + 1024)));
+    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sm_count() * per_sm);
     if (count) {
       MTN_LAUNCH(column_kernel<true>, grid, STREAM_THREADS, smem, st, a);
     } else {
       MTN_LAUNCH(column_kernel<false>, grid, STREAM_THREADS, smem, st, a);
     }
   } else {
+    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sm_count() * 5);  // 96 registers
     if (count) {
       MTN_LAUNCH(splat_kernel<true>, grid, STREAM_THREADS, 0, st, a);
     } else {
@@ -693,10 +699,7 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
     a.partials = ws.s[1].partials;
     a.px_area = px_area;
     a.exec_counts = (unsigned long long*)(ws.s[1].scalars + 8);
-    // resident CTAs per SM: column 40 KB of shared memory, splat 96 registers
-    const unsigned grid = (unsigned)std::min<int64_t>((ws.s[1].max_items + STREAM_WARPS - 1) / STREAM_WARPS,
-                                                      (int64_t)sm_count() * 5);
-    if (int rc = launch_stream(a, g.route2, g_count_exec != 0, grid, st)) return rc;
+    if (int rc = launch_stream(a, g.route2, g_count_exec != 0, ws.s[1].max_items, st)) return rc;
     MTN_LAUNCH_CHECK();
     if (g.route2 == ROUTE_COLUMN) {
       MTN_LAUNCH(column_reduce_kernel, (unsigned)ws.s[1].max_multi, 256, 0, st, g, ws.s[1].multis,

@@ -65,16 +65,25 @@ __device__ __forceinline__ bool next_item(const StreamArgs& a, int lane, Item& i
 }
 
 // ------------------------------------------------------------------------------- column
+__host__ __device__ inline int column_acc_stride(int C) { return C >= CSB ? CSB : (C + 63) / 64 * 64; }
+inline size_t column_smem_bytes(int C) {
+  return ((size_t)STREAM_WARPS * column_acc_stride(C) + ERFC_DOUBLES) * sizeof(double);
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs a) {
-  MTN_DYN_SMEM(double, col_smem);  // [STREAM_WARPS][CSB] accumulators, then a copy of the erf table
+  // [STREAM_WARPS][acc_stride] accumulators (acc_stride = channels of a superblock, rounded up
+  // to 64: a 256-channel cube needs 2 KB per warp, not the 8 KB of a full superblock -- shared
+  // memory is what limits the resident warps here), then a copy of the compact erf table
+  MTN_DYN_SMEM(double, col_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* acc = col_smem + warp * CSB;
-  double* erf_table = col_smem + STREAM_WARPS * CSB;
   const Geo& g = a.geo;
+  const int acc_stride = column_acc_stride(g.C);
+  double* acc = col_smem + warp * acc_stride;
+  double* erf_table = col_smem + STREAM_WARPS * acc_stride;
   const double sgn = g.edges_increasing ? 1.0 : -1.0;
-  for (int c = lane; c < CSB; c += 32) acc[c] = 0.0;
-  for (int k = threadIdx.x; k < ERFC_NINT * ERFC_NCOEF; k += STREAM_THREADS) erf_table[k] = g_erf_table_compact[k];
+  for (int c = lane; c < acc_stride; c += 32) acc[c] = 0.0;
+  for (int k = threadIdx.x; k < ERFC_DOUBLES; k += STREAM_THREADS) erf_table[k] = g_erf_table_compact[k];
   __syncthreads();
   unsigned long long n_upd = 0, n_w = 0, n_erf = 0;
   Item it;
@@ -233,7 +242,7 @@ __device__ __forceinline__ void gaussian_pair(const double* __restrict__ erf_tab
 
 struct SplatSmem {
   Record rec[STREAM_WARPS][PBATCH];
-  double erf_table[ERFC_NINT * ERFC_NCOEF];  // (shared-memory copy of the compact table, tables.cuh)
+  double erf_table[ERFC_DOUBLES];  // (shared-memory copy of the compact table, tables.cuh)
 };
 
 template <bool COUNT>
@@ -242,7 +251,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) splat_kernel(const StreamArgs 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Record* rec = sm.rec[warp];
   const Geo& g = a.geo;
-  for (int k = threadIdx.x; k < ERFC_NINT * ERFC_NCOEF; k += STREAM_THREADS) sm.erf_table[k] = g_erf_table_compact[k];
+  for (int k = threadIdx.x; k < ERFC_DOUBLES; k += STREAM_THREADS) sm.erf_table[k] = g_erf_table_compact[k];
   __syncthreads();
   unsigned long long n_upd = 0, n_w = 0;
   Item it;

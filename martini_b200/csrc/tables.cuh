@@ -26,13 +26,13 @@ __device__ double g_erf_table[ERF_NINT * ERF_NCOEF];
 // column / splat kernels copy into shared memory: every lane reads its own row there, and the
 // L1 / shared-memory data pipe -- 128 B per cycle -- is what bounds them (a shared-memory row
 // costs 4 wavefronts per 16-byte load of a warp, a global one 5.4 and three times the latency).
-__device__ double g_erf_table_compact[ERFC_NINT * ERFC_NCOEF];
+__device__ double g_erf_table_compact[ERFC_DOUBLES];
 
 __device__ __forceinline__ double erf_tab_compact(const double* __restrict__ table, double t) {
   const double a = fmin(fabs(t), ERF_SAT);
   const int i = (int)(a * ERFC_INV_W);  // a = ERF_SAT lands in the last (saturated) interval
   const double u = a - ((double)i + 0.5) * (1.0 / ERFC_INV_W);
-  const double2* row = reinterpret_cast<const double2*>(table + i * ERFC_NCOEF);
+  const double2* row = reinterpret_cast<const double2*>(table + erfc_row_offset(i));
   const double2 c45 = row[2], c23 = row[1], c01 = row[0];
   double r = fma(c45.y, u, c45.x);
   r = fma(r, u, c23.y);

@@ -320,6 +320,12 @@ static void build_erf_table_generic(double* tab, int inv_w, int deg, int nint) {
 }
 static void build_erf_table(double* tab) { build_erf_table_generic(tab, ERF_INV_W, ERF_DEG, ERF_NINT); }
 // the compact table of the column / splat kernels (tables.cuh: erf_tab_compact)
-static void build_erf_table_compact(double* tab) { build_erf_table_generic(tab, ERFC_INV_W, ERFC_DEG, ERFC_NINT); }
+static void build_erf_table_compact(double* tab) {
+  static double plain[ERFC_NINT * ERFC_NCOEF];
+  build_erf_table_generic(plain, ERFC_INV_W, ERFC_DEG, ERFC_NINT);
+  for (int i = 0; i < ERFC_DOUBLES; ++i) tab[i] = 0.0;
+  for (int r = 0; r < ERFC_NINT; ++r)
+    for (int k = 0; k < ERFC_NCOEF; ++k) tab[erfc_row_offset(r) + k] = plain[r * ERFC_NCOEF + k];  // skewed rows
+}
 
 }  // namespace mtn
