@@ -617,9 +617,25 @@ def measure_strong(eng, name, args, timer, world, rank, local, case=None, dev=No
     slab = peer.rows if peer is not None else torch.zeros((x_hi - x_lo, ny, nc), dtype=torch.float64, device=dev_t)
     full = torch.empty((nx, ny, nc), dtype=torch.float64, device=dev_t) if (rank == 0 and peer is None) else None
     route_ms = []
+    # the input exchange: fused bucket + peer stores into the ranks' inboxes (dist.PeerRouter);
+    # all-to-all over NCCL if symmetric memory is unavailable
+    router = None
+    if peer is not None:
+        try:
+            n_f = sum(isinstance(dev.get(k), torch.Tensor) for k in mdist.ROUTED_KEYS)
+            router = mdist.PeerRouter(n_f, n_all, dev_t)
+        except Exception as exc:  # noqa: BLE001
+            if rank == 0:
+                print(f"PeerRouter unavailable ({exc}); routing with all-to-all", file=sys.stderr)
+        ok = torch.tensor([1.0 if router is not None else 0.0], device=dev_t)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            router = None
 
     def routed_inputs():
         _, _, sm_range, _ = eng.smoothing_setup(dev["sm_length"], ctx.table)
+        if router is not None:
+            return router.route(eng, dev, sm_range, bounds)
         return mdist.route_particles(dev, sm_range, bounds)
 
     def step():
@@ -696,7 +712,7 @@ def measure_strong(eng, name, args, timer, world, rank, local, case=None, dev=No
         "value": u_dense / (ms_step * 1e-3), "unit": UNIT, "ms_per_step": ms_step, "steps": steps,
         "updates_per_step": u_dense, "insertion_wall_ms": ms_step, "slab_bounds": bounds,
         "partition": f"{world} work-balanced x-slabs of one cube; every rank holds 1/{world} of the particle list "
-                     "and routes it by slab with one all-to-all over NVLink (halo particles go to both neighbours), "
+                     "and routes it by slab (halo particles go to both neighbours): " + ("bucketing kernel that stores straight into the destination ranks' inboxes over NVLink (dist.PeerRouter), " if router is not None else "one all-to-all per quantity over NCCL, ")
                      + ("slabs stored into rank 0's cube over NVLink by the projection kernels' own stores "
                         "(symmetric memory)" if peer is not None else "NCCL gather to rank 0"),
         "per_rank": {"pairs": [float(p[1]) for p in per_rank], "kept": [float(p[2]) for p in per_rank],
@@ -714,6 +730,7 @@ def measure_strong(eng, name, args, timer, world, rank, local, case=None, dev=No
     if clocks is not None:
         blk["clocks"] = clocks
     cube = peer.buf if (peer is not None and rank == 0) else full
+    del router
     return blk, cube, case, dev, peer
 
 

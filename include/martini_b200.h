@@ -206,6 +206,33 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
 int mtn_last_launch_count(void);
 
 /*
+ * Multi-GPU input exchange: route particles to the ranks whose x-slab their candidate box can
+ * reach (martini.py:272-274 decides per pixel; a slab needs every particle with
+ * [px - r, px + r] intersecting its rows -- halo particles go to both neighbours).  The reference
+ * has no counterpart (one process, threads over pixels, martini.py:345-362).
+ *   mtn_route_count    per destination rank d (slab rows [bounds[d], bounds[d+1])): how many of
+ *                      the n particles go there -> totals_out[world] (device int64); leaves the
+ *                      per-block offsets mtn_route_scatter needs in `scratch`.
+ *   mtn_route_scatter  stores every routed particle's n_fields quantities into the destination
+ *                      rank's inbox: inboxes[d] is a DEVICE pointer valid on this device -- the
+ *                      peer-mapped inbox of rank d (symmetric memory over NVLink), laid out
+ *                      [field][capacity] -- at position src_offsets[d] (device int64[world]: the
+ *                      totals of the lower-numbered source ranks for d) + the particle's rank
+ *                      among this source's particles for d.  Order inside an inbox: source rank,
+ *                      then particle index.  fields / inboxes are HOST arrays of device pointers.
+ * The destination test is conservative (one pixel of slack); mtn_plan applies the exact
+ * predicate on the receiving rank.  world <= 16, n_fields <= 12.
+ */
+size_t mtn_route_scratch_bytes(int64_t n, int32_t world);
+int mtn_route_count(int64_t n, const double* px, const double* sm_range, int32_t world,
+                    const int32_t* bounds_host, void* scratch, size_t scratch_bytes,
+                    int64_t* totals_out, void* stream);
+int mtn_route_scatter(int64_t n, const double* px, const double* sm_range, int32_t world,
+                      const int32_t* bounds_host, int32_t n_fields, const double* const* fields_host,
+                      double* const* inboxes_host, int64_t capacity, const int64_t* src_offsets,
+                      const void* scratch, void* stream);
+
+/*
  * Measurement hooks (bench.py).  With timing enabled, mtn_project records CUDA events on
  * the caller's stream at its stage boundaries; mtn_last_timing then returns the seven stage
  * durations in ms: [emit, sort, items, project kernel, partial reduce, finalize, second stream

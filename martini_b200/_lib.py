@@ -133,6 +133,17 @@ SYMBOLS = {
         [C.POINTER(MtnParticles), C.POINTER(MtnKernelTable), C.POINTER(MtnCube),
          C.POINTER(MtnPlan), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p],
     ),
+    "mtn_route_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "mtn_route_count": (
+        C.c_int,
+        [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t,
+         C.c_void_p, C.c_void_p],
+    ),
+    "mtn_route_scatter": (
+        C.c_int,
+        [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
     "mtn_set_timing": (C.c_int, [C.c_int]),
     "mtn_last_timing": (C.c_int, [C.POINTER(C.c_float), C.c_int]),
     "mtn_set_count_exec": (C.c_int, [C.c_int]),

@@ -8,6 +8,7 @@
 #include "kernel_integrals.cuh"
 #include "plan.cuh"
 #include "project.cuh"
+#include "route.cuh"
 #include "scan.cuh"
 #include "sort.cuh"
 #include "streams.cuh"
@@ -720,6 +721,65 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
   }
   mark(7, st);
   g_ev_valid = g_timing != 0;
+  return MTN_OK;
+}
+
+static int fill_route_args(RouteArgs* a, int64_t n, const double* px, const double* sm_range, int32_t world,
+                           const int32_t* bounds) {
+  if (n < 0 || world < 1 || world > ROUTE_MAX_WORLD || !bounds || (n > 0 && (!px || !sm_range)))
+    return fail(MTN_ERR_INVALID, "route: bad arguments (world <= 16)%s", "");
+  a->n = n;
+  a->px = px;
+  a->sm_range = sm_range;
+  a->world = world;
+  for (int d = 0; d <= world; ++d) a->bounds[d] = bounds[d];
+  return MTN_OK;
+}
+
+size_t mtn_route_scratch_bytes(int64_t n, int32_t world) {
+  const int64_t nblk = std::max<int64_t>(1, (n + ROUTE_THREADS - 1) / ROUTE_THREADS);
+  return align_up((size_t)world * nblk * 4) + scan_temp_bytes(nblk, 4) + align_up((size_t)world * 4 * 2);
+}
+
+int mtn_route_count(int64_t n, const double* px, const double* sm_range, int32_t world, const int32_t* bounds,
+                    void* scratch, size_t scratch_bytes, int64_t* totals_out, void* stream) {
+  RouteArgs a;
+  if (int rc = fill_route_args(&a, n, px, sm_range, world, bounds)) return rc;
+  if (!scratch || scratch_bytes < mtn_route_scratch_bytes(n, world) || !totals_out)
+    return fail(MTN_ERR_WORKSPACE, "route: scratch too small%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nblk = std::max<int64_t>(1, (n + ROUTE_THREADS - 1) / ROUTE_THREADS);
+  uint32_t* blk = (uint32_t*)scratch;
+  void* scan_temp = (char*)scratch + align_up((size_t)world * nblk * 4);
+  uint32_t* tot32 = (uint32_t*)((char*)scan_temp + scan_temp_bytes(nblk, 4));
+  MTN_LAUNCH(route_count_kernel, (unsigned)nblk, ROUTE_THREADS, 0, st, a, nblk, blk);
+  MTN_LAUNCH_CHECK();
+  for (int d = 0; d < world; ++d)  // block counts -> exclusive block offsets, totals beside them
+    if (int rc = exclusive_scan<uint32_t, uint32_t>(blk + d * nblk, blk + d * nblk, nblk, scan_temp, tot32 + d, st))
+      return rc;
+  MTN_LAUNCH(widen_totals_kernel, 1, 32, 0, st, tot32, world, totals_out);
+  MTN_LAUNCH_CHECK();
+  return MTN_OK;
+}
+
+int mtn_route_scatter(int64_t n, const double* px, const double* sm_range, int32_t world, const int32_t* bounds,
+                      int32_t n_fields, const double* const* fields, double* const* inboxes, int64_t capacity,
+                      const int64_t* src_offsets, const void* scratch, void* stream) {
+  RouteArgs a;
+  if (int rc = fill_route_args(&a, n, px, sm_range, world, bounds)) return rc;
+  if (n_fields < 1 || n_fields > ROUTE_MAX_FIELDS || !fields || !inboxes || !src_offsets || !scratch || capacity < 0)
+    return fail(MTN_ERR_INVALID, "route: bad scatter arguments (at most 12 fields)%s", "");
+  if (n == 0) return MTN_OK;
+  const int64_t nblk = std::max<int64_t>(1, (n + ROUTE_THREADS - 1) / ROUTE_THREADS);
+  ScatterArgs s;
+  s.n_fields = n_fields;
+  for (int f = 0; f < ROUTE_MAX_FIELDS; ++f) s.src[f] = f < n_fields ? fields[f] : nullptr;
+  for (int d = 0; d < ROUTE_MAX_WORLD; ++d) s.dst[d] = d < world ? inboxes[d] : nullptr;
+  s.capacity = capacity;
+  s.blk_off = (const uint32_t*)scratch;
+  s.src_off = src_offsets;
+  MTN_LAUNCH(route_scatter_kernel, (unsigned)nblk, ROUTE_THREADS, 0, (cudaStream_t)stream, a, s, nblk);
+  MTN_LAUNCH_CHECK();
   return MTN_OK;
 }
 

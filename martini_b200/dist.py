@@ -267,3 +267,48 @@ def route_particles(dev, sm_range, bounds, group=None):
 def chunk_of(n, rank, world):
     """The contiguous share [a, b) of an n-particle list that rank ``rank`` uploads."""
     return (n * rank) // world, (n * (rank + 1)) // world
+
+
+class PeerRouter:
+    """The input exchange fused with its bucketing: every rank's routed particles are stored
+    straight into the destination ranks' inboxes through peer-mapped pointers (symmetric
+    memory over NVLink) by ``mtn_route_scatter`` -- no send buffers, no all-to-all.  Host
+    involvement per step: one 8-byte read-back (how many particles arrived) and two barriers.
+
+    ``capacity``: particles an inbox can hold (per quantity); ``route`` raises if a rank would
+    receive more."""
+
+    def __init__(self, n_fields, capacity, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group or dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.capacity, self.n_fields = int(capacity), int(n_fields)
+        self.inbox = symm_mem.empty((n_fields, self.capacity), dtype=torch.float64, device=device)
+        self.hdl = symm_mem.rendezvous(self.inbox, self.group)
+        self._peers = [self.hdl.get_buffer(r, (n_fields, self.capacity), torch.float64) for r in range(self.world)]
+        self.ptrs = [t.data_ptr() for t in self._peers]
+
+    def _barrier(self):
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.group)
+
+    def route(self, engine, dev, sm_range, bounds):
+        keys = [k for k in ROUTED_KEYS if isinstance(dev.get(k), torch.Tensor)]
+        assert len(keys) <= self.n_fields
+        out = {k: v for k, v in dev.items() if k not in keys}
+        totals, scratch = engine.route_count(dev["px"], sm_range, bounds)
+        counts = torch.empty((self.world, self.world), dtype=torch.int64, device=totals.device)  # [src][dst]
+        dist.all_gather_into_tensor(counts, totals, group=self.group)
+        src_offsets = counts[:self.rank].sum(dim=0)
+        arriving = counts.sum(dim=0)
+        n_recv = int(arriving[self.rank])            # the one read-back; also orders the host after the gather
+        if int(arriving.max()) > self.capacity:      # (same verdict on every rank)
+            raise RuntimeError(f"PeerRouter: {int(arriving.max())} particles for one rank exceed the inbox "
+                               f"capacity {self.capacity}")
+        self._barrier()                              # every rank is done reading its inbox of the last step
+        engine.route_scatter(dev["px"], sm_range, bounds, [dev[k] for k in keys], self.ptrs, self.capacity,
+                             src_offsets, scratch)
+        self._barrier()                              # all stores have landed
+        out.update({k: self.inbox[i, :n_recv] for i, k in enumerate(keys)})
+        return out

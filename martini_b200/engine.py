@@ -236,6 +236,32 @@ class Engine:
         del keep
         return plan
 
+    # ------------------------------------------------------------------ multi-GPU routing
+    @_on_device
+    def route_count(self, px, sm_range, bounds):
+        """-> (totals int64[world] on the device, scratch to hand to route_scatter)."""
+        world = len(bounds) - 1
+        n = px.numel()
+        b = (C.c_int32 * (world + 1))(*[int(x) for x in bounds])
+        nbytes = self.lib.mtn_route_scratch_bytes(n, world)
+        scratch = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+        totals = torch.zeros(world, dtype=torch.int64, device=self.device)
+        self._check(self.lib.mtn_route_count(n, _ptr(px), _ptr(sm_range), world, b, _ptr(scratch), scratch.numel(),
+                                            _ptr(totals), self._stream()), "mtn_route_count")
+        return totals, scratch
+
+    @_on_device
+    def route_scatter(self, px, sm_range, bounds, fields, inbox_ptrs, capacity, src_offsets, scratch):
+        """Store the routed particles' ``fields`` (device tensors) into the ranks' inboxes
+        (``inbox_ptrs``: one device pointer per rank, peer-mapped)."""
+        world = len(bounds) - 1
+        b = (C.c_int32 * (world + 1))(*[int(x) for x in bounds])
+        f = (C.c_void_p * len(fields))(*[t.data_ptr() for t in fields])
+        d = (C.c_void_p * world)(*[int(p) for p in inbox_ptrs])
+        self._check(self.lib.mtn_route_scatter(px.numel(), _ptr(px), _ptr(sm_range), world, b, len(fields), f, d,
+                                              int(capacity), _ptr(src_offsets), _ptr(scratch), self._stream()),
+                    "mtn_route_scatter")
+
     # ------------------------------------------------------------------ beam convolution
     @_on_device
     def convolve_beam(self, cube: torch.Tensor, kernel: torch.Tensor, scale: float = 1.0):
