@@ -208,7 +208,15 @@ static int make_geo(const MtnCube* c, const MtnKernelTable* table, Geo* g, int e
   // Keys must fit the sort's 32-bit key; if they do not, everything stays with the bricks.
   g->route2 = ROUTE_BRICK;
   g->n_keys2 = 0;
-  for (int i = 0; i < MTN_MAX_KERNELS; ++i) g->kind[i] = (table && i < table->n) ? table->k[i].kind : -1;
+  for (int i = 0; i < MTN_MAX_KERNELS; ++i) {
+    g->kind[i] = (table && i < table->n) ? table->k[i].kind : -1;
+    switch (g->kind[i]) {
+      case MTN_KERNEL_WENDLANDC2: case MTN_KERNEL_WENDLANDC6: case MTN_KERNEL_CUBICSPLINE:
+      case MTN_KERNEL_QUARTICSPLINE: g->support[i] = 1.0; break;
+      case MTN_KERNEL_GAUSSIAN: g->support[i] = table->k[i].truncate * 0.42466090014400953; break;
+      default: g->support[i] = INFINITY;
+    }
+  }
   static int streams = -1;  // MTN_STREAMS=0: developer switch, everything through the brick kernel
   if (streams < 0) {
     const char* e = getenv("MTN_STREAMS");

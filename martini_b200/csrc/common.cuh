@@ -91,6 +91,10 @@ struct Geo {
   int route2;           // ROUTE_COLUMN / ROUTE_SPLAT: the second stream of this insertion; 0: none
   int64_t n_keys2;      // keys of the second stream
   int kind[MTN_MAX_KERNELS];  // MTN_KERNEL_* of each kernel-table entry
+  // radius of the kernel's support in units of h_eff: the pixel integral is exactly zero from
+  // there on (R >= 1 for the Wendland / spline kernels, sph_kernels.py:436, 683, 852, 1561;
+  // d / h / sigma >= truncate for the Gaussian, :1030); +inf: no culling
+  double support[MTN_MAX_KERNELS];
 };
 
 // One staged particle: everything the projection kernel needs.  The footprint (candidate box

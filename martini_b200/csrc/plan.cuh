@@ -101,6 +101,7 @@ struct Foot {
   bool live;           // box && a live channel exists (&& a pixel with non-zero weight, COLUMN)
   int route;           // Route: which kernel computes this particle
   int nbx, nby;        // extent of the reference's candidate box in the slab (U_dense)
+  double px, py, s2;   // position and squared support radius [px^2] (tile culling, brick route)
 };
 
 // What the count pass leaves for the emit pass (24 bytes per particle), so the footprint --
@@ -122,17 +123,6 @@ __device__ __forceinline__ PackedFoot pack_foot(const Foot& f) {
   p.pad = 0;
   return p;
 }
-__device__ __forceinline__ Foot unpack_foot(const PackedFoot& p) {
-  Foot f;
-  f.i0 = p.i0; f.i1 = p.i1; f.j0 = p.j0; f.j1 = p.j1;
-  f.c0 = p.c0; f.c1 = p.c1;
-  f.live = p.live != 0;
-  f.box = f.live;
-  f.route = p.route;
-  f.nbx = f.nby = 0;
-  return f;
-}
-
 // Smallest and largest integer i in [lim_lo, lim_hi] with |i - p| <= r, the candidate test
 // of martini.py:272-274 evaluated exactly as numpy does (fl(i - p), then compare).
 __device__ __forceinline__ bool pixel_bounds(double p, double r, int lim_lo, int lim_hi, int& lo,
@@ -235,6 +225,12 @@ __device__ __forceinline__ Foot footprint(const PlanIn& in, const Geo& g, int64_
   if (!pixel_bounds(in.px[i], r, g.x_lo, g.x_hi - 1, f.i0, f.i1)) return f;
   if (!pixel_bounds(in.py[i], r, 0, g.ny - 1, f.j0, f.j1)) return f;
   f.box = true;
+  f.px = in.px[i];
+  f.py = in.py[i];
+  {
+    const double s = in.h_eff[i] * g.support[in.kernel_id ? in.kernel_id[i] : 0];
+    f.s2 = s * s * (1.0 + 1.0e-9);  // (a tile is culled only if it is clearly outside)
+  }
   f.nbx = f.i1 - f.i0 + 1;
   f.nby = f.j1 - f.j0 + 1;
   const double inv_s = g.spectrum == MTN_SPECTRUM_GAUSSIAN ? inv_sqrt2_sigma(in, i) : 1.0;
@@ -254,6 +250,23 @@ __device__ __forceinline__ Foot footprint(const PlanIn& in, const Geo& g, int64_
       f.live = false;
     }
   }
+  return f;
+}
+
+__device__ __forceinline__ Foot unpack_foot(const PackedFoot& p, const PlanIn& in, const Geo& g, int64_t i) {
+  Foot f;
+  f.px = in.px[i];
+  f.py = in.py[i];
+  {
+    const double s = in.h_eff[i] * g.support[in.kernel_id ? in.kernel_id[i] : 0];
+    f.s2 = s * s * (1.0 + 1.0e-9);
+  }
+  f.i0 = p.i0; f.i1 = p.i1; f.j0 = p.j0; f.j1 = p.j1;
+  f.c0 = p.c0; f.c1 = p.c1;
+  f.live = p.live != 0;
+  f.box = f.live;
+  f.route = p.route;
+  f.nbx = f.nby = 0;
   return f;
 }
 
@@ -308,6 +321,19 @@ __global__ void __launch_bounds__(256) tile_phase_kernel(int n_tiles,
   phase[t] = ph;
 }
 
+// Whether any pixel of tile (tx, ty) inside the particle's box can have a non-zero weight: the
+// square candidate box of the reference (martini.py:272-274) has corners the kernel's round
+// support does not reach, and W = 0 exactly there -- 18 % of the (particle, tile) pairs of
+// config 2 hold nothing but such zeros.  Distance from the particle to the nearest pixel centre
+// of the tile's share of the box, against the support radius (with a relative margin of 1e-9
+// on the safe side).
+__device__ __forceinline__ bool tile_reached(const Foot& f, const Geo& g, int tx, int ty) {
+  const double xl = (double)max(g.x_lo + tx * TILE_X, f.i0), xh = (double)min(g.x_lo + tx * TILE_X + TILE_X - 1, f.i1);
+  const double yl = (double)max(ty * TILE_Y, f.j0), yh = (double)min(ty * TILE_Y + TILE_Y - 1, f.j1);
+  const double dx = fmax(fmax(xl - f.px, f.px - xh), 0.0), dy = fmax(fmax(yl - f.py, f.py - yh), 0.0);
+  return !(dx * dx + dy * dy >= f.s2);  // (NaN / inf support: reached)
+}
+
 // Pairs a particle contributes to its stream: (particle, brick) for the brick kernel,
 // (particle, pixel x channel superblock) for COLUMN, (particle, tile x channel) for SPLAT.
 __device__ __forceinline__ int64_t count_pairs(const Foot& f, const Geo& g) {
@@ -318,6 +344,7 @@ __device__ __forceinline__ int64_t count_pairs(const Foot& f, const Geo& g) {
   int64_t n = 0;
   for (int tx = tx0; tx <= tx1; ++tx)
     for (int ty = ty0; ty <= ty1; ++ty) {
+      if (!tile_reached(f, g, tx, ty)) continue;
       int k0, k1;
       block_range(f, g.phase[tx * g.nty + ty], k0, k1);
       n += k1 - k0 + 1;
@@ -369,7 +396,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
   f.live = false;
   f.route = ROUTE_BRICK;
   if (i < in.n) {
-    f = unpack_foot(feet[i]);  // (computed by plan_count_kernel)
+    f = unpack_foot(feet[i], in, g, i);  // (computed by plan_count_kernel)
     if (f.live) {
       kept = 1;
       (f.route == ROUTE_BRICK ? npair : npair2) = count_pairs(f, g);
@@ -423,6 +450,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
           pairs2_out[off2++] = ((uint64_t)(uint32_t)((int64_t)tile * g.C + c) << 32) | (uint64_t)(uint32_t)ridx;
         continue;
       }
+      if (!tile_reached(f, g, tx, ty)) continue;
       int k0, k1;
       block_range(f, g.phase[tile], k0, k1);
       for (int k = k0; k <= k1; ++k) {
