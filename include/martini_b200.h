@@ -206,6 +206,34 @@ int mtn_project(const MtnParticles* p, const MtnKernelTable* table, const MtnCub
 int mtn_last_launch_count(void);
 
 /*
+ * Coordinate front-end: replaces SPHSource._init_skycoords and
+ * _init_pixcoords (martini/sources/sph_source.py:265-362: rotate to (ra, dec), translate by the
+ * distance, peculiar velocity + Hubble flow, spherical representation, WCS pixel coordinates)
+ * and _BaseSPHKernel._init_sm_lengths (martini/sph_kernels.py:235-255) for the ICRS frame /
+ * specsys and the cube's RA---TAN / DEC--TAN / VRAD-or-FREQ system (martini/datacube.py:426-486).
+ * xyz, vxyz: (n, 3) row-major, kpc and km/s in the galaxy's frame (after SPHSource.rotate);
+ * hsm: kpc (NULL selects hsm_scalar).  Outputs (device, length n): pixel coordinates (0-indexed,
+ * pad included), radial velocity [km/s], distance [Mpc], smoothing length [pixels].
+ */
+typedef struct MtnFrontEnd {
+  double rotation[9];      /* row-major: galaxy frame -> frame whose x axis points to (ra, dec) */
+  double direction[3];     /* unit vector towards (ra, dec) */
+  double distance_mpc;     /* source.distance */
+  double vpeculiar;        /* km/s, along the line of sight */
+  double hubble;           /* h * 100 km/s/Mpc */
+  double ra0_rad, dec0_rad;/* cube centre (datacube.ra, .dec) */
+  double px_size_arcsec;   /* datacube.px_size */
+  double crpix[3];         /* 1-indexed reference pixels: n/2 + 0.5 (+ pad) (datacube.py:469-475) */
+  double spectral_centre;  /* km/s (VRAD) or Hz (FREQ) */
+  double channel_width;    /* |cdelt3| in the same unit */
+  int32_t freq_mode;       /* 1: FREQ axis (frequency increases with channel), 0: VRAD */
+  int32_t reserved;
+} MtnFrontEnd;
+int mtn_sky_to_pix(const MtnFrontEnd* fe, int64_t n, const double* xyz, const double* vxyz,
+                   const double* hsm, double hsm_scalar, double* px, double* py, double* pz, double* v,
+                   double* D, double* sm_length, void* stream);
+
+/*
  * Multi-GPU input exchange: route particles to the ranks whose x-slab their candidate box can
  * reach (martini.py:272-274 decides per pixel; a slab needs every particle with
  * [px - r, px + r] intersecting its rows -- halo particles go to both neighbours).  The reference

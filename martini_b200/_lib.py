@@ -90,6 +90,24 @@ class MtnCube(C.Structure):
     ]
 
 
+class MtnFrontEnd(C.Structure):
+    _fields_ = [
+        ("rotation", C.c_double * 9),
+        ("direction", C.c_double * 3),
+        ("distance_mpc", C.c_double),
+        ("vpeculiar", C.c_double),
+        ("hubble", C.c_double),
+        ("ra0_rad", C.c_double),
+        ("dec0_rad", C.c_double),
+        ("px_size_arcsec", C.c_double),
+        ("crpix", C.c_double * 3),
+        ("spectral_centre", C.c_double),
+        ("channel_width", C.c_double),
+        ("freq_mode", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 class MtnPlan(C.Structure):
     _fields_ = [
         ("n_kept", C.c_int64),
@@ -132,6 +150,11 @@ SYMBOLS = {
         C.c_int,
         [C.POINTER(MtnParticles), C.POINTER(MtnKernelTable), C.POINTER(MtnCube),
          C.POINTER(MtnPlan), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
+    "mtn_sky_to_pix": (
+        C.c_int,
+        [C.POINTER(MtnFrontEnd), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
     "mtn_route_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "mtn_route_count": (

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "convolve.cuh"
+#include "frontend.cuh"
 #include "kernel_integrals.cuh"
 #include "plan.cuh"
 #include "project.cuh"
@@ -866,6 +867,46 @@ int mtn_convolve_beam(const double* cube_in, double* cube_out, int32_t nx, int32
   const dim3 grid((nc + 31) / 32, (ny + CONV_WARPS * CONV_TY - 1) / (CONV_WARPS * CONV_TY), (nx + CONV_TX - 1) / CONV_TX);
   MTN_LAUNCH(convolve_beam_kernel, grid, CONV_WARPS * 32, smem, (cudaStream_t)stream, cube_in, cube_out, nx, ny, nc,
              kernel, ka, kb, scale);
+  MTN_LAUNCH_CHECK();
+  return MTN_OK;
+}
+
+int mtn_sky_to_pix(const MtnFrontEnd* fe, int64_t n, const double* xyz, const double* vxyz, const double* hsm,
+                   double hsm_scalar, double* px, double* py, double* pz, double* v, double* D, double* sm_length,
+                   void* stream) {
+  if (!fe || n < 0 || (n > 0 && (!xyz || !vxyz || !px || !py || !pz || !v || !D || !sm_length)))
+    return fail(MTN_ERR_INVALID, "sky_to_pix: bad arguments%s", "");
+  if (!(fe->px_size_arcsec > 0.0) || !(fe->channel_width > 0.0))
+    return fail(MTN_ERR_INVALID, "sky_to_pix: px_size and channel_width must be > 0%s", "");
+  if (n == 0) return MTN_OK;
+  FrontEndArgs a;
+  a.n = n;
+  a.xyz = xyz;
+  a.vxyz = vxyz;
+  a.hsm = hsm;
+  a.hsm_scalar = hsm_scalar;
+  for (int k = 0; k < 9; ++k) a.R[k] = fe->rotation[k];
+  for (int k = 0; k < 3; ++k) a.unit[k] = fe->direction[k];
+  a.distance_kpc = fe->distance_mpc * 1.0e3;
+  a.vpeculiar = fe->vpeculiar;
+  a.hubble = fe->hubble;
+  a.sin_d0 = sin(fe->dec0_rad);
+  a.cos_d0 = cos(fe->dec0_rad);
+  a.a0 = fe->ra0_rad;
+  a.rad_to_px = 1.0 / (fe->px_size_arcsec * (3.14159265358979323846 / 648000.0));
+  a.crpix_x = fe->crpix[0];
+  a.crpix_y = fe->crpix[1];
+  a.crpix_z = fe->crpix[2];
+  a.freq_mode = fe->freq_mode;
+  a.spectral_centre = fe->spectral_centre;
+  a.channel_width = fe->channel_width;
+  a.px = px;
+  a.py = py;
+  a.pz = pz;
+  a.v = v;
+  a.D = D;
+  a.sm_length = sm_length;
+  MTN_LAUNCH(sky_to_pix_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, a);
   MTN_LAUNCH_CHECK();
   return MTN_OK;
 }

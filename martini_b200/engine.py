@@ -236,6 +236,18 @@ class Engine:
         del keep
         return plan
 
+    # ------------------------------------------------------------------ coordinate front-end
+    @_on_device
+    def sky_to_pix(self, fe: "L.MtnFrontEnd", xyz, vxyz, hsm):
+        """-> (px, py, pz, v, D, sm_length) device tensors; see mtn_sky_to_pix.  ``xyz`` / ``vxyz``:
+        (n, 3) float64 device tensors; ``hsm``: (n,) tensor or a scalar."""
+        n = xyz.shape[0]
+        out = [torch.empty(n, dtype=torch.float64, device=self.device) for _ in range(6)]
+        ht, hs = _scalar_or_tensor(hsm, self.device)
+        self._check(self.lib.mtn_sky_to_pix(C.byref(fe), n, _ptr(xyz), _ptr(vxyz), _ptr(ht), hs,
+                                           *[_ptr(t) for t in out], self._stream()), "mtn_sky_to_pix")
+        return tuple(out)
+
     # ------------------------------------------------------------------ multi-GPU routing
     @_on_device
     def route_count(self, px, sm_range, bounds):

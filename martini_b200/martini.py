@@ -53,25 +53,34 @@ class _BaseMartini:
             self.beam.init_kernel(self._datacube)
             self._datacube.add_pad(self.beam.needs_pad())
 
-        self.source._init_skycoords()
-        self.source._init_pixcoords(self._datacube)  # after datacube is padded
-        self._init_device_particles()
+        # coordinates: one fused kernel on the device where the source offers it (SPHSource:
+        # mtn_sky_to_pix), the host mirror of the reference's steps otherwise
+        front = getattr(self.source, "_init_on_device", None)
+        dev_coords = front(self.engine, self._datacube) if front is not None else None  # after datacube is padded
+        if dev_coords is None:
+            self.source._init_skycoords()
+            self.source._init_pixcoords(self._datacube)
+        self._init_device_particles(dev_coords)
         self._prune_particles(**(_prune_kwargs or {}))
 
     # ------------------------------------------------------------------ device state
-    def _init_device_particles(self):
-        """Upload the seam arrays and run K0 (sph_kernels.py:235-262, 1241-1274).  Everything the
-        projection needs stays on the device from here on."""
+    def _init_device_particles(self, dev_coords=None):
+        """Upload the seam arrays (or take them from the device front-end) and run K0
+        (sph_kernels.py:235-262, 1241-1274).  Everything the projection needs stays on the device
+        from here on."""
         eng, src = self.engine, self.source
         scalar_or_dev = lambda x: eng.to_device(x) if np.ndim(x) > 0 else float(x)  # noqa: E731
-        self._dev = {
-            "px": eng.to_device(src.pixcoords[0]), "py": eng.to_device(src.pixcoords[1]),
-            "pz": eng.to_device(src.pixcoords[2]),
-            "sm_length": eng.to_device(src.sm_lengths_px(self._datacube)),
-            "v": eng.to_device(src.radial_velocity),
-            "D": scalar_or_dev(src.distance_p), "mHI": scalar_or_dev(src.mHI_g),
-            "sigma": scalar_or_dev(self.spectral_model.half_width(src)),
-        }
+        if dev_coords is not None:
+            self._dev = dict(dev_coords)
+        else:
+            self._dev = {
+                "px": eng.to_device(src.pixcoords[0]), "py": eng.to_device(src.pixcoords[1]),
+                "pz": eng.to_device(src.pixcoords[2]),
+                "sm_length": eng.to_device(src.sm_lengths_px(self._datacube)),
+                "v": eng.to_device(src.radial_velocity), "D": scalar_or_dev(src.distance_p),
+            }
+        self._dev["mHI"] = scalar_or_dev(src.mHI_g)
+        self._dev["sigma"] = scalar_or_dev(self.spectral_model.half_width(src))
         kid, valid, sm_range, h_eff = eng.smoothing_setup(self._dev["sm_length"], self._table)
         self._dev.update(kernel_id=kid, valid=valid, sm_range=sm_range, h_eff=h_eff)
         # host copies of the kernel state are fetched when somebody reads them (sph_kernels.py)
@@ -294,6 +303,8 @@ class GlobalProfile(_BaseMartini):
 
 class _AtOrigin:
     """Wrap a source so that every particle sits at pixel (0, 0) (martini.py:1541-1549)."""
+
+    _init_on_device = None  # (host front-end: the pixel coordinates are overwritten below)
 
     def __init__(self, source):
         self._s = source

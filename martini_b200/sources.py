@@ -69,7 +69,10 @@ def _lazy(name):
     def get(self):
         if self.__dict__.get("_pending_mask") is not None:
             self._flush_mask()
-        return self.__dict__.get(key)
+        value = self.__dict__.get(key)
+        if callable(value):  # a host mirror of a device array, fetched on first access
+            value = self.__dict__[key] = value()
+        return value
 
     def set(self, value):
         if self.__dict__.get("_pending_mask") is not None:
@@ -184,8 +187,48 @@ class SPHSource:
         px, py, pz = datacube.world2pix(self.skycoords["ra"], self.skycoords["dec"], self.radial_velocity)
         self.pixcoords = np.vstack((px, py, pz))
 
+    def _init_on_device(self, engine, datacube):
+        """The coordinate front-end on the GPU (``mtn_sky_to_pix``: what ``_init_skycoords`` +
+        ``_init_pixcoords`` + ``sm_lengths_px`` compute on the host, fused into one pass over the
+        particles).  Returns the device tensors the projection reads; the host attributes
+        (``pixcoords``, ``radial_velocity``, ``distance_p``, ``skycoords``) are fetched from them
+        when somebody reads them."""
+        from . import _lib as L
+
+        a0, d0 = np.deg2rad(self.ra), np.deg2rad(self.dec)
+        fe = L.MtnFrontEnd()
+        R = _rot("z", a0).dot(_rot("y", -d0))
+        fe.rotation[:] = list(R.ravel())
+        fe.direction[:] = [np.cos(d0) * np.cos(a0), np.cos(d0) * np.sin(a0), np.sin(d0)]
+        fe.distance_mpc, fe.vpeculiar, fe.hubble = self.distance, self.vpeculiar, self.h * 100.0
+        fe.ra0_rad, fe.dec0_rad = np.deg2rad(datacube.ra), np.deg2rad(datacube.dec)
+        fe.px_size_arcsec = datacube.px_size
+        fe.crpix[:] = [datacube.n_px_x / 2.0 + 0.5 + datacube.padx, datacube.n_px_y / 2.0 + 0.5 + datacube.pady,
+                       datacube.n_channels / 2.0 + 0.5]
+        fe.spectral_centre, fe.channel_width = datacube.spectral_centre, datacube.channel_width
+        fe.freq_mode = int(datacube._freq_channel_mode)
+        hsm = self.hsm_g if self.hsm_g is not None else 0.0
+        px, py, pz, v, D, sm = engine.sky_to_pix(fe, engine.to_device(self.xyz_g), engine.to_device(self.vxyz_g),
+                                                 engine.to_device(hsm) if np.ndim(hsm) > 0 else float(hsm))
+        host = lambda t: t.cpu().numpy()  # noqa: E731
+        self.__dict__["_lz_pixcoords"] = lambda: np.vstack((host(px), host(py), host(pz)))
+        self.__dict__["_lz_radial_velocity"] = lambda: host(v)
+        self.__dict__["_lz_distance_p"] = lambda: host(D)
+        self.__dict__["_lz_skycoords"] = self._skycoords_from_host
+        self.__dict__["_lz__sm_lengths"] = lambda: host(sm)
+        return {"px": px, "py": py, "pz": pz, "v": v, "D": D, "sm_length": sm}
+
+    def _skycoords_from_host(self):
+        a0, d0 = np.deg2rad(self.ra), np.deg2rad(self.dec)
+        unit = np.array([np.cos(d0) * np.cos(a0), np.cos(d0) * np.sin(a0), np.sin(d0)])
+        xyz = self.xyz_g.dot(_rot("z", a0).dot(_rot("y", -d0)).T) + unit * (self.distance * 1.0e3)
+        r = np.sqrt(np.sum(xyz * xyz, axis=1))
+        return {"ra": np.rad2deg(np.arctan2(xyz[:, 1], xyz[:, 0])), "dec": np.rad2deg(np.arcsin(xyz[:, 2] / r))}
+
     def sm_lengths_px(self, datacube):
         """Smoothing lengths in pixels: arctan(hsm / D) / px_size (sph_kernels.py:250-253)."""
+        if self.__dict__.get("_lz__sm_lengths") is not None:  # computed by the device front-end
+            return self._sm_lengths
         hsm = np.broadcast_to(self.hsm_g, (self.npart,)) if self.hsm_g is not None else np.zeros(self.npart)
         # kpc / Mpc -> dimensionless, radians -> pixels: the operation order astropy's unit
         # converters give the reference (pinned by tests/golden/seam.npz)
@@ -237,6 +280,8 @@ class SPHSource:
             raise ValueError("Mask must have same length as particle arrays.")
         if mask.sum() == 0:
             raise RuntimeError("No non-zero mHI source particles in target region.")
+        for name in ("skycoords", "pixcoords", "radial_velocity", "distance_p", "_sm_lengths"):
+            getattr(self, name, None)  # host mirrors of device arrays are fetched before anything is compacted
         self.npart = int(mask.sum())
         if self.T_g is not None and self.T_g.ndim > 0:
             self.T_g = self.T_g[mask]
@@ -252,6 +297,8 @@ class SPHSource:
             self.pixcoords = self.pixcoords[:, mask]
         if self.hsm_g is not None and self.hsm_g.ndim > 0:
             self.hsm_g = self.hsm_g[mask]
+        if type(self) is SPHSource and self._sm_lengths is not None:
+            self._sm_lengths = self._sm_lengths[mask]
 
 
 class PixelSource(SPHSource):
@@ -290,6 +337,8 @@ class PixelSource(SPHSource):
         if "_distance" not in self.__dict__:
             self._distance = float(np.mean(self.__dict__.pop("_D0")))
         return self._distance
+
+    _init_on_device = None  # (already at the seam: nothing to transform)
 
     def _init_skycoords(self):
         pass

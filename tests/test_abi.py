@@ -45,7 +45,8 @@ def test_struct_layouts_match_header(tmp_path):
     import subprocess
 
     structs = {"MtnKernelEntry": L.MtnKernelEntry, "MtnKernelTable": L.MtnKernelTable,
-               "MtnParticles": L.MtnParticles, "MtnCube": L.MtnCube, "MtnPlan": L.MtnPlan}
+               "MtnParticles": L.MtnParticles, "MtnCube": L.MtnCube, "MtnPlan": L.MtnPlan,
+               "MtnFrontEnd": L.MtnFrontEnd}
     if shutil.which("gcc") is None:
         pytest.skip("no gcc")
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "martini_b200.h"', "int main(void) {"]

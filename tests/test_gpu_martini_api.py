@@ -118,6 +118,62 @@ def test_mass_accuracy_frequency_channels(kernel, hsm, spectrum):
     assert mf.datacube._freq_channel_mode and np.allclose(mf.datacube.channel_edges, dc.channel_edges)
 
 
+def _engine_for_tests():
+    import martini_b200.martini as M
+
+    return M.Engine("cuda:0")  # (the emulated twin of this module swaps M.Engine)
+
+
+def test_device_front_end_kat():
+    """SURVEY row f1 on the device (mtn_sky_to_pix): the reference's pixel-coordinate KAT
+    (tests/test_sources.py:335-380: 6 particles, 1 kpc = 1 arcsec, h = 0)."""
+    distance = 1.0e-3 / np.deg2rad(1.0 / 3600.0)
+    lin = np.linspace(-2.5, 2.5, 6)
+    source = SPHSource(distance=distance, h=0.0, T_g=np.ones(6) * 1e4, mHI_g=np.ones(6) * 1e4,
+                       xyz_g=np.vstack((np.zeros(6), lin, lin)).T,
+                       vxyz_g=np.vstack((lin, np.zeros(6), np.zeros(6))).T, hsm_g=np.ones(6))
+    dc = DataCube(n_px_x=6, n_px_y=6, n_channels=6, px_size=1.0, channel_width=1.0)
+    dev = source._init_on_device(_engine_for_tests(), dc)
+    expected = np.vstack((np.arange(6)[::-1], np.arange(6), np.arange(6)[::-1]))
+    got = np.vstack([dev[k].cpu().numpy() for k in ("px", "py", "pz")])
+    assert np.allclose(got, expected, atol=1e-4)
+    assert np.allclose(source.pixcoords, expected, atol=1e-4)  # the lazily fetched host mirror
+    assert np.allclose(dev["sm_length"].cpu().numpy(), 1.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("freq", (False, True))
+@pytest.mark.parametrize("ra,dec", ((0.0, 0.0), (148.3, -31.7), (271.0, 64.2)))
+def test_device_front_end_matches_host_mirror(ra, dec, freq):
+    """mtn_sky_to_pix against the host numpy restatement of sph_source.py:265-362 +
+    sph_kernels.py:250-253 on a random source: rotation, translation, peculiar velocity, Hubble
+    flow, TAN projection with pad, both channel modes; 1e-9 pixel / 1e-12 relative."""
+    from martini_b200.datacube import C_KMS, HI_FREQ_HZ
+
+    rng = np.random.Generator(np.random.PCG64(17))
+    n = 5000
+    kw = dict(distance=12.5, vpeculiar=83.0, ra=ra, dec=dec, h=0.7, mHI_g=np.ones(n),
+              xyz_g=rng.normal(0, 12.0, (n, 3)), vxyz_g=rng.normal(0, 150.0, (n, 3)),
+              hsm_g=rng.lognormal(0.0, 0.7, n), L_coords=None)
+    host, devs = SPHSource(**kw), SPHSource(**kw)
+    ch = dict(channel_width=HI_FREQ_HZ * 5.0 / C_KMS, channel_unit="Hz") if freq else dict(channel_width=5.0)
+
+    def cube():
+        dc = DataCube(n_px_x=64, n_px_y=48, n_channels=40, px_size=6.0, spectral_centre=host.vsys,
+                      ra=ra + 0.01, dec=dec - 0.005, **ch)
+        dc.add_pad((7, 5))
+        return dc
+
+    host._init_skycoords()
+    host._init_pixcoords(cube())
+    dev = devs._init_on_device(_engine_for_tests(), cube())
+    for k, want in (("px", host.pixcoords[0]), ("py", host.pixcoords[1]), ("pz", host.pixcoords[2])):
+        assert np.abs(dev[k].cpu().numpy() - want).max() < 1e-9, k
+    assert np.allclose(dev["v"].cpu().numpy(), host.radial_velocity, rtol=1e-12, atol=1e-10)
+    assert np.allclose(dev["D"].cpu().numpy(), host.distance_p, rtol=1e-13)
+    assert np.allclose(dev["sm_length"].cpu().numpy(), host.sm_lengths_px(cube()), rtol=1e-12)
+    assert np.allclose(devs.distance_p, host.distance_p, rtol=1e-13) and devs.pixcoords.shape == (3, n)
+
+
 def test_kernel_validation_raises_unless_skipped():
     """reference test_sph_kernels.py:209-278: 'use this with care'."""
     def build():
