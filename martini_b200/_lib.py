@@ -28,6 +28,7 @@ SPECTRUM_GAUSSIAN = 0
 SPECTRUM_DIRACDELTA = 1
 PRUNE_SPATIAL, PRUNE_SPECTRAL, PRUNE_MASS = 1, 2, 4
 CUBE_ACCUMULATE, CUBE_ZEROED = 0, 1
+ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_LIMIT = -1, -2, -3, -4
 
 
 class MartiniB200Error(RuntimeError):

@@ -43,6 +43,19 @@ class KernelTable:
         return t
 
 
+class MergedPlan:
+    """The plans of the x-sub-slabs an insertion was split into, summed (``n_kept`` counts a
+    particle once per sub-slab it reaches)."""
+
+    def __init__(self, parts):
+        self.parts = parts
+        for k in ("n_kept", "n_pairs", "n_pairs2", "updates_dense", "workspace_bytes"):
+            setattr(self, k, sum(getattr(p, k) for p in parts))
+        self.route2 = parts[0].route2
+        self.n_bricks = sum(p.n_bricks for p in parts)
+        self.edges_increasing = parts[0].edges_increasing
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -181,15 +194,42 @@ class Engine:
         return accept, count
 
     # ------------------------------------------------------------------ plan + project
+    #: test hook: treat a slab with more (particle, key) pairs than this like one that exceeds the
+    #: library's 32-bit pair index, i.e. split it (None: only the library's own limit)
+    pair_limit = None
+
+    def insert(self, *, cube, x_lo=0, x_hi=None, nx_full=None, **kw):
+        """Project particles into ``cube`` (rows [x_lo, x_hi) of the full cube); see
+        :meth:`_insert_slab`.  A slab whose sorted pair list would exceed the 32-bit index of the
+        radix sort (2^32 - 1 pairs per stream: wide footprints on a big cube) is cut into
+        x-sub-slabs, each planned and projected on its own -- every sub-slab writes only its own
+        rows, halo particles are simply planned for both, so the result is the unsplit one."""
+        if x_hi is None:
+            x_hi = x_lo + cube.shape[0]
+        nx_full = int(nx_full if nx_full is not None else x_hi)
+        plan = self._insert_slab(cube=cube, x_lo=x_lo, x_hi=x_hi, nx_full=nx_full, **kw)
+        if plan is not None:
+            return plan
+        rows = x_hi - x_lo
+        if rows <= 8:
+            raise L.MartiniB200Error("insert: a slab of 8 rows still exceeds the 32-bit pair index")
+        mid = x_lo + max(8, (rows // 2 + 7) // 8 * 8)  # cuts stay on brick boundaries
+        parts = [self.insert(cube=cube[a - x_lo:b - x_lo], x_lo=a, x_hi=b, nx_full=nx_full, **kw)
+                 for a, b in ((x_lo, mid), (mid, x_hi))]
+        merged = MergedPlan(parts)
+        self.last_plan = merged
+        return merged
+
     @_on_device
-    def insert(self, *, px, py, h_eff, sm_range, v, kernel_id=None, sigma=None, mHI=None, D=None,
+    def _insert_slab(self, *, px, py, h_eff, sm_range, v, kernel_id=None, sigma=None, mHI=None, D=None,
                accept=None, table: KernelTable, spectrum: int, edges: torch.Tensor,
                cube: torch.Tensor, px_size_arcsec: float, x_lo: int = 0, x_hi: int | None = None,
                nx_full: int | None = None, zeroed: bool = False, edges_increasing: bool | None = None):
         """Project particles into ``cube`` (a (x_hi-x_lo, ny, C) float64 device tensor holding
         rows [x_lo, x_hi) of the full cube), in place:  cube = (cube + inserted) / px_size^2.
 
-        Returns the ``MtnPlan`` (n_kept, n_pairs, updates_dense, ...).
+        Returns the ``MtnPlan`` (n_kept, n_pairs, updates_dense, ...), or None if the slab has
+        more pairs than the sort can index (``insert`` then splits it).
         """
         assert cube.is_contiguous() and cube.dtype == torch.float64 and cube.ndim == 3
         n = px.numel()
@@ -225,8 +265,13 @@ class Engine:
         sbytes = self.lib.mtn_plan_scratch_bytes(n, C.byref(c))
         scratch = self._grow("_scratch", sbytes)
         plan = L.MtnPlan()
-        self._check(self.lib.mtn_plan(C.byref(p), C.byref(tc), C.byref(c), _ptr(scratch), scratch.numel(),
-                                  C.byref(plan), stream), "mtn_plan")
+        rc = self.lib.mtn_plan(C.byref(p), C.byref(tc), C.byref(c), _ptr(scratch), scratch.numel(),
+                               C.byref(plan), stream)
+        too_many = rc == L.ERR_LIMIT and b"pairs exceed" in self.lib.mtn_last_error()
+        if too_many or (rc == 0 and self.pair_limit is not None and max(plan.n_pairs, plan.n_pairs2) > self.pair_limit
+                        and c.x_hi - c.x_lo > 8):
+            return None  # the caller splits the slab
+        self._check(rc, "mtn_plan")
         ws = self._grow("_workspace", plan.workspace_bytes)
         self._check(self.lib.mtn_project(C.byref(p), C.byref(tc), C.byref(c), C.byref(plan),
                                      _ptr(scratch), scratch.numel(), _ptr(ws), ws.numel(), stream),

@@ -236,3 +236,25 @@ def test_route_kernels_fill_inboxes_in_global_order(eng):
         assert np.array_equal(got[0], px[want]) and np.array_equal(got[1], fields[1][want])
         assert np.all(inbox[d][:, n_d:].numpy() == -1.0)            # nothing written past the end
     assert 5 in np.flatnonzero(np.isinf(r)) and all(5.0 in inbox[d][2].numpy() for d in range(world))
+
+
+@pytest.mark.parametrize("name", ("cfg2_small", "cfg4_wide_dirac", "cfg3_thermal"))
+def test_slab_is_split_when_the_pair_index_would_overflow(name):
+    """Engine.insert cuts a slab whose pair list exceeds the sort's 32-bit index into x-sub-slabs
+    (here: the test hook Engine.pair_limit forces it at a few hundred pairs); the cube is the
+    unsplit one up to the association of partial sums, U_dense adds up exactly."""
+    from tests.emu import EmuEngine
+
+    case = CASES[name]
+    want = run_hot_path(EmuEngine(), case)
+    eng = EmuEngine()
+    eng.pair_limit = max(want["plan"].n_pairs, want["plan"].n_pairs2) // 5
+    got = run_hot_path(eng, case)
+    assert len(got["plan"].parts) >= 2 and got["plan"].updates_dense == want["plan"].updates_dense
+    G.assert_same_cube(got["cube"], want["cube"])
+    # accumulate mode: every sub-slab converts only its own rows
+    rng = np.random.Generator(np.random.PCG64(3))
+    cube0 = rng.normal(0.0, 1e-6, case["shape"])
+    a = run_hot_path(eng, case, cube=eng.to_device(cube0.copy()))["cube"]
+    b = run_hot_path(EmuEngine(), case, cube=eng.to_device(cube0.copy()))["cube"]
+    G.assert_same_cube(a, b)
