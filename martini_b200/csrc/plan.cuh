@@ -340,7 +340,12 @@ __device__ __forceinline__ int64_t count_pairs(const Foot& f, const Geo& g) {
   if (f.route == ROUTE_COLUMN) return f.c1 / CSB - f.c0 / CSB + 1;
   int tx0, tx1, ty0, ty1;
   tile_range(f, g, tx0, tx1, ty0, ty1);
-  if (f.route == ROUTE_SPLAT) return (int64_t)(tx1 - tx0 + 1) * (ty1 - ty0 + 1) * (f.c1 - f.c0 + 1);
+  if (f.route == ROUTE_SPLAT) {
+    int64_t tiles = 0;
+    for (int tx = tx0; tx <= tx1; ++tx)
+      for (int ty = ty0; ty <= ty1; ++ty) tiles += tile_reached(f, g, tx, ty) ? 1 : 0;
+    return tiles * (f.c1 - f.c0 + 1);
+  }
   int64_t n = 0;
   for (int tx = tx0; tx <= tx1; ++tx)
     for (int ty = ty0; ty <= ty1; ++ty) {
@@ -445,12 +450,12 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
   for (int tx = tx0; tx <= tx1; ++tx)
     for (int ty = ty0; ty <= ty1; ++ty) {
       const int tile = tx * g.nty + ty;
+      if (!tile_reached(f, g, tx, ty)) continue;  // (all pixels outside the kernel's support)
       if (f.route == ROUTE_SPLAT) {
         for (int c = f.c0; c <= f.c1; ++c)
           pairs2_out[off2++] = ((uint64_t)(uint32_t)((int64_t)tile * g.C + c) << 32) | (uint64_t)(uint32_t)ridx;
         continue;
       }
-      if (!tile_reached(f, g, tx, ty)) continue;
       int k0, k1;
       block_range(f, g.phase[tile], k0, k1);
       for (int k = k0; k <= k1; ++k) {
