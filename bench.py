@@ -632,16 +632,16 @@ def measure_strong(eng, name, args, timer, world, rank, local, case=None, dev=No
         if float(ok) == 0.0:
             router = None
 
-    def routed_inputs():
+    def routed_inputs(inbox_free=False):
         _, _, sm_range, _ = eng.smoothing_setup(dev["sm_length"], ctx.table)
         if router is not None:
-            return router.route(eng, dev, sm_range, bounds)
+            return router.route(eng, dev, sm_range, bounds, inbox_free=inbox_free)
         return mdist.route_particles(dev, sm_range, bounds)
 
     def step():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        mine = routed_inputs()
+        mine = routed_inputs(inbox_free=peer is not None)  # (the last step ended with PeerCube.end's barrier)
         e1.record()
         if peer is not None:
             peer.begin()

@@ -129,8 +129,11 @@ class PeerCube:
         self.rows.zero_()
 
     def end(self):
-        torch.cuda.current_stream().synchronize()
-        dist.barrier(group=self.group)
+        try:  # device-side barrier on the signal pads of the symmetric allocation (stream-ordered)
+            self.hdl.barrier(channel=0)
+        except Exception:  # noqa: BLE001 -- older handle API
+            torch.cuda.current_stream().synchronize()
+            dist.barrier(group=self.group)
         return self.buf if self.rank == self.dst else None
 
 
@@ -290,10 +293,18 @@ class PeerRouter:
         self.ptrs = [t.data_ptr() for t in self._peers]
 
     def _barrier(self):
-        torch.cuda.current_stream().synchronize()
-        dist.barrier(group=self.group)
+        """All ranks' work enqueued so far is complete.  Device-side (symmetric-memory signal
+        pads, stream-ordered) where the handle offers it; NCCL barrier after a stream sync
+        otherwise."""
+        try:
+            self.hdl.barrier(channel=0)
+        except Exception:  # noqa: BLE001 -- older handle API
+            torch.cuda.current_stream().synchronize()
+            dist.barrier(group=self.group)
 
-    def route(self, engine, dev, sm_range, bounds):
+    def route(self, engine, dev, sm_range, bounds, inbox_free=False):
+        """``inbox_free``: the caller guarantees that every rank has finished reading its inbox
+        of the previous step (e.g. a barrier closed that step): saves one barrier."""
         keys = [k for k in ROUTED_KEYS if isinstance(dev.get(k), torch.Tensor)]
         assert len(keys) <= self.n_fields
         out = {k: v for k, v in dev.items() if k not in keys}
@@ -301,12 +312,13 @@ class PeerRouter:
         counts = torch.empty((self.world, self.world), dtype=torch.int64, device=totals.device)  # [src][dst]
         dist.all_gather_into_tensor(counts, totals, group=self.group)
         src_offsets = counts[:self.rank].sum(dim=0)
-        arriving = counts.sum(dim=0)
-        n_recv = int(arriving[self.rank])            # the one read-back; also orders the host after the gather
-        if int(arriving.max()) > self.capacity:      # (same verdict on every rank)
-            raise RuntimeError(f"PeerRouter: {int(arriving.max())} particles for one rank exceed the inbox "
+        arriving = counts.sum(dim=0).tolist()        # the one read-back (also orders the host after the gather)
+        n_recv = arriving[self.rank]
+        if max(arriving) > self.capacity:            # (same verdict on every rank)
+            raise RuntimeError(f"PeerRouter: {max(arriving)} particles for one rank exceed the inbox "
                                f"capacity {self.capacity}")
-        self._barrier()                              # every rank is done reading its inbox of the last step
+        if not inbox_free:
+            self._barrier()                          # every rank is done reading its inbox of the last step
         engine.route_scatter(dev["px"], sm_range, bounds, [dev[k] for k in keys], self.ptrs, self.capacity,
                              src_offsets, scratch)
         self._barrier()                              # all stores have landed
