@@ -109,10 +109,11 @@ class PeerCube:
     bytes per warp) -- the access pattern NVLink peer stores like.  Use with MTN_CUBE_ZEROED
     only (accumulate mode would read the cube back over the link).
 
-    Per insertion: ``begin()`` (every rank zeroes ITS OWN rows of the destination through the
-    peer mapping -- same stream as the projection that follows, so nothing can overtake it, and
-    no rank touches another rank's rows), the ranks project, ``end()`` (one barrier: all stores
-    have landed).  The previous insertion's ``end()`` is what makes the next ``begin()`` safe."""
+    Per insertion: ``begin()`` (the destination rank zeroes its cube locally -- 0.1 ms for
+    537 MB at HBM rate; every rank zeroing its own rows through the peer mapping instead puts
+    the whole cube through the destination's NVLink ingress, 0.6 ms at 8 ranks -- then a
+    device-side barrier on the allocation's signal pads so no store can overtake the memset),
+    the ranks project, ``end()`` (barrier: all stores have landed)."""
 
     def __init__(self, shape, bounds, device, dst=0, group=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -125,15 +126,20 @@ class PeerCube:
         lo, hi = bounds[self.rank], bounds[self.rank + 1]
         self.rows = self.hdl.get_buffer(dst, (hi - lo, ny, nc), torch.float64, storage_offset=lo * ny * nc)
 
-    def begin(self):
-        self.rows.zero_()
-
-    def end(self):
+    def _barrier(self):
         try:  # device-side barrier on the signal pads of the symmetric allocation (stream-ordered)
             self.hdl.barrier(channel=0)
         except Exception:  # noqa: BLE001 -- older handle API
             torch.cuda.current_stream().synchronize()
             dist.barrier(group=self.group)
+
+    def begin(self):
+        if self.rank == self.dst:
+            self.buf.zero_()
+        self._barrier()
+
+    def end(self):
+        self._barrier()
         return self.buf if self.rank == self.dst else None
 
 
