@@ -46,18 +46,15 @@ static_assert(ERF_DEG % 2 == 1, "rows are read as pairs of coefficients");
 constexpr int ERF_NCOEF = ERF_DEG + 1;  // 10 doubles = 80 B per interval (16-B aligned rows)
 constexpr int ERF_NINT = 6 * ERF_INV_W + 1;
 // The compact erf table of the column / splat kernels, which keep it in shared memory and are
-// bound by the shared-memory data pipe: every lane reads its own row, and rows a non-integer
-// distance apart land in pseudo-random bank groups (ncu, source page: 2.35 x the ideal
-// wavefronts on the table loads -- no layout fixes that), so the lever is bytes per row.
-// 1/128-wide intervals, degree 3: 32-byte rows, two 16-byte loads per evaluation (the brick
-// kernel's table: five).  Truncation (1/256)^4 max|d4 erf| / 24 < 5e-11 absolute -- against
-// a tolerance of 1e-6 x cube peak per voxel; the total flux does not see it at all, because
-// adjacent channels share their edge value and the sum over a line telescopes to the two
-// saturated ends.
-constexpr int ERFC_INV_W = 128;
-constexpr int ERFC_DEG = 3;
+// bound by the shared-memory data pipe (every lane reads its own row): 1/64-wide intervals,
+// degree 5 -- 48-byte rows, three 16-byte loads per evaluation instead of five; truncation
+// (1/128)^6 |erf^(6)| / 720 < 2e-14, five orders below what the 1e-9 flux tolerance needs.
+constexpr int ERFC_INV_W = 64;
+constexpr int ERFC_DEG = 5;
 constexpr int ERFC_NCOEF = ERFC_DEG + 1;
 constexpr int ERFC_NINT = 6 * ERFC_INV_W + 1;
+// (rows are plain 48-byte records; a 16-byte skew every eight rows, which makes even row
+// distances between lanes conflict-free, was measured and changed nothing: 2.41 against 2.35 ms)
 __host__ __device__ constexpr int erfc_row_offset(int r) { return ERFC_NCOEF * r; }
 constexpr int ERFC_DOUBLES = ERFC_NCOEF * ERFC_NINT;
 // One staged particle record: 80 bytes (common.cuh: Record), 16-B aligned so a single

@@ -33,8 +33,10 @@ __device__ __forceinline__ double erf_tab_compact(const double* __restrict__ tab
   const int i = (int)(a * ERFC_INV_W);  // a = ERF_SAT lands in the last (saturated) interval
   const double u = a - ((double)i + 0.5) * (1.0 / ERFC_INV_W);
   const double2* row = reinterpret_cast<const double2*>(table + erfc_row_offset(i));
-  const double2 c23 = row[1], c01 = row[0];
-  double r = fma(c23.y, u, c23.x);
+  const double2 c45 = row[2], c23 = row[1], c01 = row[0];
+  double r = fma(c45.y, u, c45.x);
+  r = fma(r, u, c23.y);
+  r = fma(r, u, c23.x);
   r = fma(r, u, c01.y);
   r = fma(r, u, c01.x);
   r = fmin(r, 1.0);
