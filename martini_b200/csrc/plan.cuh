@@ -151,31 +151,46 @@ __device__ __forceinline__ bool pixel_bounds(double p, double r, int lim_lo, int
 // Live channel window.  g(e) = sgn * (edges[e] - v) * inv_s is non-decreasing in e;
 // channel c can be non-zero only if g(c+1) > -T and g(c) < T (T = ERF_SAT for the Gaussian
 // line, closed at 0 for the Dirac line).  Returns false if no channel is live.
+// Smallest e in [0, C + 1) with pred(e) (pred is monotone: false ... false true ... true);
+// C + 1 if there is none.  `guess` is where a uniform channel grid puts the answer: two probes
+// around it bracket the answer to five candidates (on a uniform grid always), otherwise the
+// search falls back to plain bisection of what is left -- the result never depends on the guess.
+template <typename Pred>
+__device__ __forceinline__ int first_true(Pred pred, int C, int guess) {
+  int lo = 0, hi = C + 1;
+  const int a = min(max(guess - 2, 0), C), b = min(a + 4, C);
+  if (a > 0) {
+    if (pred(a - 1)) hi = a - 1; else lo = a;
+  }
+  if (lo == a) {
+    if (pred(b)) hi = b; else lo = b + 1;
+  }
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (pred(mid)) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
 __device__ __forceinline__ bool channel_window(const double* __restrict__ edges, int C, int sgn,
                                                int spectrum, double v, double inv_s, int& c0,
                                                int& c1) {
   const bool dirac = spectrum == MTN_SPECTRUM_DIRACDELTA;
   const double scale = dirac ? (double)sgn : (double)sgn * inv_s;
   auto g = [&](int e) { return (__ldg(edges + e) - v) * scale; };
+  // where a uniform grid has g(e) = x:  e = (x / scale + v - edges[0]) / mean channel width
+  const double e0 = __ldg(edges), inv_step = (double)C / (__ldg(edges + C) - e0);
+  const double half = dirac ? 0.0 : ERF_SAT / scale;  // (signed: scale carries the direction)
+  auto guess = [&](double x_over_scale) {
+    const double e = (x_over_scale + v - e0) * inv_step;
+    return (int)fmin(fmax(e, -1.0), (double)C + 1.0);  // (NaN -> 0 on the device: any guess is fine)
+  };
   // first edge e in [0, C] with g(e) > -T (>= 0 for dirac)
-  int lo = 0, hi = C + 1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    const double x = g(mid);
-    const bool t = dirac ? (x >= 0.0) : (x > -ERF_SAT);
-    if (t) hi = mid; else lo = mid + 1;
-  }
-  const int e_first = lo;  // C+1 if none
+  const int e_first = first_true([&](int e) { const double x = g(e); return dirac ? (x >= 0.0) : (x > -ERF_SAT); },
+                                 C, guess(-half));  // C+1 if none
   // last edge e in [0, C] with g(e) < T (<= 0 for dirac): first e failing, minus one
-  lo = 0;
-  hi = C + 1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    const double x = g(mid);
-    const bool t = dirac ? (x <= 0.0) : (x < ERF_SAT);
-    if (t) lo = mid + 1; else hi = mid;
-  }
-  const int e_last = lo - 1;  // -1 if none
+  const int e_last = first_true([&](int e) { const double x = g(e); return !(dirac ? (x <= 0.0) : (x < ERF_SAT)); },
+                                C, guess(half) + 1) - 1;  // -1 if none
   if (e_first > C || e_last < 0) return false;
   c0 = max(e_first - 1, 0);
   c1 = min(e_last, C - 1);
@@ -362,7 +377,6 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(
     PlanIn in, Geo g, int64_t* __restrict__ blk_kept, int64_t* __restrict__ blk_pairs,
     int64_t* __restrict__ blk_pairs2, unsigned long long* __restrict__ updates,
     PackedFoot* __restrict__ feet) {
-  __shared__ int64_t sm[33];
   const int64_t i = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
   int64_t kept = 0, pairs = 0, pairs2 = 0, upd = 0;
   if (i < in.n) {
@@ -375,16 +389,24 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(
       (f.route == ROUTE_BRICK ? pairs : pairs2) = count_pairs(f, g);
     }
   }
-  int64_t tk, tp, tq, tu;
-  block_excl_scan(kept, sm, &tk);
-  block_excl_scan(pairs, sm, &tp);
-  block_excl_scan(pairs2, sm, &tq);
-  block_excl_scan(upd, sm, &tu);
+  // block totals: warp reductions, one shared-memory atomic per warp and quantity, one barrier
+  // (four block-wide scans cost twelve barriers and were a third of this kernel)
+  __shared__ unsigned long long tot[4];
+  if (threadIdx.x < 4) tot[threadIdx.x] = 0ull;
+  __syncthreads();
+  long long q[4] = {(long long)kept, (long long)pairs, (long long)pairs2, (long long)upd};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) q[k] += __shfl_down_sync(0xffffffffu, q[k], d);
+    if ((threadIdx.x & 31) == 0 && q[k]) atomicAdd(&tot[k], (unsigned long long)q[k]);
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    blk_kept[blockIdx.x] = tk;
-    blk_pairs[blockIdx.x] = tp;
-    blk_pairs2[blockIdx.x] = tq;
-    if (tu) atomicAdd(updates, (unsigned long long)tu);
+    blk_kept[blockIdx.x] = (int64_t)tot[0];
+    blk_pairs[blockIdx.x] = (int64_t)tot[1];
+    blk_pairs2[blockIdx.x] = (int64_t)tot[2];
+    if (tot[3]) atomicAdd(updates, tot[3]);
   }
 }
 
@@ -394,7 +416,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
     PlanIn in, Geo g, const int64_t* __restrict__ blk_kept, const int64_t* __restrict__ blk_pairs,
     const int64_t* __restrict__ blk_pairs2, const PackedFoot* __restrict__ feet,
     Record* __restrict__ records, uint64_t* __restrict__ pairs_out, uint64_t* __restrict__ pairs2_out) {
-  __shared__ int64_t sm[33];
+  __shared__ int64_t sm3[3][33];
   const int64_t i = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
   int64_t kept = 0, npair = 0, npair2 = 0;
   Foot f;
@@ -407,10 +429,11 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
       (f.route == ROUTE_BRICK ? npair : npair2) = count_pairs(f, g);
     }
   }
-  int64_t tk, tp;
-  const int64_t ridx = blk_kept[blockIdx.x] + block_excl_scan(kept, sm, &tk);
-  int64_t off = blk_pairs[blockIdx.x] + block_excl_scan(npair, sm, &tp);
-  int64_t off2 = blk_pairs2[blockIdx.x] + block_excl_scan(npair2, sm, &tp);
+  int64_t ex[3] = {kept, npair, npair2};
+  block_excl_scan3(ex, sm3);  // one pass, two barriers, for the three prefixes
+  const int64_t ridx = blk_kept[blockIdx.x] + ex[0];
+  int64_t off = blk_pairs[blockIdx.x] + ex[1];
+  int64_t off2 = blk_pairs2[blockIdx.x] + ex[2];
   if (!f.live) return;
   Record rec;
   rec.px = in.px[i];

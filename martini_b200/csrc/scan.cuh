@@ -47,6 +47,28 @@ __device__ __forceinline__ T block_excl_scan(T x, T* smem, T* total) {
   return res;
 }
 
+// Exclusive scans of three values per thread across the block in one pass (x[k] is replaced by
+// its exclusive prefix).  `smem` holds 3 x 33 values.  Two barriers.
+__device__ __forceinline__ void block_excl_scan3(int64_t x[3], int64_t (*smem)[33]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  int64_t incl[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    incl[k] = warp_incl_scan(x[k]);
+    if (lane == 31) smem[k][warp] = incl[k];
+  }
+  __syncthreads();
+  if (warp < 3) {  // warp k scans the warp totals of quantity k
+    const int64_t w = lane < nwarps ? smem[warp][lane] : 0;
+    const int64_t wi = warp_incl_scan(w);
+    smem[warp][lane] = wi - w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 3; ++k) x[k] = smem[k][warp] + incl[k] - x[k];
+}
+
 template <typename TIn, typename T>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums(const TIn* __restrict__ in,
                                                                 int64_t n, T* __restrict__ sums) {
