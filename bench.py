@@ -320,7 +320,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_sample_step"],
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args.workload, case, args.particles),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -806,7 +806,7 @@ def run_b200(args):
               "higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
     if world == 1:
         blk = measure_single(eng, args.workload, args, args.steps, args.warmup, timer, clocks_for=local)
-        line = dict(common, scaling="weak", **blk)
+        line = dict(common, scaling="strong", **blk)  # (N > 1 runs the same cube: strong scaling)
         line["gpu_launches"] = blk["gpu_launches_per_step"] * args.steps
         others = [w for w in args.others.split(",") if w and w != "none" and w != args.workload]
         if args.particles is None and others:
