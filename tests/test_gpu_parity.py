@@ -328,6 +328,21 @@ def test_slabs_concatenate(eng):
         assert_same_cube(torch.cat(parts, dim=0), full)
 
 
+def test_slab_is_split_at_the_pair_limit(eng):
+    """Engine.insert cuts a slab whose pair list would overflow the sort's 32-bit index into
+    x-sub-slabs; forced here through the Engine.pair_limit hook."""
+    for name in ("cfg2_small", "cfg4_wide_dirac"):
+        case = SMALL[name]
+        want = run_hot_path(eng, case)
+        try:
+            eng.pair_limit = max(want["plan"].n_pairs, want["plan"].n_pairs2) // 6
+            got = run_hot_path(eng, case)
+        finally:
+            eng.pair_limit = None
+        assert len(got["plan"].parts) >= 2 and got["plan"].updates_dense == want["plan"].updates_dense
+        assert_same_cube(got["cube"], want["cube"])
+
+
 def test_deterministic(eng):
     case = SMALL["cfg3_thermal"]
     a = run_hot_path(eng, case)["cube"]
@@ -454,7 +469,7 @@ def test_cfg4_wide_footprints_midsize(eng):
     case = synthetic.make_case("cfg4", n=100_000, nx=256, ny=256, nc=64)
     case["sm_length"] = case["sm_length"] * 2.0  # keep 8..40 px smoothing lengths at this cube size
     out = sampled_pixel_check(eng, case, 24, seed=404, bright_box=(64, 192))
-    assert out["plan"].route2 == 2 and out["plan"].n_pairs2 > 50 * out["plan"].n_kept  # splat stream
+    assert out["plan"].route2 == 2 and out["plan"].n_pairs2 > 20 * out["plan"].n_kept  # splat stream (tiles outside the round support are culled)
 
 
 def test_cfg3_full_size_columns_and_flux(eng):
