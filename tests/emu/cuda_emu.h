@@ -144,6 +144,16 @@ inline int __double2hiint(double d) {
   memcpy(&b, &d, 8);
   return (int)(b >> 32);
 }
+inline double __longlong_as_double(long long v) {
+  double d;
+  memcpy(&d, &v, 8);
+  return d;
+}
+inline long long __double_as_longlong(double d) {
+  long long v;
+  memcpy(&v, &d, 8);
+  return v;
+}
 inline double __hiloint2double(int hi, int lo) {
   const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
   double d;
