@@ -66,8 +66,8 @@ __device__ __forceinline__ bool next_item(const StreamArgs& a, int lane, Item& i
 
 // ------------------------------------------------------------------------------- column
 __host__ __device__ inline int column_acc_stride(int C) { return C >= CSB ? CSB : (C + 63) / 64 * 64; }
-inline size_t column_smem_bytes(int C) {  // accumulators + erf table + staged line parameters
-  return ((size_t)STREAM_WARPS * column_acc_stride(C) + ERFC_DOUBLES + STREAM_WARPS * 32 * 4) * sizeof(double);
+inline size_t column_smem_bytes(int C) {
+  return ((size_t)STREAM_WARPS * column_acc_stride(C) + ERFC_DOUBLES) * sizeof(double);
 }
 
 template <bool COUNT>
@@ -81,10 +81,6 @@ __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs
   const int acc_stride = column_acc_stride(g.C);
   double* acc = col_smem + warp * acc_stride;
   double* erf_table = col_smem + STREAM_WARPS * acc_stride;
-  // per-warp staging of a batch's line parameters {v, sgn / (sqrt2 sigma), amp, window}: two
-  // broadcast 16-byte loads per particle instead of seven shuffles (the shuffles share the
-  // data pipe that bounds this kernel)
-  double4* stage = reinterpret_cast<double4*>(erf_table + ERFC_DOUBLES) + warp * 32;
   const double sgn = g.edges_increasing ? 1.0 : -1.0;
   for (int c = lane; c < acc_stride; c += 32) acc[c] = 0.0;
   for (int k = threadIdx.x; k < ERFC_DOUBLES; k += STREAM_THREADS) erf_table[k] = g_erf_table_compact[k];
@@ -100,20 +96,20 @@ __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs
     int lo = CSB, hi = 0;  // touched range of the accumulator
     for (uint32_t base = it.begin; base < it.end; base += 32) {
       const int nb = (int)min(32u, it.end - base);
+      double v_l = 0.0, inv_l = 0.0, amp_l = 0.0;
+      uint32_t cw_l = 0;
       if (lane < nb) {
         const Record* r = a.records + (uint32_t)a.pairs[base + lane];
-        double4 q;
-        q.x = r->v;
-        q.y = sgn * r->inv_s;
-        q.z = r->amp;
-        q.w = __longlong_as_double((long long)((uint32_t)r->c_first | ((uint32_t)r->c_last << 16)));
-        stage[lane] = q;
+        v_l = r->v;
+        inv_l = r->inv_s;
+        amp_l = r->amp;
+        cw_l = (uint32_t)r->c_first | ((uint32_t)r->c_last << 16);
       }
-      __syncwarp();
       for (int k = 0; k < nb; ++k) {
-        const double4 q = stage[k];  // (warp-uniform: broadcast)
-        const double v = q.x, sc = q.y, amp = q.z;
-        const uint32_t cwk = (uint32_t)__double_as_longlong(q.w);
+        const double v = __shfl_sync(0xffffffffu, v_l, k);
+        const double sc = sgn * __shfl_sync(0xffffffffu, inv_l, k);
+        const double amp = __shfl_sync(0xffffffffu, amp_l, k);
+        const uint32_t cwk = __shfl_sync(0xffffffffu, cw_l, k);
         // the particle's live window (plan.cuh: channel_window, exact predicates) cut to the
         // superblock: channels [cs, ce)
         const int cs = max((int)(cwk & 0xffffu) - cbase, 0), ce = min((int)(cwk >> 16) + 1 - cbase, nchs);
@@ -168,7 +164,6 @@ __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs
           }
         }
       }
-      __syncwarp();  // the staged batch is free again
     }
     __syncwarp();
     // ---- flush the touched range, and clear it for the next item
