@@ -258,3 +258,39 @@ def test_slab_is_split_when_the_pair_index_would_overflow(name):
     a = run_hot_path(eng, case, cube=eng.to_device(cube0.copy()))["cube"]
     b = run_hot_path(EmuEngine(), case, cube=eng.to_device(cube0.copy()))["cube"]
     G.assert_same_cube(a, b)
+
+
+def test_streams_switch_keeps_everything_on_the_brick_kernel():
+    """MTN_STREAMS=0 (developer switch, read once per process): no column / splat kernel, every
+    particle goes through the brick kernel -- the cubes of both routings agree."""
+    import os
+    import pickle
+    import subprocess
+    import sys
+    import tempfile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import pickle, sys\n"
+        "from tests import test_emu_parity as T\n"
+        "from tests.emu import EmuEngine\n"
+        "from martini_b200.pipeline import run_hot_path\n"
+        "eng = EmuEngine()\n"
+        "out = {}\n"
+        "for name in ('cfg3_thermal', 'cfg4_wide_dirac', 'dirac_edges'):\n"
+        "    r = run_hot_path(eng, T.CASES[name])\n"
+        "    out[name] = (r['cube'].numpy(), r['plan'].route2, r['plan'].n_pairs2)\n"
+        "pickle.dump(out, open(sys.argv[1], 'wb'))\n"
+    )
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "out.pkl")
+        subprocess.run([sys.executable, "-c", code, path], check=True, cwd=root, timeout=600,
+                       env=dict(os.environ, MTN_STREAMS="0", PYTHONPATH=root))
+        off = pickle.load(open(path, "rb"))
+    eng = EmuEngine()
+    for name, (cube, route2, n2) in off.items():
+        assert route2 == 0 and n2 == 0
+        on = run_hot_path(eng, CASES[name])
+        assert on["plan"].route2 in (1, 2) and on["plan"].n_pairs2 > 0
+        ref = on["cube"].numpy()
+        assert np.abs(cube - ref).max() <= 1e-12 * np.abs(ref).max()
