@@ -1,10 +1,10 @@
 // The tile projection kernel and its small companions (work items, partial reduce).
 //
 // One CTA works on one brick -- TILE x TILE pixels x 64 channels -- at a time and keeps the
-// brick's sums in registers: warp w owns a 4 x 4 pixel sub-block, lane l owns channels
-// (2l, 2l+1) of the brick, i.e. 16 pixels x 2 channels = 32 float64 accumulators per thread.
-// With the default 8 x 8 tile a CTA is 4 warps and four CTAs share an SM, so one CTA's
-// barrier waits are covered by the others.  The particle records of the brick are gathered
+// brick's sums in registers: warp w owns a 4 x 4 pixel sub-block; lane l owns one pixel row of
+// it (l / 8) and eight adjacent channels (8 (l % 8) ...), i.e. a 4 pixel x 8 channel register
+// tile = 32 float64 accumulators per thread.  With the default 8 x 8 tile a CTA is 4 warps and
+// four CTAs share an SM, so one CTA's barrier waits are covered by the others.  The particle records of the brick are gathered
 // into shared memory with cp.async.bulk (one 80-byte bulk copy per record, completion on an
 // mbarrier, double buffered).  Per batch of 32 staged particles:
 //
@@ -16,15 +16,20 @@
 //   A      every (particle, box pixel) pair and every (particle, live edge) pair is handed to
 //          one thread through those prefix sums -- all lanes hold real work, two items per
 //          lane so two dependency chains are in flight -- which evaluates the SPH-kernel
-//          pixel integral (tabulated, tables.cuh) or the edge erf ONCE into shared memory;
+//          pixel integral (tabulated, tables.cuh; times the particle's amplitude) or the edge
+//          erf ONCE into shared memory; the edges outside a particle's live window are filled
+//          with the saturated values -1 / +1 they have in the reference, so that phase C needs
+//          no channel predicate;
 //   C      each warp builds, with one ballot, the list of particles that touch its sub-block
-//          and their pixel masks, then walks it: the lane forms its two spectrum values
-//          S = (E[c+1] - E[c]) amp / dv from the shared edge erfs and does acc[pixel] += W * S
-//          for the masked pixels (W is a shared-memory broadcast); the next particle's mask
-//          shuffle and spectrum loads are issued ahead of the current FMAs.
+//          (zeroing the weights of its sub-block that lie outside the particle's box), then
+//          walks it: two 16-byte loads bring the lane's four weights, four and a half its nine
+//          edge erfs (both conflict-free by layout: ~7 shared-memory wavefronts per 32 FMAs,
+//          against 22 for the 16 pixel x 2 channel tile of rounds 1-2), eight subtractions form
+//          E[c+1] - E[c], then acc[pixel][channel] += (W amp) * (E[c+1] - E[c]); the factor
+//          1 / dv of the channel is applied once, at the store.
 //
-// No atomics on the data path; every voxel is stored exactly once, as a 16-byte vector store
-// (a warp writes 512 contiguous bytes per pixel).
+// No atomics on the data path; every voxel is stored exactly once, as 16-byte vector stores
+// (a lane writes 64 contiguous bytes per pixel, a warp 4 x 512).
 #pragma once
 
 #include "common.cuh"
@@ -169,7 +174,19 @@ struct ProjArgs {
   unsigned long long* exec_counts;  // COUNT instantiation only: [updates, weights, erfs]
 };
 
-constexpr int W_STRIDE = TILE_PIX + 1;  // odd row stride: lane-per-particle reads hit 32 banks
+// Shared-memory layouts of the per-batch weights and edge erfs, chosen for phase C's vector
+// loads.  W: the 16 weights of a sub-block are contiguous (row of the sub-block major), so the
+// four pixel rows a warp's lanes read are one 128-byte line; rows of W are 16-byte aligned.
+// ES: edge e sits at e + 2 (e / 8): the eight channel groups of a warp start 80 bytes apart,
+// i.e. in eight different 16-byte bank groups (a lane reads the eight edges of its group as
+// four 16-byte loads and the ninth, the first edge of the next group, 80 bytes from its own).
+constexpr int W_STRIDE = TILE_PIX + 2;
+constexpr int ES_STRIDE = CB + 2 * (CB / 8) + 2;
+static_assert(SUB_X == 4 && SUB_Y == 4 && CB == 64, "phase C's register tile is 4 pixels x 8 channels");
+__host__ __device__ constexpr int w_index(int tpx, int tpy) {
+  return (((tpx >> 2) * SUBS_Y + (tpy >> 2)) << 4) | ((tpx & 3) << 2) | (tpy & 3);
+}
+__host__ __device__ constexpr int es_pos(int e) { return e + 2 * (e >> 3); }
 
 // What the per-batch set-up leaves for the evaluation and accumulation phases.
 struct SetupBuf {
@@ -186,8 +203,9 @@ struct SetupBuf {
 
 struct ProjSmem {
   Record rec[2][PBATCH];
-  double W[PBATCH][W_STRIDE];   // kernel integrals, valid inside the particle's box only
-  double ES[PBATCH][CB + 2];    // edge erfs of the live channels (up to CB+1 per particle)
+  double W[PBATCH][W_STRIDE];   // kernel integrals x amplitude at w_index(pixel); valid inside the
+                                // particle's box (phase C zeroes the rest of the sub-blocks it visits)
+  double ES[PBATCH][ES_STRIDE]; // the CB + 1 edge erfs of every live particle at es_pos(edge)
   double inv_dv[CB];            // (16-byte aligned: read as double2)
   double edge[CB + 1];
   SetupBuf sb[2];  // (two: batch b+1 is set up while batch b is evaluated)
@@ -275,9 +293,11 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
     for (int c = tid; c < CB; c += PROJ_THREADS)
       sm.inv_dv[c] = (c >= clo && c < nch) ? 1.0 / fabs(a.edges[c0 + c + 1] - a.edges[c0 + c]) : 0.0;
 
-    double acc[SUB_PIX][2];
+    double acc[4][8];  // [pixel of my sub-block row][channel of my group]
 #pragma unroll
-    for (int j = 0; j < SUB_PIX; ++j) acc[j][0] = acc[j][1] = 0.0;
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[k][q] = 0.0;
 
     const uint32_t n_part = it.end - it.begin;
     const uint32_t n_batch = (n_part + PBATCH - 1) / PBATCH;
@@ -386,7 +406,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
           for (int u = 0; u < NW; ++u) ord[u] = owner_ordinal(q0 + 32 * u, my_start, my_nonempty, lane);
           bool ok[NW];
           int pp[NW], pix[NW], kind[NW], kid[NW];
-          double dx[NW], dy[NW], R2[NW], ih2[NW], tv[NW];
+          double dx[NW], dy[NW], R2[NW], ih2[NW], tv[NW], amp[NW];
 #pragma unroll
           for (int u = 0; u < NW; ++u) {
             const uint32_t q = q0 + 32 * u + lane;
@@ -398,8 +418,9 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
             const int tpx = S.box[p][0] + ix, tpy = S.box[p][2] + iy;
             const Record& r = sm.rec[buf][p];
             pp[u] = p;
-            pix[u] = tpx * TILE_Y + tpy;
+            pix[u] = w_index(tpx, tpy);
             kid[u] = r.kid;
+            amp[u] = r.amp;
             kind[u] = (KIND >= 0 && kid[u] == 0) ? KIND : a.table.kind[kid[u]];
             // dij = pixcoords - ij (martini.py:276)
             dx[u] = __dsub_rn(r.px, (double)(x0 + tpx));
@@ -420,7 +441,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
                 w = kernel_weight_closed(kind[u], dx[u], dy[u], r.h, r.inv_h2, a.table.truncate[r.kid],
                                          a.table.norm[r.kid]);
               }
-              sm.W[pp[u]][pix[u]] = w;
+              sm.W[pp[u]][pix[u]] = w * amp[u];
               if (COUNT) ++n_w;
             }
           }
@@ -454,114 +475,131 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             if (ok[u]) {
-              sm.ES[pp[u]][ee[u]] = ev[u];
+              sm.ES[pp[u]][es_pos(ee[u])] = ev[u];
               if (COUNT) n_erf += fabs(t[u]) < ERF_SAT;
+            }
+          }
+        }
+      }
+      // ---- edges outside the live window: thread = (particle, 16-edge quarter).  The reference
+      // evaluates erf at every edge; outside [cs, ce] it is saturated, -1 below and +1 above in
+      // the g orientation (plan.cuh: channel_window), so the differences E[c+1] - E[c] of the dead
+      // channels are exactly zero without a predicate in phase C.  The Dirac line is written as
+      // the step function whose differences are 1 on the live channels [cs, ce).
+      {
+        const int p = tid >> 2, qtr = tid & 3;
+        if (p < nb && S.hlive[p]) {
+          const int cs = S.chan[p][0], ce = S.chan[p][1];
+          double* row = sm.ES[p];
+          const int e_end = qtr == 3 ? CB + 1 : 16 * qtr + 16;
+          for (int e = 16 * qtr; e < e_end; ++e) {
+            if (gaussian_line) {
+              if (e < cs || e > ce) row[es_pos(e)] = e < cs ? -1.0 : 1.0;
+            } else {
+              row[es_pos(e)] = (double)(min(max(e, cs), ce) - cs);
             }
           }
         }
       }
       __syncthreads();
 
-      // ---- warp-private list: which particles touch my sub-block, and on which pixels -----
-      uint32_t mymask = 0;
+      // ---- warp-private list: which particles touch my sub-block.  Lane = particle: the 16
+      // weights of my sub-block that lie outside the particle's box are stale shared memory --
+      // zero them (only this warp reads them), so phase C needs no pixel predicate either.
+      bool visit = false;
       if (lane < nb && S.hlive[lane]) {
         const int bx0 = S.box[lane][0], bx1 = bx0 + S.box[lane][1];
         const int by0 = S.box[lane][2], by1 = by0 + S.box[lane][3];
+        double* wsub = &sm.W[lane][sub * SUB_PIX];
+        uint32_t inbox = 0, nonzero = 0;
 #pragma unroll
         for (int j = 0; j < SUB_PIX; ++j) {
-          const int tpx = sub_x(sub, j), tpy = sub_y(sub, j);
-          // (the W != 0 test drops the box pixels outside the kernel's support: measured 6 %
-          // faster than box-only masks, which make more warps visit a particle for nothing)
-          if (tpx >= bx0 && tpx < bx1 && tpy >= by0 && tpy < by1 &&
-              sm.W[lane][tpx * TILE_Y + tpy] != 0.0)
-            mymask |= 1u << j;
+          const int tpx = (sub / SUBS_Y) * SUB_X + j / SUB_Y, tpy = (sub % SUBS_Y) * SUB_Y + j % SUB_Y;
+          if (tpx >= bx0 && tpx < bx1 && tpy >= by0 && tpy < by1) {
+            inbox |= 1u << j;
+            // (the W != 0 test drops the box pixels outside the kernel's support: fewer warps
+            // visit a particle for nothing)
+            if (wsub[j] != 0.0) nonzero |= 1u << j;
+          }
+        }
+        visit = nonzero != 0;
+        if (visit && inbox != 0xffffu) {
+#pragma unroll
+          for (int j = 0; j < SUB_PIX; ++j)
+            if (!(inbox & (1u << j))) wsub[j] = 0.0;
         }
       }
-      uint32_t rel = __ballot_sync(0xffffffffu, mymask != 0);
+      __syncwarp();  // the zeroing above is read by the other lanes below
+      uint32_t rel = __ballot_sync(0xffffffffu, visit);
 
-      // ---- phase C: acc[pixel][2 channels] += W * S for the masked pixels -----------------
-      // Software-pipelined: the next particle's mask shuffle, shared-memory loads and spectrum
-      // arithmetic are issued before the current particle's FMAs, so their ~110-cycle chain
-      // (bit scan, shuffle, load) overlaps the FMA stream instead of preceding it.
-      const int c = 2 * lane;
-      const double2 idv = *reinterpret_cast<const double2*>(&sm.inv_dv[c]);
-      // this lane's two channels of particle p's line spectrum, from the shared edge erfs
-      // (adjacent channels share an edge):  S = 0.5 [erf(hi) - erf(lo)] A / dv / 2.36e5, the
-      // 0.5 and 2.36e5 live in amp; channels outside the live range are exactly zero
-      struct RawSpec {  // what spectrum_of needs from shared memory, loaded ahead of time
-        uint32_t chan;
-        double amp, ec;
-        double2 eab;
-      };
-      auto load_spec = [&](int p) {
-        RawSpec r;
-        r.chan = *reinterpret_cast<const uint16_t*>(S.chan[p]);
-        r.amp = sm.rec[buf][p].amp;
-        r.eab = *reinterpret_cast<const double2*>(&sm.ES[p][c]);
-        r.ec = sm.ES[p][c + 2];
-        return r;
-      };
-      auto spectrum_of = [&](const RawSpec& r) {
-        const uint32_t cs = r.chan & 0xffu, span = (r.chan >> 8) - cs;
-        const bool in0 = (uint32_t)c - cs < span, in1 = (uint32_t)c + 1u - cs < span;
-        double2 s2;
-        if (gaussian_line) {
-          s2.x = in0 ? (r.eab.y - r.eab.x) * (r.amp * idv.x) : 0.0;
-          s2.y = in1 ? (r.ec - r.eab.y) * (r.amp * idv.y) : 0.0;
-        } else {  // Dirac line: the live channels are exactly those with lo <= v <= hi
-          s2.x = in0 ? r.amp * idv.x : 0.0;
-          s2.y = in1 ? r.amp * idv.y : 0.0;
-        }
-        return s2;
-      };
-      if (rel) {
-        int p = __ffs(rel) - 1;
-        rel &= rel - 1;
-        uint32_t m = __shfl_sync(0xffffffffu, mymask, p);
-        double2 s2 = spectrum_of(load_spec(p));
-        for (;;) {
-          const bool more = rel != 0;
-          const int pn = more ? __ffs(rel) - 1 : p;
+      // ---- phase C: acc[4 pixels][8 channels] += (W amp) (E[c+1] - E[c]) ------------------------
+      {
+        const int pr = lane >> 3, cg = lane & 7;
+        const double* wbase = &sm.W[0][sub * SUB_PIX + pr * SUB_Y];
+        const double* ebase = &sm.ES[0][es_pos(8 * cg)];
+        while (rel) {
+          const int p = __ffs(rel) - 1;
           rel &= rel - 1;
-          // loads for the next particle go out now, their arithmetic comes after the FMAs
-          const uint32_t mn = __shfl_sync(0xffffffffu, mymask, pn);
-          const RawSpec rn = load_spec(pn);
-          const double* Wp = sm.W[p];
+          const double2* wp = reinterpret_cast<const double2*>(wbase + p * W_STRIDE);
+          const double2* ep = reinterpret_cast<const double2*>(ebase + p * ES_STRIDE);
+          const double2 w01 = wp[0], w23 = wp[1];
+          const double2 e01 = ep[0], e23 = ep[1], e45 = ep[2], e67 = ep[3];
+          const double e8 = ebase[p * ES_STRIDE + 10];  // = es_pos(8 cg + 8): first edge of the next group
+          const double w[4] = {w01.x, w01.y, w23.x, w23.y};
+          const double d[8] = {e01.y - e01.x, e23.x - e01.y, e23.y - e23.x, e45.x - e23.y,
+                               e45.y - e45.x, e67.x - e45.y, e67.y - e67.x, e8 - e67.y};
 #pragma unroll
-          for (int j = 0; j < SUB_PIX; ++j) {
-            if (m & (1u << j)) {
-              const double w = Wp[sub_x(sub, j) * TILE_Y + sub_y(sub, j)];
-              acc[j][0] = fma(w, s2.x, acc[j][0]);
-              acc[j][1] = fma(w, s2.y, acc[j][1]);
-              if (COUNT) n_upd += (s2.x != 0.0) + (s2.y != 0.0);
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              acc[k][q] = fma(w[k], d[q], acc[k][q]);
+              if (COUNT) n_upd += (w[k] != 0.0) && (d[q] != 0.0);
             }
-          }
-          if (!more) break;
-          p = pn;
-          m = mn;
-          s2 = spectrum_of(rn);
         }
       }
       __syncthreads();  // W, ES, boxes and rec[buf] are free again
       if (b + 2 < n_batch) issue(b + 2);
     }
 
-    // ---- one store per voxel -------------------------------------------------------------
-    const int cl = 2 * lane;  // this lane's first channel within the brick
-    const int nvalid = cl < clo ? 0 : max(0, min(2, nch - cl));
-    if (it.slot >= 0) {
-      double* dst = a.partials + (size_t)it.slot * TILE_PIX * CB + cl;
+    // ---- one store per voxel: x 1 / dv of the channel (spectral_models.py:139), then
+    // out = (in + acc) / px_area ----------------------------------------------------------
+    {
+      const int pr = lane >> 3, cg = lane & 7;
+      const int tpx = (sub / SUBS_Y) * SUB_X + pr, tpy0 = (sub % SUBS_Y) * SUB_Y;
+      const double2* idv = reinterpret_cast<const double2*>(&sm.inv_dv[8 * cg]);
 #pragma unroll
-      for (int j = 0; j < SUB_PIX; ++j)
-        *reinterpret_cast<double2*>(dst + (size_t)(sub_x(sub, j) * TILE_Y + sub_y(sub, j)) * CB) =
-            make_double2(acc[j][0], acc[j][1]);
-    } else if (nvalid > 0) {
+      for (int h = 0; h < 4; ++h) {
+        const double2 i2 = idv[h];
 #pragma unroll
-      for (int j = 0; j < SUB_PIX; ++j) {
-        const int gx = x0 + sub_x(sub, j), gy = y0 + sub_y(sub, j);
-        if (gx < g.x_hi && gy < g.ny) {
-          double* dst = a.slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + cl;
-          store2(dst, acc[j][0], acc[j][1], nvalid, a.px_area, !a.zeroed, (g.C & 1) == 0);
+        for (int k = 0; k < 4; ++k) {
+          acc[k][2 * h] *= i2.x;
+          acc[k][2 * h + 1] *= i2.y;
+        }
+      }
+      if (it.slot >= 0) {
+        double* dst = a.partials + (size_t)it.slot * TILE_PIX * CB + 8 * cg;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+            *reinterpret_cast<double2*>(dst + (size_t)(tpx * TILE_Y + tpy0 + k) * CB + 2 * h) =
+                make_double2(acc[k][2 * h], acc[k][2 * h + 1]);
+      } else {
+        const int gx = x0 + tpx;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int gy = y0 + tpy0 + k;
+          if (gx < g.x_hi && gy < g.ny) {
+            double* dst = a.slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + 8 * cg;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int cl = 8 * cg + 2 * h;  // first channel of the pair within the brick
+              const int nvalid = cl < clo ? 0 : max(0, min(2, nch - cl));
+              if (nvalid > 0)
+                store2(dst + 2 * h, acc[k][2 * h], acc[k][2 * h + 1], nvalid, a.px_area, !a.zeroed,
+                       (g.C & 1) == 0);
+            }
+          }
         }
       }
     }
