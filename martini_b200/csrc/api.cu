@@ -342,7 +342,7 @@ static size_t workspace_layout(int64_t n_kept, const int64_t n_pairs[2], const i
   ws.inv_dv = (double*)take((size_t)n_channels * sizeof(double));
   const int64_t np_max = std::max(n_pairs[0], n_pairs[1]), nk_max = std::max(n_keys[0], n_keys[1]);
   ws.hist = (uint32_t*)take(sort_hist_bytes(np_max));
-  ws.scan_temp = take(std::max(scan_temp_bytes(sort_num_chunks(np_max) * RADIX, 4), scan_temp_bytes(nk_max, 4)));
+  ws.scan_temp = take(std::max(scan_temp_bytes(sort_hist_entries(np_max), 4), scan_temp_bytes(nk_max, 4)));
   for (int k = 0; k < 2; ++k) {
     StreamWs& t = ws.s[k];
     const int64_t np = n_pairs[k], nk = np > 0 || k == 0 ? n_keys[k] : 0, ch = std::max<int64_t>(1, chunk[k]);

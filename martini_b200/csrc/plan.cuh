@@ -6,7 +6,9 @@
 
 namespace mtn {
 
-constexpr int PLAN_THREADS = 1024;
+// 256-thread blocks: at ~50 registers five of them share an SM (a 1024-thread block was alone on
+// it: half the warp slots idle while every particle waits on its loads)
+constexpr int PLAN_THREADS = 256;
 constexpr int TILE_STAT_STRIDE = 32;
 
 // ---------------------------------------------------------------------------------------
@@ -172,17 +174,29 @@ __device__ __forceinline__ int first_true(Pred pred, int C, int guess) {
   return lo;
 }
 
+// Where a uniform channel grid puts an edge value: e = (x - e0) * inv_step.  The same for every
+// particle, so a block computes it once (one division).
+struct ChanGrid {
+  double e0, inv_step;
+};
+__device__ __forceinline__ ChanGrid chan_grid(const double* __restrict__ edges, int C) {
+  ChanGrid cg;
+  cg.e0 = __ldg(edges);
+  cg.inv_step = (double)C / (__ldg(edges + C) - cg.e0);
+  return cg;
+}
+
+// `sg`: sigma of the Gaussian line (only steers the guesses); inv_s = 1 / (sqrt(2) sigma).
 __device__ __forceinline__ bool channel_window(const double* __restrict__ edges, int C, int sgn,
-                                               int spectrum, double v, double inv_s, int& c0,
-                                               int& c1) {
+                                               int spectrum, double v, double inv_s, double sg,
+                                               const ChanGrid& cg, int& c0, int& c1) {
   const bool dirac = spectrum == MTN_SPECTRUM_DIRACDELTA;
   const double scale = dirac ? (double)sgn : (double)sgn * inv_s;
   auto g = [&](int e) { return (__ldg(edges + e) - v) * scale; };
   // where a uniform grid has g(e) = x:  e = (x / scale + v - edges[0]) / mean channel width
-  const double e0 = __ldg(edges), inv_step = (double)C / (__ldg(edges + C) - e0);
-  const double half = dirac ? 0.0 : ERF_SAT / scale;  // (signed: scale carries the direction)
+  const double half = dirac ? 0.0 : (double)sgn * (ERF_SAT * 1.4142135623730951) * sg;  // = ERF_SAT / scale
   auto guess = [&](double x_over_scale) {
-    const double e = (x_over_scale + v - e0) * inv_step;
+    const double e = (x_over_scale + v - cg.e0) * cg.inv_step;
     return (int)fmin(fmax(e, -1.0), (double)C + 1.0);  // (NaN -> 0 on the device: any guess is fine)
   };
   // first edge e in [0, C] with g(e) > -T (>= 0 for dirac)
@@ -215,11 +229,6 @@ struct PlanIn {
   const double* edges;
 };
 
-__device__ __forceinline__ double inv_sqrt2_sigma(const PlanIn& in, int64_t i) {
-  const double sg = in.sigma ? in.sigma[i] : in.sigma_scalar;
-  return 1.0 / (1.4142135623730951 * sg);
-}
-
 // The one pixel a DiracDelta-kernel particle reaches: |p - i| < 0.5 on both axes, strict
 // (sph_kernels.py:1165), evaluated as numpy does (fl(p - i)); false if there is none (a
 // particle exactly on a pixel edge lands nowhere) or it lies outside [lo, hi].
@@ -231,57 +240,45 @@ __device__ __forceinline__ bool dirac_pixel(double p, int lo, int hi, int& i) {
   return true;
 }
 
-__device__ __forceinline__ Foot footprint(const PlanIn& in, const Geo& g, int64_t i) {
+__device__ __forceinline__ Foot footprint(const PlanIn& in, const Geo& g, int64_t i, const ChanGrid& cg) {
   Foot f;
   f.box = f.live = false;
   f.route = ROUTE_BRICK;
-  if (in.accept && !in.accept[i]) return f;
-  const double r = in.sm_range[i];
-  if (!pixel_bounds(in.px[i], r, g.x_lo, g.x_hi - 1, f.i0, f.i1)) return f;
-  if (!pixel_bounds(in.py[i], r, 0, g.ny - 1, f.j0, f.j1)) return f;
+  // every input up front: independent loads, one exposed memory latency instead of five in a
+  // row behind the early returns (all in bounds for a rejected particle too)
+  const bool accepted = in.accept ? in.accept[i] != 0 : true;
+  const double r = in.sm_range[i], px = in.px[i], py = in.py[i], h = in.h_eff[i], v = in.v[i];
+  const int kid = in.kernel_id ? in.kernel_id[i] : 0;
+  const bool gauss = g.spectrum == MTN_SPECTRUM_GAUSSIAN;
+  const double sg = gauss ? (in.sigma ? in.sigma[i] : in.sigma_scalar) : 1.0;
+  if (!accepted) return f;
+  if (!pixel_bounds(px, r, g.x_lo, g.x_hi - 1, f.i0, f.i1)) return f;
+  if (!pixel_bounds(py, r, 0, g.ny - 1, f.j0, f.j1)) return f;
   f.box = true;
-  f.px = in.px[i];
-  f.py = in.py[i];
+  f.px = px;
+  f.py = py;
   {
-    const double s = in.h_eff[i] * g.support[in.kernel_id ? in.kernel_id[i] : 0];
+    const double s = h * g.support[kid];
     f.s2 = s * s * (1.0 + 1.0e-9);  // (a tile is culled only if it is clearly outside)
   }
   f.nbx = f.i1 - f.i0 + 1;
   f.nby = f.j1 - f.j0 + 1;
-  const double inv_s = g.spectrum == MTN_SPECTRUM_GAUSSIAN ? inv_sqrt2_sigma(in, i) : 1.0;
-  f.live = channel_window(in.edges, g.C, g.edges_increasing ? 1 : -1, g.spectrum, in.v[i], inv_s,
-                          f.c0, f.c1);
+  const double inv_s = gauss ? 1.0 / (1.4142135623730951 * sg) : 1.0;
+  f.live = channel_window(in.edges, g.C, g.edges_increasing ? 1 : -1, g.spectrum, v, inv_s, sg, cg, f.c0, f.c1);
   if (!f.live) return f;
   if (g.route2 == ROUTE_SPLAT) {
     f.route = ROUTE_SPLAT;
-  } else if (g.route2 == ROUTE_COLUMN && g.kind[in.kernel_id ? in.kernel_id[i] : 0] == MTN_KERNEL_DIRACDELTA) {
+  } else if (g.route2 == ROUTE_COLUMN && g.kind[kid] == MTN_KERNEL_DIRACDELTA) {
     // the candidate box shrinks to the single pixel with non-zero weight (or to nothing)
     f.route = ROUTE_COLUMN;
     int x, y;
-    if (dirac_pixel(in.px[i], f.i0, f.i1, x) && dirac_pixel(in.py[i], f.j0, f.j1, y)) {
+    if (dirac_pixel(px, f.i0, f.i1, x) && dirac_pixel(py, f.j0, f.j1, y)) {
       f.i0 = f.i1 = x;
       f.j0 = f.j1 = y;
     } else {
       f.live = false;
     }
   }
-  return f;
-}
-
-__device__ __forceinline__ Foot unpack_foot(const PackedFoot& p, const PlanIn& in, const Geo& g, int64_t i) {
-  Foot f;
-  f.px = in.px[i];
-  f.py = in.py[i];
-  {
-    const double s = in.h_eff[i] * g.support[in.kernel_id ? in.kernel_id[i] : 0];
-    f.s2 = s * s * (1.0 + 1.0e-9);
-  }
-  f.i0 = p.i0; f.i1 = p.i1; f.j0 = p.j0; f.j1 = p.j1;
-  f.c0 = p.c0; f.c1 = p.c1;
-  f.live = p.live != 0;
-  f.box = f.live;
-  f.route = p.route;
-  f.nbx = f.nby = 0;
   return f;
 }
 
@@ -309,7 +306,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) tile_stats_kernel(
   // the phase is a heuristic: a 1-in-TILE_STAT_STRIDE sample of the particles decides it
   const int64_t i = ((int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x) * TILE_STAT_STRIDE;
   if (i >= in.n) return;
-  const Foot f = footprint(in, g, i);
+  const Foot f = footprint(in, g, i, chan_grid(in.edges, g.C));
   if (!f.live || f.route != ROUTE_BRICK) return;
   int tx0, tx1, ty0, ty1;
   tile_range(f, g, tx0, tx1, ty0, ty1);
@@ -378,35 +375,52 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(
     int64_t* __restrict__ blk_pairs2, unsigned long long* __restrict__ updates,
     PackedFoot* __restrict__ feet) {
   const int64_t i = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
-  int64_t kept = 0, pairs = 0, pairs2 = 0, upd = 0;
+  __shared__ ChanGrid s_cg;
+  __shared__ unsigned long long wtot[PLAN_THREADS / 32][4];
+  if (threadIdx.x == 0) s_cg = chan_grid(in.edges, g.C);
+  __syncthreads();
+  // per particle: kept 0/1, pairs of either stream (< 2^24: tiles x channel blocks), candidate
+  // box area (U_dense / C)
+  uint32_t kept = 0, pairs = 0, pairs2 = 0;
+  uint64_t area = 0;
   if (i < in.n) {
-    const Foot f = footprint(in, g, i);
+    const Foot f = footprint(in, g, i, s_cg);
     feet[i] = pack_foot(f);
     // U_dense counts the reference's candidate box, whatever kernel computes the particle
-    if (f.box) upd = (int64_t)f.nbx * f.nby * g.C;
+    if (f.box) area = (uint64_t)f.nbx * (uint64_t)f.nby;
     if (f.live) {
       kept = 1;
-      (f.route == ROUTE_BRICK ? pairs : pairs2) = count_pairs(f, g);
+      (f.route == ROUTE_BRICK ? pairs : pairs2) = (uint32_t)count_pairs(f, g);
     }
   }
-  // block totals: warp reductions, one shared-memory atomic per warp and quantity, one barrier
-  // (four block-wide scans cost twelve barriers and were a third of this kernel)
-  __shared__ unsigned long long tot[4];
-  if (threadIdx.x < 4) tot[threadIdx.x] = 0ull;
-  __syncthreads();
-  long long q[4] = {(long long)kept, (long long)pairs, (long long)pairs2, (long long)upd};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) q[k] += __shfl_down_sync(0xffffffffu, q[k], d);
-    if ((threadIdx.x & 31) == 0 && q[k]) atomicAdd(&tot[k], (unsigned long long)q[k]);
+  // block totals: one warp-wide integer reduction (REDUX) per quantity -- the area in three
+  // 16-bit limbs so that 32 of them cannot overflow --, per-warp partials in shared memory, one
+  // barrier.  (Round 2 reduced four 64-bit values by shuffles and added them with shared-memory
+  // 64-bit atomics, a CAS loop under contention: a tenth of the kernel's instructions and most
+  // of its barrier stalls.)
+  {
+    const uint32_t wk = __popc(__ballot_sync(0xffffffffu, kept != 0));
+    const uint32_t wp = __reduce_add_sync(0xffffffffu, pairs);
+    const uint32_t wp2 = __reduce_add_sync(0xffffffffu, pairs2);
+    const uint32_t a0 = __reduce_add_sync(0xffffffffu, (uint32_t)(area & 0xffffu));
+    const uint32_t a1 = __reduce_add_sync(0xffffffffu, (uint32_t)((area >> 16) & 0xffffu));
+    const uint32_t a2 = __reduce_add_sync(0xffffffffu, (uint32_t)(area >> 32));
+    if ((threadIdx.x & 31) == 0) {
+      unsigned long long* w = wtot[threadIdx.x >> 5];
+      w[0] = wk;
+      w[1] = wp;
+      w[2] = wp2;
+      w[3] = (unsigned long long)a0 + ((unsigned long long)a1 << 16) + ((unsigned long long)a2 << 32);
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    blk_kept[blockIdx.x] = (int64_t)tot[0];
-    blk_pairs[blockIdx.x] = (int64_t)tot[1];
-    blk_pairs2[blockIdx.x] = (int64_t)tot[2];
-    if (tot[3]) atomicAdd(updates, tot[3]);
+  if (threadIdx.x < 4) {
+    unsigned long long t = 0;
+    for (int w = 0; w < PLAN_THREADS / 32; ++w) t += wtot[w][threadIdx.x];
+    if (threadIdx.x == 0) blk_kept[blockIdx.x] = (int64_t)t;
+    if (threadIdx.x == 1) blk_pairs[blockIdx.x] = (int64_t)t;
+    if (threadIdx.x == 2) blk_pairs2[blockIdx.x] = (int64_t)t;
+    if (threadIdx.x == 3 && t) atomicAdd(updates, t * (unsigned long long)g.C);
   }
 }
 
@@ -416,52 +430,85 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_emit_kernel(
     PlanIn in, Geo g, const int64_t* __restrict__ blk_kept, const int64_t* __restrict__ blk_pairs,
     const int64_t* __restrict__ blk_pairs2, const PackedFoot* __restrict__ feet,
     Record* __restrict__ records, uint64_t* __restrict__ pairs_out, uint64_t* __restrict__ pairs2_out) {
-  __shared__ int64_t sm3[3][33];
+  __shared__ uint32_t sm3[3][33];
+  // the block's records, in order: staged here and copied out as one contiguous run of 16-byte
+  // stores (a thread storing its own 80-byte record touches five half-used sectors per
+  // instruction; that store was 17 % of the kernel's stall samples, queue-throttled)
+  __shared__ Record srec[PLAN_THREADS];
   const int64_t i = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
-  int64_t kept = 0, npair = 0, npair2 = 0;
+  uint32_t kept = 0, npair = 0, npair2 = 0;
   Foot f;
   f.live = false;
   f.route = ROUTE_BRICK;
+  double px = 0.0, py = 0.0, h = 0.0, v = 0.0, m = 0.0, d = 1.0, sg = 1.0;
+  int kid = 0;
   if (i < in.n) {
-    f = unpack_foot(feet[i], in, g, i);  // (computed by plan_count_kernel)
-    if (f.live) {
+    const PackedFoot pf = feet[i];  // (computed by plan_count_kernel)
+    if (pf.live) {  // the particle's quantities, all loads in flight together
+      px = in.px[i];
+      py = in.py[i];
+      h = in.h_eff[i];
+      v = in.v[i];
+      kid = in.kernel_id ? in.kernel_id[i] : 0;
+      m = in.mHI ? in.mHI[i] : in.mHI_scalar;
+      d = in.D ? in.D[i] : in.D_scalar;
+      if (g.spectrum == MTN_SPECTRUM_GAUSSIAN) sg = in.sigma ? in.sigma[i] : in.sigma_scalar;
+      f.px = px;
+      f.py = py;
+      const double s = h * g.support[kid];
+      f.s2 = s * s * (1.0 + 1.0e-9);
+      f.i0 = pf.i0; f.i1 = pf.i1; f.j0 = pf.j0; f.j1 = pf.j1;
+      f.c0 = pf.c0; f.c1 = pf.c1;
+      f.live = f.box = true;
+      f.route = pf.route;
+      f.nbx = f.nby = 0;
       kept = 1;
-      (f.route == ROUTE_BRICK ? npair : npair2) = count_pairs(f, g);
+      (f.route == ROUTE_BRICK ? npair : npair2) = (uint32_t)count_pairs(f, g);
     }
   }
-  int64_t ex[3] = {kept, npair, npair2};
+  // (32-bit prefixes inside a block: a slab holds fewer than 2^32 pairs per stream, mtn_plan
+  // refuses more)
+  uint32_t ex[3] = {kept, npair, npair2};
   block_excl_scan3(ex, sm3);  // one pass, two barriers, for the three prefixes
   const int64_t ridx = blk_kept[blockIdx.x] + ex[0];
   int64_t off = blk_pairs[blockIdx.x] + ex[1];
   int64_t off2 = blk_pairs2[blockIdx.x] + ex[2];
-  if (!f.live) return;
-  Record rec;
-  rec.px = in.px[i];
-  rec.py = in.py[i];
-  rec.h = in.h_eff[i];
-  rec.inv_h2 = f.route == ROUTE_COLUMN ? 0.0 : 1.0 / (rec.h * rec.h);  // (a DiracDelta kernel has no scale)
-  rec.v = in.v[i];
-  const double m = in.mHI ? in.mHI[i] : in.mHI_scalar;
-  const double d = in.D ? in.D[i] : in.D_scalar;
-  // A = mHI * D^-2 (spectral_models.py:94), / 2.36e5 (:139); the Gaussian line's 0.5 is
-  // folded in here (exact: a power of two)
-  const double amp = m * (1.0 / (d * d)) / 2.36e5;
-  if (g.spectrum == MTN_SPECTRUM_GAUSSIAN) {
-    rec.inv_s = inv_sqrt2_sigma(in, i);
-    rec.amp = 0.5 * amp;
-  } else {
-    rec.inv_s = 1.0;
-    rec.amp = amp;
+  if (f.live) {
+    Record rec;
+    rec.px = px;
+    rec.py = py;
+    rec.h = h;
+    rec.inv_h2 = f.route == ROUTE_COLUMN ? 0.0 : 1.0 / (h * h);  // (a DiracDelta kernel has no scale)
+    rec.v = v;
+    // A = mHI * D^-2 (spectral_models.py:94), / 2.36e5 (:139); the Gaussian line's 0.5 is
+    // folded in here (exact: a power of two)
+    const double amp = m * (1.0 / (d * d)) / 2.36e5;
+    if (g.spectrum == MTN_SPECTRUM_GAUSSIAN) {
+      rec.inv_s = 1.0 / (1.4142135623730951 * sg);  // (as footprint() formed it for the window)
+      rec.amp = 0.5 * amp;
+    } else {
+      rec.inv_s = 1.0;
+      rec.amp = amp;
+    }
+    rec.i0 = f.i0;
+    rec.i1 = f.i1;
+    rec.j0 = f.j0;
+    rec.j1 = f.j1;
+    rec.c_first = (uint16_t)f.c0;  // mtn_plan refuses cubes with more than 65535 channels
+    rec.c_last = (uint16_t)f.c1;
+    rec.kid = (uint8_t)kid;
+    for (int k = 0; k < 3; ++k) rec.pad[k] = 0;
+    srec[ex[0]] = rec;
   }
-  rec.i0 = f.i0;
-  rec.i1 = f.i1;
-  rec.j0 = f.j0;
-  rec.j1 = f.j1;
-  rec.c_first = (uint16_t)f.c0;  // mtn_plan refuses cubes with more than 65535 channels
-  rec.c_last = (uint16_t)f.c1;
-  rec.kid = in.kernel_id ? in.kernel_id[i] : (uint8_t)0;
-  for (int k = 0; k < 3; ++k) rec.pad[k] = 0;
-  records[ridx] = rec;
+  __syncthreads();
+  {
+    // records [blk_kept[b], blk_kept[b] + kept in this block) as 16-byte words
+    const uint32_t n_words = (sm3[0][32]) * (REC_BYTES / 16);
+    const int4* src = reinterpret_cast<const int4*>(srec);
+    int4* dst = reinterpret_cast<int4*>(records + blk_kept[blockIdx.x]);
+    for (uint32_t w = threadIdx.x; w < n_words; w += PLAN_THREADS) dst[w] = src[w];
+  }
+  if (!f.live) return;
   if (f.route == ROUTE_COLUMN) {
     const int64_t pixel = (int64_t)(f.i0 - g.x_lo) * g.ny + f.j0;
     for (int sb = f.c0 / CSB; sb <= f.c1 / CSB; ++sb)

@@ -48,11 +48,13 @@ __device__ __forceinline__ T block_excl_scan(T x, T* smem, T* total) {
 }
 
 // Exclusive scans of three values per thread across the block in one pass (x[k] is replaced by
-// its exclusive prefix).  `smem` holds 3 x 33 values.  Two barriers.
-__device__ __forceinline__ void block_excl_scan3(int64_t x[3], int64_t (*smem)[33]) {
+// its exclusive prefix).  `smem` holds 3 x 33 values; smem[k][32] is left holding the block
+// total of quantity k.  Two barriers.
+template <typename T>
+__device__ __forceinline__ void block_excl_scan3(T x[3], T (*smem)[33]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = (blockDim.x + 31) >> 5;
-  int64_t incl[3];
+  T incl[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     incl[k] = warp_incl_scan(x[k]);
@@ -60,9 +62,10 @@ __device__ __forceinline__ void block_excl_scan3(int64_t x[3], int64_t (*smem)[3
   }
   __syncthreads();
   if (warp < 3) {  // warp k scans the warp totals of quantity k
-    const int64_t w = lane < nwarps ? smem[warp][lane] : 0;
-    const int64_t wi = warp_incl_scan(w);
+    const T w = lane < nwarps ? smem[warp][lane] : T(0);
+    const T wi = warp_incl_scan(w);
     smem[warp][lane] = wi - w;
+    if (lane == 31) smem[warp][32] = wi;
   }
   __syncthreads();
 #pragma unroll

@@ -2,10 +2,17 @@
 //
 // Pairs are emitted in particle order and the sort is stable, so inside every brick the
 // particles stay in index order -- the summation order of the reference's per-pixel
-// np.sum (martini.py:281).  Hand-written: 8-bit digits; per pass (1) per-warp-chunk digit
-// histograms, (2) one exclusive scan over the digit-major histogram matrix, (3) a stable
-// scatter in which each warp walks its chunk in order and ranks equal digits with
-// __match_any_sync.  HBM-bound integer work: 24 B moved per pair per pass.
+// np.sum (martini.py:281).  Hand-written.  The key's bits are split evenly over the fewest
+// passes of at most SORT_MAX_BITS each (18-bit pixel keys: 2 x 9, 20-bit (tile, channel) keys:
+// 2 x 10).  Per pass: (1) one digit histogram per block tile of SORT_TILE pairs, (2) one
+// exclusive scan over the digit-major histogram matrix, (3) a scatter in which the block first
+// orders its tile by digit in shared memory -- every warp walks its contiguous share in order
+// and ranks equal digits with __match_any_sync, the warps' counts are prefix-summed per digit
+// -- and then writes each digit's run to its place in one piece: runs of SORT_TILE / 2^bits
+// pairs (64 to 512 bytes) instead of the single 8-byte stores of rounds 1-2, which cost four
+// times their bytes in 32-byte sectors (131 us against 32 us per pass of 9.3e6 pairs, the
+// same instructions, depending only on how scattered the digit was).  HBM-bound integer work:
+// 24 B moved per pair per pass.
 #pragma once
 
 #include "common.cuh"
@@ -13,63 +20,135 @@
 
 namespace mtn {
 
-constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_MAX_BITS = 10;
 constexpr int SORT_WARPS = 8;
 constexpr int SORT_THREADS = SORT_WARPS * 32;
-constexpr int SORT_IPW = 1024;  // pairs per warp chunk
+constexpr int SORT_PER_THREAD = 32;                       // pairs a thread holds in registers
+constexpr int SORT_IPW = 32 * SORT_PER_THREAD;            // pairs per warp (contiguous)
+constexpr int SORT_TILE = SORT_WARPS * SORT_IPW;          // pairs per block: 8192
 
-inline int64_t sort_num_chunks(int64_t n) { return (n + SORT_IPW - 1) / SORT_IPW; }
+inline int64_t sort_num_tiles(int64_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+// passes and bits per pass for a key of `key_bits` bits
+inline int sort_passes(int key_bits) { return (key_bits + SORT_MAX_BITS - 1) / SORT_MAX_BITS; }
+inline int sort_bits_per_pass(int key_bits) {
+  const int p = sort_passes(key_bits);
+  return p ? (key_bits + p - 1) / p : 0;
+}
+inline int64_t sort_hist_entries(int64_t n) { return sort_num_tiles(n) << SORT_MAX_BITS; }
 inline size_t sort_hist_bytes(int64_t n) {
-  return align_up((size_t)sort_num_chunks(n) * RADIX * sizeof(uint32_t) + 16);
+  return align_up((size_t)sort_hist_entries(n) * sizeof(uint32_t) + 16);
+}
+// dynamic shared memory of the scatter kernel: the staged tile, per-warp digit counters,
+// per-digit (global offset - local start)
+inline size_t sort_scatter_smem(int bits) {
+  return (size_t)SORT_TILE * 8 + ((size_t)SORT_WARPS + 1) * ((size_t)4 << bits);
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) radix_count_kernel(
-    const uint64_t* __restrict__ in, int64_t n, int shift, int64_t n_chunks,
+    const uint64_t* __restrict__ in, int64_t n, int shift, int bits, int64_t n_tiles,
     uint32_t* __restrict__ hist) {
-  __shared__ uint32_t cnt[SORT_WARPS][RADIX];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t chunk = (int64_t)blockIdx.x * SORT_WARPS + warp;
-  if (chunk >= n_chunks) return;  // whole warp leaves together; no block barrier below
-  for (int d = lane; d < RADIX; d += 32) cnt[warp][d] = 0;
-  __syncwarp();
-  const int64_t base = chunk * SORT_IPW;
-#pragma unroll 4
-  for (int s = 0; s < SORT_IPW / 32; ++s) {
-    const int64_t i = base + s * 32 + lane;
-    if (i < n) atomicAdd(&cnt[warp][(uint32_t)(in[i] >> shift) & (RADIX - 1)], 1u);
+  __shared__ uint32_t cnt[1 << SORT_MAX_BITS];
+  const int bins = 1 << bits;
+  const uint32_t mask = (uint32_t)bins - 1u;
+  for (int d = threadIdx.x; d < bins; d += SORT_THREADS) cnt[d] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+#pragma unroll 8
+  for (int s = 0; s < SORT_TILE / SORT_THREADS; ++s) {
+    const int64_t i = base + s * SORT_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[(uint32_t)(in[i] >> shift) & mask], 1u);
   }
-  __syncwarp();
-  for (int d = lane; d < RADIX; d += 32) hist[(int64_t)d * n_chunks + chunk] = cnt[warp][d];
+  __syncthreads();
+  for (int d = threadIdx.x; d < bins; d += SORT_THREADS) hist[(int64_t)d * n_tiles + blockIdx.x] = cnt[d];
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(
-    const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int64_t n, int shift,
-    int64_t n_chunks, const uint32_t* __restrict__ offs) {
-  __shared__ uint32_t pos[SORT_WARPS][RADIX];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t chunk = (int64_t)blockIdx.x * SORT_WARPS + warp;
-  if (chunk >= n_chunks) return;
-  for (int d = lane; d < RADIX; d += 32) pos[warp][d] = offs[(int64_t)d * n_chunks + chunk];
-  __syncwarp();
+    const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int64_t n, int shift, int bits,
+    int64_t n_tiles, const uint32_t* __restrict__ offs) {
+  MTN_DYN_SMEM(unsigned char, smem_raw);
+  const int bins = 1 << bits;
+  const uint32_t mask = (uint32_t)bins - 1u;
+  uint64_t* stage = reinterpret_cast<uint64_t*>(smem_raw);                  // [SORT_TILE]
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(stage + SORT_TILE);          // [SORT_WARPS][bins]
+  uint32_t* delta = cnt + SORT_WARPS * bins;                               // [bins]
+  __shared__ uint32_t scan_sm[33];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+  const int n_valid = (int)min((int64_t)SORT_TILE, n - base);
+
+  for (int k = tid; k < SORT_WARPS * bins; k += SORT_THREADS) cnt[k] = 0;
+  // this thread's pairs: element s of lane l of warp w is pair  w * SORT_IPW + s * 32 + l  of the
+  // tile (coalesced loads, all in flight together)
+  uint64_t kv[SORT_PER_THREAD];
+#pragma unroll
+  for (int s = 0; s < SORT_PER_THREAD; ++s) {
+    const int loc = warp * SORT_IPW + s * 32 + lane;
+    kv[s] = loc < n_valid ? in[base + loc] : 0ull;
+  }
+  __syncthreads();
+
+  // rank inside the warp's share: pairs of equal digit, in order
+  uint16_t rank[SORT_PER_THREAD];
+  uint32_t* wcnt = cnt + warp * bins;
   const uint32_t lt = (1u << lane) - 1u;
-  const int64_t base = chunk * SORT_IPW;
-  for (int s = 0; s < SORT_IPW / 32; ++s) {
-    const int64_t i = base + s * 32 + lane;
-    const bool valid = i < n;
-    const uint64_t kv = valid ? in[i] : 0ull;
+#pragma unroll
+  for (int s = 0; s < SORT_PER_THREAD; ++s) {
+    const bool valid = warp * SORT_IPW + s * 32 + lane < n_valid;
     // invalid lanes get private digits so they never match a real one
-    const uint32_t d = valid ? ((uint32_t)(kv >> shift) & (RADIX - 1)) : (uint32_t)(RADIX + lane);
+    const uint32_t d = valid ? ((uint32_t)(kv[s] >> shift) & mask) : (uint32_t)(bins + lane);
     const uint32_t peers = __match_any_sync(0xffffffffu, d);
-    const uint32_t rank = __popc(peers & lt);
-    uint32_t p = 0;
-    if (valid) p = pos[warp][d] + rank;
+    const uint32_t r = __popc(peers & lt);
+    uint32_t before = 0;
+    if (valid) before = wcnt[d];
     __syncwarp();
-    if (valid) {
-      out[p] = kv;
-      if (rank == 0) pos[warp][d] += __popc(peers);
+    if (valid && r == 0) wcnt[d] = before + __popc(peers);
+    __syncwarp();
+    rank[s] = (uint16_t)(before + r);
+  }
+  __syncthreads();
+
+  // per digit: exclusive prefix over the warps, then over the digits (the tile's local order)
+  {
+    const int per = (bins + SORT_THREADS - 1) / SORT_THREADS;  // consecutive digits per thread (<= 4)
+    uint32_t tot[4] = {0, 0, 0, 0};
+    uint32_t mine = 0;
+    for (int k = 0; k < per; ++k) {
+      const int d = tid * per + k;
+      if (d < bins) {
+        uint32_t run = 0;
+        for (int w = 0; w < SORT_WARPS; ++w) {
+          const uint32_t c = cnt[w * bins + d];
+          cnt[w * bins + d] = run;
+          run += c;
+        }
+        tot[k] = run;
+        mine += run;
+      }
     }
-    __syncwarp();
+    uint32_t total;
+    uint32_t start = block_excl_scan(mine, scan_sm, &total);
+    for (int k = 0; k < per; ++k) {
+      const int d = tid * per + k;
+      if (d < bins) {
+        for (int w = 0; w < SORT_WARPS; ++w) cnt[w * bins + d] += start;
+        delta[d] = offs[(int64_t)d * n_tiles + blockIdx.x] - start;  // (mod 2^32)
+        start += tot[k];
+      }
+    }
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int s = 0; s < SORT_PER_THREAD; ++s) {
+    if (warp * SORT_IPW + s * 32 + lane < n_valid) {
+      const uint32_t d = (uint32_t)(kv[s] >> shift) & mask;
+      stage[wcnt[d] + rank[s]] = kv[s];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n_valid; i += SORT_THREADS) {
+    const uint64_t v = stage[i];
+    out[(uint32_t)i + delta[(uint32_t)(v >> shift) & mask]] = v;
   }
 }
 
@@ -79,17 +158,29 @@ inline int radix_sort_pairs(uint64_t* a, uint64_t* b, int64_t n, int key_bits, u
                             void* scan_temp, uint64_t** sorted, cudaStream_t st) {
   *sorted = a;
   if (n <= 1) return MTN_OK;
-  const int64_t n_chunks = sort_num_chunks(n);
-  const unsigned grid = (unsigned)((n_chunks + SORT_WARPS - 1) / SORT_WARPS);
+  const int64_t n_tiles = sort_num_tiles(n);
+  const int bits = sort_bits_per_pass(key_bits);
+  const size_t smem = sort_scatter_smem(bits);
+#ifndef MTN_HOST_EMU
+  static thread_local int attr_dev = -1;  // (per host thread and device, like the projection kernels')
+  int dev = 0;
+  MTN_CUDA(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    MTN_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sort_scatter_smem(SORT_MAX_BITS)));
+    attr_dev = dev;
+  }
+#endif
   uint64_t* src = a;
   uint64_t* dst = b;
-  for (int bit = 0; bit < key_bits; bit += RADIX_BITS) {
+  for (int bit = 0; bit < key_bits; bit += bits) {
     const int shift = 32 + bit;
-    MTN_LAUNCH(radix_count_kernel, grid, SORT_THREADS, 0, st, src, n, shift, n_chunks, hist);
+    MTN_LAUNCH(radix_count_kernel, (unsigned)n_tiles, SORT_THREADS, 0, st, src, n, shift, bits, n_tiles, hist);
     MTN_LAUNCH_CHECK();
-    int rc = exclusive_scan<uint32_t, uint32_t>(hist, hist, n_chunks * RADIX, scan_temp, nullptr, st);
+    int rc = exclusive_scan<uint32_t, uint32_t>(hist, hist, n_tiles << bits, scan_temp, nullptr, st);
     if (rc) return rc;
-    MTN_LAUNCH(radix_scatter_kernel, grid, SORT_THREADS, 0, st, src, dst, n, shift, n_chunks, hist);
+    MTN_LAUNCH(radix_scatter_kernel, (unsigned)n_tiles, SORT_THREADS, smem, st, src, dst, n, shift, bits, n_tiles,
+               hist);
     MTN_LAUNCH_CHECK();
     uint64_t* t = src;
     src = dst;

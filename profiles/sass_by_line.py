@@ -48,8 +48,12 @@ def main():
     min_pct = float(sys.argv[3]) if len(sys.argv) > 3 else 0.4
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr = next(r for r in rows if len(r) > 3 and r[1] == "Source")
-    body = [dict(zip(hdr, r)) for r in rows[rows.index(hdr) + 1:] if len(r) == len(hdr)]
+    # one section per profiled kernel, each starting with its own header row; NCU_SECTION picks one
+    heads = [i for i, r in enumerate(rows) if len(r) > 3 and r[1] == "Source"]
+    k = int(os.environ.get("NCU_SECTION", "0"))
+    hdr = rows[heads[k]]
+    end = heads[k + 1] if k + 1 < len(heads) else len(rows)
+    body = [dict(zip(hdr, r)) for r in rows[heads[k] + 1:end] if len(r) == len(hdr)]
     table = line_table(lib, sys.argv[4] if len(sys.argv) > 4 else "project_kernelILb0")
     assert len(table) == len(body), (len(table), len(body))
     agg = collections.OrderedDict()
@@ -64,7 +68,7 @@ def main():
     ts = sum(a["samples"] for a in agg.values())
     print(f"total warp instructions {ti}, stall samples {ts}")
     print("file:line  inst%  samples%  top stalls")
-    for key in sorted(agg, key=lambda k: (k[0] != "project.cuh", k[0], k[1])):
+    for key in sorted(agg, key=lambda k: (k[0] != "project.cuh", k[0], k[1])):  # (file, line) order
         a = agg[key]
         if 100 * a["inst"] / ti < min_pct and 100 * a["samples"] / ts < min_pct:
             continue
