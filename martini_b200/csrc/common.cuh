@@ -47,15 +47,16 @@ constexpr int ERF_NCOEF = ERF_DEG + 1;  // 10 doubles = 80 B per interval (16-B 
 constexpr int ERF_NINT = 6 * ERF_INV_W + 1;
 // The compact erf table of the column / splat kernels, which keep it in shared memory and are
 // bound by the shared-memory data pipe (every lane reads its own row): 1/64-wide intervals,
-// degree 5 -- 48-byte rows, three 16-byte loads per evaluation instead of five; truncation
+// and per interval only erf(x0) and A = 2/sqrt(pi) exp(-x0^2) at its centre x0 -- ONE 16-byte
+// load per evaluation.  The Taylor coefficients of degree 2..5 follow from x0 and A in registers
+// (erf^(n)(x) = (-1)^(n-1) A H_(n-1)(x), H = physicists' Hermite polynomials): nine FP64
+// instructions on a pipe that was a quarter busy, against two more 16-byte loads per lane on
+// the pipe that was 96 % busy (rounds 1-2 stored all six coefficients: 48-byte rows, 36 of the
+// column kernel's 57 shared-memory wavefronts per particle).  Truncation as before:
 // (1/128)^6 |erf^(6)| / 720 < 2e-14, five orders below what the 1e-9 flux tolerance needs.
 constexpr int ERFC_INV_W = 64;
-constexpr int ERFC_DEG = 5;
-constexpr int ERFC_NCOEF = ERFC_DEG + 1;
+constexpr int ERFC_NCOEF = 2;  // {erf(x0), 2/sqrt(pi) exp(-x0^2)}
 constexpr int ERFC_NINT = 6 * ERFC_INV_W + 1;
-// (rows are plain 48-byte records; a 16-byte skew every eight rows, which makes even row
-// distances between lanes conflict-free, was measured and changed nothing: 2.41 against 2.35 ms)
-__host__ __device__ constexpr int erfc_row_offset(int r) { return ERFC_NCOEF * r; }
 constexpr int ERFC_DOUBLES = ERFC_NCOEF * ERFC_NINT;
 // One staged particle record: 80 bytes (common.cuh: Record), 16-B aligned so a single
 // cp.async.bulk moves it.

@@ -537,24 +537,54 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         const int pr = lane >> 3, cg = lane & 7;
         const double* wbase = &sm.W[0][sub * SUB_PIX + pr * SUB_Y];
         const double* ebase = &sm.ES[0][es_pos(8 * cg)];
-        while (rel) {
-          const int p = __ffs(rel) - 1;
+        // Software-pipelined in half visits (4 pixels x 4 channels = 16 FMAs each): the loads of
+        // the second half go out before the FMAs of the first, those of the next particle's first
+        // half before the FMAs of the second, so every shared-memory latency is covered by FMAs
+        // of the same warp (four warps per scheduler are too few to cover it between them).
+        if (rel) {
+          int p = __ffs(rel) - 1;
           rel &= rel - 1;
           const double2* wp = reinterpret_cast<const double2*>(wbase + p * W_STRIDE);
           const double2* ep = reinterpret_cast<const double2*>(ebase + p * ES_STRIDE);
-          const double2 w01 = wp[0], w23 = wp[1];
-          const double2 e01 = ep[0], e23 = ep[1], e45 = ep[2], e67 = ep[3];
-          const double e8 = ebase[p * ES_STRIDE + 10];  // = es_pos(8 cg + 8): first edge of the next group
-          const double w[4] = {w01.x, w01.y, w23.x, w23.y};
-          const double d[8] = {e01.y - e01.x, e23.x - e01.y, e23.y - e23.x, e45.x - e23.y,
-                               e45.y - e45.x, e67.x - e45.y, e67.y - e67.x, e8 - e67.y};
+          double2 w01 = wp[0], w23 = wp[1], ea = ep[0], eb = ep[1], ec = ep[2];
+          for (;;) {
+            const double2 ed = ep[3];
+            const double e8 = reinterpret_cast<const double*>(ep)[10];  // = es_pos(8 cg + 8): first edge of the next group
+            const double w[4] = {w01.x, w01.y, w23.x, w23.y};
+            {
+              const double d[4] = {ea.y - ea.x, eb.x - ea.y, eb.y - eb.x, ec.x - eb.y};
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
+              for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              acc[k][q] = fma(w[k], d[q], acc[k][q]);
-              if (COUNT) n_upd += (w[k] != 0.0) && (d[q] != 0.0);
+                for (int q = 0; q < 4; ++q) {
+                  acc[k][q] = fma(w[k], d[q], acc[k][q]);
+                  if (COUNT) n_upd += (w[k] != 0.0) && (d[q] != 0.0);
+                }
             }
+            const double d4 = ec.y - ec.x, e5 = ec.y;
+            const bool more = rel != 0;
+            const int pn = more ? __ffs(rel) - 1 : p;
+            rel &= rel - 1;
+            wp = reinterpret_cast<const double2*>(wbase + pn * W_STRIDE);
+            ep = reinterpret_cast<const double2*>(ebase + pn * ES_STRIDE);
+            w01 = wp[0];
+            w23 = wp[1];
+            ea = ep[0];
+            eb = ep[1];
+            ec = ep[2];
+            {
+              const double d[4] = {d4, ed.x - e5, ed.y - ed.x, e8 - ed.y};
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  acc[k][4 + q] = fma(w[k], d[q], acc[k][4 + q]);
+                  if (COUNT) n_upd += (w[k] != 0.0) && (d[q] != 0.0);
+                }
+            }
+            if (!more) break;
+            p = pn;
+          }
         }
       }
       __syncthreads();  // W, ES, boxes and rec[buf] are free again

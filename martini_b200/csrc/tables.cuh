@@ -25,20 +25,27 @@ __device__ double g_erf_table[ERF_NINT * ERF_NCOEF];
 // kernel, where few rows matter more than few loads) and the compact one (common.cuh) that the
 // column / splat kernels copy into shared memory: every lane reads its own row there, and the
 // L1 / shared-memory data pipe -- 128 B per cycle -- is what bounds them (a shared-memory row
-// costs 4 wavefronts per 16-byte load of a warp, a global one 5.4 and three times the latency).
+// costs 4 wavefronts per 16-byte load of a warp, a global one 5.4 and three times the latency),
+// so the compact table holds one 16-byte row per interval and the evaluator derives the rest.
 __device__ double g_erf_table_compact[ERFC_DOUBLES];
 
 __device__ __forceinline__ double erf_tab_compact(const double* __restrict__ table, double t) {
   const double a = fmin(fabs(t), ERF_SAT);
   const int i = (int)(a * ERFC_INV_W);  // a = ERF_SAT lands in the last (saturated) interval
-  const double u = a - ((double)i + 0.5) * (1.0 / ERFC_INV_W);
-  const double2* row = reinterpret_cast<const double2*>(table + erfc_row_offset(i));
-  const double2 c45 = row[2], c23 = row[1], c01 = row[0];
-  double r = fma(c45.y, u, c45.x);
-  r = fma(r, u, c23.y);
-  r = fma(r, u, c23.x);
-  r = fma(r, u, c01.y);
-  r = fma(r, u, c01.x);
+  const double x0 = ((double)i + 0.5) * (1.0 / ERFC_INV_W);
+  const double u = a - x0;
+  const double2 fa = reinterpret_cast<const double2*>(table)[i];  // {erf(x0), 2/sqrt(pi) exp(-x0^2)}
+  // erf(x0 + u) = erf(x0) + A u (1 + u (k2 + u (k3 + u (k4 + u k5)))):
+  //   k2 = -x0, k3 = (2 x0^2 - 1) / 3, k4 = -x0 (2 x0^2 - 3) / 6, k5 = (4 x0^4 - 12 x0^2 + 3) / 30
+  const double q = x0 * x0;
+  const double k3 = fma(q, 2.0 / 3.0, -1.0 / 3.0);
+  const double k4 = x0 * fma(q, -1.0 / 3.0, 0.5);
+  const double k5 = fma(fma(q, 4.0 / 30.0, -12.0 / 30.0), q, 3.0 / 30.0);
+  double p = fma(k5, u, k4);
+  p = fma(p, u, k3);
+  p = fma(p, u, -x0);
+  p = fma(p, u, 1.0);
+  double r = fma(fa.y * u, p, fa.x);
   r = fmin(r, 1.0);
   r = fabs(t) >= ERF_SAT ? 1.0 : r;
   return copysign(r, t);

@@ -319,13 +319,15 @@ static void build_erf_table_generic(double* tab, int inv_w, int deg, int nint) {
   }
 }
 static void build_erf_table(double* tab) { build_erf_table_generic(tab, ERF_INV_W, ERF_DEG, ERF_NINT); }
-// the compact table of the column / splat kernels (tables.cuh: erf_tab_compact)
+// the compact table of the column / splat kernels (tables.cuh: erf_tab_compact): value and
+// first derivative at the interval centres
 static void build_erf_table_compact(double* tab) {
-  static double plain[ERFC_NINT * ERFC_NCOEF];
-  build_erf_table_generic(plain, ERFC_INV_W, ERFC_DEG, ERFC_NINT);
-  for (int i = 0; i < ERFC_DOUBLES; ++i) tab[i] = 0.0;
-  for (int r = 0; r < ERFC_NINT; ++r)
-    for (int k = 0; k < ERFC_NCOEF; ++k) tab[erfc_row_offset(r) + k] = plain[r * ERFC_NCOEF + k];  // skewed rows
+  const ld two_over_sqrt_pi = 1.1283791670955125738961589031215452L;
+  for (int r = 0; r < ERFC_NINT; ++r) {
+    const ld c = ((ld)r + 0.5L) / ERFC_INV_W;
+    tab[ERFC_NCOEF * r + 0] = (double)erfl(c);
+    tab[ERFC_NCOEF * r + 1] = (double)(two_over_sqrt_pi * expl(-c * c));
+  }
 }
 
 }  // namespace mtn
