@@ -2,7 +2,7 @@
 //
 // One CTA works on one brick -- TILE x TILE pixels x 64 channels -- at a time and keeps the
 // brick's sums in registers: warp w owns a 4 x 4 pixel sub-block; lane l owns one pixel row of
-// it (l / 8) and eight adjacent channels (8 (l % 8) ...), i.e. a 4 pixel x 8 channel register
+// it (l / 8) and four channel pairs (2 (l % 8) + 16 h, + 1), i.e. a 4 pixel x 8 channel register
 // tile = 32 float64 accumulators per thread.  With the default 8 x 8 tile a CTA is 4 warps and
 // four CTAs share an SM, so one CTA's barrier waits are covered by the others.  The particle records of the brick are gathered
 // into shared memory with cp.async.bulk (one 80-byte bulk copy per record, completion on an
@@ -22,14 +22,16 @@
 //          no channel predicate;
 //   C      each warp builds, with one ballot, the list of particles that touch its sub-block
 //          (zeroing the weights of its sub-block that lie outside the particle's box), then
-//          walks it: two 16-byte loads bring the lane's four weights, four and a half its nine
-//          edge erfs (both conflict-free by layout: ~7 shared-memory wavefronts per 32 FMAs,
-//          against 22 for the 16 pixel x 2 channel tile of rounds 1-2), eight subtractions form
-//          E[c+1] - E[c], then acc[pixel][channel] += (W amp) * (E[c+1] - E[c]); the factor
-//          1 / dv of the channel is applied once, at the store.
+//          walks it: two 16-byte loads bring the lane's four weights, four 16-byte and four
+//          8-byte loads the three edge erfs of each of its channel pairs (all conflict-free by
+//          layout: ~10 shared-memory wavefronts per 32 FMAs, against 22 for the 16 pixel x
+//          2 channel tile of rounds 1-2), eight subtractions form E[c+1] - E[c], then
+//          acc[pixel][channel] += (W amp) * (E[c+1] - E[c]); the factor 1 / dv of the channel
+//          is applied once, at the store.
 //
 // No atomics on the data path; every voxel is stored exactly once, as 16-byte vector stores
-// (a lane writes 64 contiguous bytes per pixel, a warp 4 x 512).
+// (per pixel and channel-pair index the eight channel groups of a warp write 128 contiguous
+// bytes).
 #pragma once
 
 #include "common.cuh"
@@ -177,16 +179,17 @@ struct ProjArgs {
 // Shared-memory layouts of the per-batch weights and edge erfs, chosen for phase C's vector
 // loads.  W: the 16 weights of a sub-block are contiguous (row of the sub-block major), so the
 // four pixel rows a warp's lanes read are one 128-byte line; rows of W are 16-byte aligned.
-// ES: edge e sits at e + 2 (e / 8): the eight channel groups of a warp start 80 bytes apart,
-// i.e. in eight different 16-byte bank groups (a lane reads the eight edges of its group as
-// four 16-byte loads and the ninth, the first edge of the next group, 80 bytes from its own).
+// ES: the CB + 1 edge erfs of a particle in order.  Lane l of a warp owns pixel row l / 8 of the
+// sub-block and the channel pairs (2g + 16h, 2g + 16h + 1), g = l % 8, h = 0..3: for every h the
+// eight channel groups of a warp read one contiguous 128-byte line of edges (plus the pair's
+// third edge, 16 bytes apart: conflict-free), and at the end store one contiguous 128-byte
+// line of the cube per pixel and h -- whole 32-byte sectors.
 constexpr int W_STRIDE = TILE_PIX + 2;
-constexpr int ES_STRIDE = CB + 2 * (CB / 8) + 2;
+constexpr int ES_STRIDE = CB + 2;
 static_assert(SUB_X == 4 && SUB_Y == 4 && CB == 64, "phase C's register tile is 4 pixels x 8 channels");
 __host__ __device__ constexpr int w_index(int tpx, int tpy) {
   return (((tpx >> 2) * SUBS_Y + (tpy >> 2)) << 4) | ((tpx & 3) << 2) | (tpy & 3);
 }
-__host__ __device__ constexpr int es_pos(int e) { return e + 2 * (e >> 3); }
 
 // What the per-batch set-up leaves for the evaluation and accumulation phases.
 struct SetupBuf {
@@ -205,7 +208,7 @@ struct ProjSmem {
   Record rec[2][PBATCH];
   double W[PBATCH][W_STRIDE];   // kernel integrals x amplitude at w_index(pixel); valid inside the
                                 // particle's box (phase C zeroes the rest of the sub-blocks it visits)
-  double ES[PBATCH][ES_STRIDE]; // the CB + 1 edge erfs of every live particle at es_pos(edge)
+  double ES[PBATCH][ES_STRIDE]; // the CB + 1 edge erfs of every live particle
   double inv_dv[CB];            // (16-byte aligned: read as double2)
   double edge[CB + 1];
   SetupBuf sb[2];  // (two: batch b+1 is set up while batch b is evaluated)
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             if (ok[u]) {
-              sm.ES[pp[u]][es_pos(ee[u])] = ev[u];
+              sm.ES[pp[u]][ee[u]] = ev[u];
               if (COUNT) n_erf += fabs(t[u]) < ERF_SAT;
             }
           }
@@ -491,13 +494,25 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         if (p < nb && S.hlive[p]) {
           const int cs = S.chan[p][0], ce = S.chan[p][1];
           double* row = sm.ES[p];
-          const int e_end = qtr == 3 ? CB + 1 : 16 * qtr + 16;
-          for (int e = 16 * qtr; e < e_end; ++e) {
-            if (gaussian_line) {
-              if (e < cs || e > ce) row[es_pos(e)] = e < cs ? -1.0 : 1.0;
-            } else {
-              row[es_pos(e)] = (double)(min(max(e, cs), ce) - cs);
+          if (gaussian_line) {
+            // eight aligned edge pairs per thread: a pair wholly outside the window is one
+            // 16-byte store, a pair the window's end cuts gets its outside edge alone
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const int e = 16 * qtr + 2 * m;
+              if (e + 1 < cs) {
+                *reinterpret_cast<double2*>(row + e) = make_double2(-1.0, -1.0);
+              } else if (e > ce) {
+                *reinterpret_cast<double2*>(row + e) = make_double2(1.0, 1.0);
+              } else {
+                if (e < cs) row[e] = -1.0;
+                if (e + 1 > ce) row[e + 1] = 1.0;
+              }
             }
+            if (qtr == 3 && ce < CB) row[CB] = 1.0;
+          } else {
+            const int e_end = qtr == 3 ? CB + 1 : 16 * qtr + 16;
+            for (int e = 16 * qtr; e < e_end; ++e) row[e] = (double)(min(max(e, cs), ce) - cs);
           }
         }
       }
@@ -532,58 +547,36 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
       __syncwarp();  // the zeroing above is read by the other lanes below
       uint32_t rel = __ballot_sync(0xffffffffu, visit);
 
-      // ---- phase C: acc[4 pixels][8 channels] += (W amp) (E[c+1] - E[c]) ------------------------
+      // ---- phase C: acc[4 pixels][4 channel pairs] += (W amp) (E[c+1] - E[c]) -------------------
+      // (A version that issued the next half visit's loads ahead of the FMAs measured 2.5 % slower:
+      // the register rotation costs more than the latency it hides.)
       {
         const int pr = lane >> 3, cg = lane & 7;
         const double* wbase = &sm.W[0][sub * SUB_PIX + pr * SUB_Y];
-        const double* ebase = &sm.ES[0][es_pos(8 * cg)];
-        // Software-pipelined in half visits (4 pixels x 4 channels = 16 FMAs each): the loads of
-        // the second half go out before the FMAs of the first, those of the next particle's first
-        // half before the FMAs of the second, so every shared-memory latency is covered by FMAs
-        // of the same warp (four warps per scheduler are too few to cover it between them).
-        if (rel) {
-          int p = __ffs(rel) - 1;
+        const double* ebase = &sm.ES[0][2 * cg];
+        while (rel) {
+          const int p = __ffs(rel) - 1;
           rel &= rel - 1;
           const double2* wp = reinterpret_cast<const double2*>(wbase + p * W_STRIDE);
-          const double2* ep = reinterpret_cast<const double2*>(ebase + p * ES_STRIDE);
-          double2 w01 = wp[0], w23 = wp[1], ea = ep[0], eb = ep[1], ec = ep[2];
-          for (;;) {
-            const double2 ed = ep[3];
-            const double e8 = reinterpret_cast<const double*>(ep)[10];  // = es_pos(8 cg + 8): first edge of the next group
-            const double w[4] = {w01.x, w01.y, w23.x, w23.y};
-            {
-              const double d[4] = {ea.y - ea.x, eb.x - ea.y, eb.y - eb.x, ec.x - eb.y};
+          const double* ep = ebase + p * ES_STRIDE;
+          const double2 w01 = wp[0], w23 = wp[1];
+          double2 e01[4];
+          double e2[4];
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
+          for (int h = 0; h < 4; ++h) {
+            e01[h] = *reinterpret_cast<const double2*>(ep + 16 * h);
+            e2[h] = ep[16 * h + 2];
+          }
+          const double w[4] = {w01.x, w01.y, w23.x, w23.y};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  acc[k][q] = fma(w[k], d[q], acc[k][q]);
-                  if (COUNT) n_upd += (w[k] != 0.0) && (d[q] != 0.0);
-                }
+          for (int h = 0; h < 4; ++h) {
+            const double d0 = e01[h].y - e01[h].x, d1 = e2[h] - e01[h].y;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              acc[k][2 * h] = fma(w[k], d0, acc[k][2 * h]);
+              acc[k][2 * h + 1] = fma(w[k], d1, acc[k][2 * h + 1]);
+              if (COUNT) n_upd += ((w[k] != 0.0) && (d0 != 0.0)) + ((w[k] != 0.0) && (d1 != 0.0));
             }
-            const double d4 = ec.y - ec.x, e5 = ec.y;
-            const bool more = rel != 0;
-            const int pn = more ? __ffs(rel) - 1 : p;
-            rel &= rel - 1;
-            wp = reinterpret_cast<const double2*>(wbase + pn * W_STRIDE);
-            ep = reinterpret_cast<const double2*>(ebase + pn * ES_STRIDE);
-            w01 = wp[0];
-            w23 = wp[1];
-            ea = ep[0];
-            eb = ep[1];
-            ec = ep[2];
-            {
-              const double d[4] = {d4, ed.x - e5, ed.y - ed.x, e8 - ed.y};
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  acc[k][4 + q] = fma(w[k], d[q], acc[k][4 + q]);
-                  if (COUNT) n_upd += (w[k] != 0.0) && (d[q] != 0.0);
-                }
-            }
-            if (!more) break;
-            p = pn;
           }
         }
       }
@@ -592,14 +585,14 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
     }
 
     // ---- one store per voxel: x 1 / dv of the channel (spectral_models.py:139), then
-    // out = (in + acc) / px_area ----------------------------------------------------------
+    // out = (in + acc) / px_area; per pixel and h the eight channel groups of a warp write one
+    // contiguous 128-byte line ------------------------------------------------------------
     {
       const int pr = lane >> 3, cg = lane & 7;
       const int tpx = (sub / SUBS_Y) * SUB_X + pr, tpy0 = (sub % SUBS_Y) * SUB_Y;
-      const double2* idv = reinterpret_cast<const double2*>(&sm.inv_dv[8 * cg]);
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        const double2 i2 = idv[h];
+        const double2 i2 = *reinterpret_cast<const double2*>(&sm.inv_dv[2 * cg + 16 * h]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           acc[k][2 * h] *= i2.x;
@@ -607,12 +600,12 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         }
       }
       if (it.slot >= 0) {
-        double* dst = a.partials + (size_t)it.slot * TILE_PIX * CB + 8 * cg;
+        double* dst = a.partials + (size_t)it.slot * TILE_PIX * CB + 2 * cg;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
           for (int h = 0; h < 4; ++h)
-            *reinterpret_cast<double2*>(dst + (size_t)(tpx * TILE_Y + tpy0 + k) * CB + 2 * h) =
+            *reinterpret_cast<double2*>(dst + (size_t)(tpx * TILE_Y + tpy0 + k) * CB + 16 * h) =
                 make_double2(acc[k][2 * h], acc[k][2 * h + 1]);
       } else {
         const int gx = x0 + tpx;
@@ -620,13 +613,13 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         for (int k = 0; k < 4; ++k) {
           const int gy = y0 + tpy0 + k;
           if (gx < g.x_hi && gy < g.ny) {
-            double* dst = a.slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + 8 * cg;
+            double* dst = a.slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + 2 * cg;
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-              const int cl = 8 * cg + 2 * h;  // first channel of the pair within the brick
+              const int cl = 2 * cg + 16 * h;  // first channel of the pair within the brick
               const int nvalid = cl < clo ? 0 : max(0, min(2, nch - cl));
               if (nvalid > 0)
-                store2(dst + 2 * h, acc[k][2 * h], acc[k][2 * h + 1], nvalid, a.px_area, !a.zeroed,
+                store2(dst + 16 * h, acc[k][2 * h], acc[k][2 * h + 1], nvalid, a.px_area, !a.zeroed,
                        (g.C & 1) == 0);
             }
           }

@@ -66,8 +66,17 @@ __device__ __forceinline__ bool next_item(const StreamArgs& a, int lane, Item& i
 
 // ------------------------------------------------------------------------------- column
 __host__ __device__ inline int column_acc_stride(int C) { return C >= CSB ? CSB : (C + 63) / 64 * 64; }
+// what the column kernel needs of a particle, staged per warp for its batch of 32: 32 bytes,
+// read back as two broadcast 16-byte loads (seven shuffles per particle before)
+struct __align__(16) ColRec {
+  double v, sc;   // line centre, sgn / (sqrt(2) sigma)
+  double amp;
+  uint32_t cw;    // c_first | c_last << 16
+  uint32_t pad;
+};
 inline size_t column_smem_bytes(int C) {
-  return ((size_t)STREAM_WARPS * column_acc_stride(C) + ERFC_DOUBLES) * sizeof(double);
+  return ((size_t)STREAM_WARPS * column_acc_stride(C) + ERFC_DOUBLES) * sizeof(double) +
+         (size_t)STREAM_WARPS * 32 * sizeof(ColRec);
 }
 
 template <bool COUNT>
@@ -81,6 +90,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs
   const int acc_stride = column_acc_stride(g.C);
   double* acc = col_smem + warp * acc_stride;
   double* erf_table = col_smem + STREAM_WARPS * acc_stride;
+  ColRec* crec = reinterpret_cast<ColRec*>(erf_table + ERFC_DOUBLES) + warp * 32;  // (16-byte aligned: even counts)
   const double sgn = g.edges_increasing ? 1.0 : -1.0;
   for (int c = lane; c < acc_stride; c += 32) acc[c] = 0.0;
   for (int k = threadIdx.x; k < ERFC_DOUBLES; k += STREAM_THREADS) erf_table[k] = g_erf_table_compact[k];
@@ -96,20 +106,24 @@ __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs
     int lo = CSB, hi = 0;  // touched range of the accumulator
     for (uint32_t base = it.begin; base < it.end; base += 32) {
       const int nb = (int)min(32u, it.end - base);
-      double v_l = 0.0, inv_l = 0.0, amp_l = 0.0;
-      uint32_t cw_l = 0;
+      __syncwarp();  // (the previous batch's records are no longer read)
       if (lane < nb) {
         const Record* r = a.records + (uint32_t)a.pairs[base + lane];
-        v_l = r->v;
-        inv_l = r->inv_s;
-        amp_l = r->amp;
-        cw_l = (uint32_t)r->c_first | ((uint32_t)r->c_last << 16);
+        ColRec c;
+        c.v = r->v;
+        c.sc = sgn * r->inv_s;
+        c.amp = r->amp;
+        c.cw = (uint32_t)r->c_first | ((uint32_t)r->c_last << 16);
+        c.pad = 0;
+        crec[lane] = c;
       }
+      __syncwarp();
       for (int k = 0; k < nb; ++k) {
-        const double v = __shfl_sync(0xffffffffu, v_l, k);
-        const double sc = sgn * __shfl_sync(0xffffffffu, inv_l, k);
-        const double amp = __shfl_sync(0xffffffffu, amp_l, k);
-        const uint32_t cwk = __shfl_sync(0xffffffffu, cw_l, k);
+        const double2 vs = *reinterpret_cast<const double2*>(&crec[k].v);
+        const int4 aw = *reinterpret_cast<const int4*>(&crec[k].amp);
+        const double v = vs.x, sc = vs.y;
+        const double amp = __hiloint2double(aw.y, aw.x);
+        const uint32_t cwk = (uint32_t)aw.z;
         // the particle's live window (plan.cuh: channel_window, exact predicates) cut to the
         // superblock: channels [cs, ce)
         const int cs = max((int)(cwk & 0xffffu) - cbase, 0), ce = min((int)(cwk >> 16) + 1 - cbase, nchs);

@@ -29,10 +29,20 @@ __device__ double g_erf_table[ERF_NINT * ERF_NCOEF];
 // so the compact table holds one 16-byte row per interval and the evaluator derives the rest.
 __device__ double g_erf_table_compact[ERFC_DOUBLES];
 
+// Exactly +-1 for |t| >= ERF_SAT without a test: the clamped argument lands in the last row,
+// whose erf(x0) is 1.0 in float64 and whose A u is below 2^-58.  Never above 1: the truncated
+// series stays below erf's distance from 1 everywhere (its remainder carries exp(-x0^2) too).
+// The interval index comes from the float64 rounding trick (add 2^52 + 2^51: the sum's low
+// mantissa word is the integer, the sum minus the constant its float64 value) instead of a
+// float64 -> int32 -> float64 round trip through the conversion unit; any index whose centre is
+// within 1/128 of |t| serves, so round-to-nearest of 64 |t| - 1/2 is as good as the floor.
 __device__ __forceinline__ double erf_tab_compact(const double* __restrict__ table, double t) {
-  const double a = fmin(fabs(t), ERF_SAT);
-  const int i = (int)(a * ERFC_INV_W);  // a = ERF_SAT lands in the last (saturated) interval
-  const double x0 = ((double)i + 0.5) * (1.0 / ERFC_INV_W);
+  constexpr double MAGIC = 6755399441055744.0;  // 2^52 + 2^51
+  double a = fabs(t);
+  a = a < ERF_SAT ? a : ERF_SAT;  // (NaN -> ERF_SAT, as fmin did)
+  const double r_ = fma(a, (double)ERFC_INV_W, -0.5) + MAGIC;  // = MAGIC + round(64 a - 1/2)
+  const int i = __double2loint(r_);  // in [0, 6 ERFC_INV_W]
+  const double x0 = fma(r_ - MAGIC, 1.0 / ERFC_INV_W, 0.5 / ERFC_INV_W);
   const double u = a - x0;
   const double2 fa = reinterpret_cast<const double2*>(table)[i];  // {erf(x0), 2/sqrt(pi) exp(-x0^2)}
   // erf(x0 + u) = erf(x0) + A u (1 + u (k2 + u (k3 + u (k4 + u k5)))):
@@ -45,9 +55,7 @@ __device__ __forceinline__ double erf_tab_compact(const double* __restrict__ tab
   p = fma(p, u, k3);
   p = fma(p, u, -x0);
   p = fma(p, u, 1.0);
-  double r = fma(fa.y * u, p, fa.x);
-  r = fmin(r, 1.0);
-  r = fabs(t) >= ERF_SAT ? 1.0 : r;
+  const double r = fma(fa.y * u, p, fa.x);
   return copysign(r, t);
 }
 

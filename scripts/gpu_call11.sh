@@ -1,0 +1,7 @@
+#!/bin/bash
+# A/B: default (compact erf rows of 16 bytes + pipelined phase C) against lib_var_head.so (the
+# commit before) and lib_var_old.so (round-2 evidence state); quick parity first
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -p no:cacheprovider -k "not full_size" 2>&1 | tail -3
+WORKLOADS="cfg2 cfg3 cfg4" STEPS=5 bash scripts/ab_bench.sh

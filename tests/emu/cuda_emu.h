@@ -152,6 +152,11 @@ inline int __double2hiint(double d) {
   memcpy(&b, &d, 8);
   return (int)(b >> 32);
 }
+inline int __double2loint(double d) {
+  uint64_t b;
+  memcpy(&b, &d, 8);
+  return (int)(uint32_t)b;
+}
 inline double __longlong_as_double(long long v) {
   double d;
   memcpy(&d, &v, 8);
