@@ -28,7 +28,10 @@ constexpr int N_SUB = TILE_PIX / SUB_PIX;      // sub-blocks per tile
 constexpr int PROJ_WARPS = N_SUB;              // warp = sub-block
 constexpr int PROJ_THREADS = PROJ_WARPS * 32;
 // resident CTAs per SM: register-limited (16 warps per SM at 128 registers)
-constexpr int PROJ_CTAS_PER_SM = 512 / PROJ_THREADS;
+#ifndef MTN_PROJ_CTAS
+#define MTN_PROJ_CTAS (512 / PROJ_THREADS)
+#endif
+constexpr int PROJ_CTAS_PER_SM = MTN_PROJ_CTAS;
 constexpr int PBATCH = 32;            // particle records staged per batch (= one per lane)
 static_assert(PBATCH == 32, "the batch is indexed by lane in several places");
 

@@ -185,7 +185,18 @@ struct ProjArgs {
 // third edge, 16 bytes apart: conflict-free), and at the end store one contiguous 128-byte
 // line of the cube per pixel and h -- whole 32-byte sectors.
 constexpr int W_STRIDE = TILE_PIX + 2;
+#ifndef MTN_TILE_IL
+#define MTN_TILE_IL 1
+#endif
+#if MTN_TILE_IL
 constexpr int ES_STRIDE = CB + 2;
+__host__ __device__ constexpr int es_pos(int e) { return e; }
+#else
+// (experiment: lane owns eight ADJACENT channels; edge e sits at e + 2 (e / 8) so that the eight
+// channel groups start 80 bytes apart -- fewer loads per visit, but 16-byte stores 64 bytes apart)
+constexpr int ES_STRIDE = CB + 2 * (CB / 8) + 2;
+__host__ __device__ constexpr int es_pos(int e) { return e + 2 * (e >> 3); }
+#endif
 static_assert(SUB_X == 4 && SUB_Y == 4 && CB == 64, "phase C's register tile is 4 pixels x 8 channels");
 __host__ __device__ constexpr int w_index(int tpx, int tpy) {
   return (((tpx >> 2) * SUBS_Y + (tpy >> 2)) << 4) | ((tpx & 3) << 2) | (tpy & 3);
@@ -206,9 +217,13 @@ struct SetupBuf {
 
 struct ProjSmem {
   Record rec[2][PBATCH];
-  double W[PBATCH][W_STRIDE];   // kernel integrals x amplitude at w_index(pixel); valid inside the
-                                // particle's box (phase C zeroes the rest of the sub-blocks it visits)
+  double W[PBATCH][W_STRIDE];   // kernel integrals x amplitude at w_index(pixel): zero outside the
+                                // particle's box (every warp clears its sub-block's share after use)
   double ES[PBATCH][ES_STRIDE]; // the CB + 1 edge erfs of every live particle
+  double erf_table[ERFC_DOUBLES];  // copy of the compact erf table (tables.cuh): the edge erfs read it here
+                                   // instead of the degree-9 table through L1, whose five loads per
+                                   // evaluation, each lane in its own row, kept the L1 tag stage busy for
+                                   // most of the kernel (22 tag look-ups per load instruction)
   double inv_dv[CB];            // (16-byte aligned: read as double2)
   double edge[CB + 1];
   SetupBuf sb[2];  // (two: batch b+1 is set up while batch b is evaluated)
@@ -273,6 +288,8 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
     mbar_init(&sm.bar[1], 1);
     mbar_fence_init();
   }
+  for (int k = tid; k < PBATCH * W_STRIDE; k += PROJ_THREADS) (&sm.W[0][0])[k] = 0.0;
+  for (int k = tid; k < ERFC_DOUBLES; k += PROJ_THREADS) sm.erf_table[k] = g_erf_table_compact[k];
   __syncthreads();
   uint32_t phase = 0;  // bit k: parity to wait for on bar[k]
   unsigned long long n_upd = 0, n_w = 0, n_erf = 0;
@@ -474,11 +491,11 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
             t[u] = (sm.edge[e] - r.v) * (sgn * r.inv_s);
           }
 #pragma unroll
-          for (int u = 0; u < 2; ++u) ev[u] = erf_tab(t[u]);
+          for (int u = 0; u < 2; ++u) ev[u] = erf_tab_compact(sm.erf_table, t[u]);
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             if (ok[u]) {
-              sm.ES[pp[u]][ee[u]] = ev[u];
+              sm.ES[pp[u]][es_pos(ee[u])] = ev[u];
               if (COUNT) n_erf += fabs(t[u]) < ERF_SAT;
             }
           }
@@ -501,65 +518,56 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
             for (int m = 0; m < 8; ++m) {
               const int e = 16 * qtr + 2 * m;
               if (e + 1 < cs) {
-                *reinterpret_cast<double2*>(row + e) = make_double2(-1.0, -1.0);
+                *reinterpret_cast<double2*>(row + es_pos(e)) = make_double2(-1.0, -1.0);
               } else if (e > ce) {
-                *reinterpret_cast<double2*>(row + e) = make_double2(1.0, 1.0);
+                *reinterpret_cast<double2*>(row + es_pos(e)) = make_double2(1.0, 1.0);
               } else {
-                if (e < cs) row[e] = -1.0;
-                if (e + 1 > ce) row[e + 1] = 1.0;
+                if (e < cs) row[es_pos(e)] = -1.0;
+                if (e + 1 > ce) row[es_pos(e + 1)] = 1.0;
               }
             }
-            if (qtr == 3 && ce < CB) row[CB] = 1.0;
+            if (qtr == 3 && ce < CB) row[es_pos(CB)] = 1.0;
           } else {
             const int e_end = qtr == 3 ? CB + 1 : 16 * qtr + 16;
-            for (int e = 16 * qtr; e < e_end; ++e) row[e] = (double)(min(max(e, cs), ce) - cs);
+            for (int e = 16 * qtr; e < e_end; ++e) row[es_pos(e)] = (double)(min(max(e, cs), ce) - cs);
           }
         }
       }
       __syncthreads();
 
-      // ---- warp-private list: which particles touch my sub-block.  Lane = particle: the 16
-      // weights of my sub-block that lie outside the particle's box are stale shared memory --
-      // zero them (only this warp reads them), so phase C needs no pixel predicate either.
+      // ---- warp-private list: which particles touch my sub-block.  Lane = particle: W is zero
+      // wherever phase A did not write (outside the box) and where the kernel's support ends, so
+      // "any of my sub-block's 16 weights non-zero" is the whole test.
       bool visit = false;
       if (lane < nb && S.hlive[lane]) {
-        const int bx0 = S.box[lane][0], bx1 = bx0 + S.box[lane][1];
-        const int by0 = S.box[lane][2], by1 = by0 + S.box[lane][3];
-        double* wsub = &sm.W[lane][sub * SUB_PIX];
-        uint32_t inbox = 0, nonzero = 0;
+        const double2* wsub = reinterpret_cast<const double2*>(&sm.W[lane][sub * SUB_PIX]);
 #pragma unroll
-        for (int j = 0; j < SUB_PIX; ++j) {
-          const int tpx = (sub / SUBS_Y) * SUB_X + j / SUB_Y, tpy = (sub % SUBS_Y) * SUB_Y + j % SUB_Y;
-          if (tpx >= bx0 && tpx < bx1 && tpy >= by0 && tpy < by1) {
-            inbox |= 1u << j;
-            // (the W != 0 test drops the box pixels outside the kernel's support: fewer warps
-            // visit a particle for nothing)
-            if (wsub[j] != 0.0) nonzero |= 1u << j;
-          }
-        }
-        visit = nonzero != 0;
-        if (visit && inbox != 0xffffu) {
-#pragma unroll
-          for (int j = 0; j < SUB_PIX; ++j)
-            if (!(inbox & (1u << j))) wsub[j] = 0.0;
+        for (int j = 0; j < SUB_PIX / 2; ++j) {
+          const double2 w2 = wsub[j];
+          visit |= (w2.x != 0.0) | (w2.y != 0.0);
         }
       }
-      __syncwarp();  // the zeroing above is read by the other lanes below
       uint32_t rel = __ballot_sync(0xffffffffu, visit);
 
-      // ---- phase C: acc[4 pixels][4 channel pairs] += (W amp) (E[c+1] - E[c]) -------------------
+      // ---- phase C: acc[4 pixels][8 channels] += (W amp) (E[c+1] - E[c]) ------------------------
       // (A version that issued the next half visit's loads ahead of the FMAs measured 2.5 % slower:
       // the register rotation costs more than the latency it hides.)
       {
         const int pr = lane >> 3, cg = lane & 7;
         const double* wbase = &sm.W[0][sub * SUB_PIX + pr * SUB_Y];
+#if MTN_TILE_IL
         const double* ebase = &sm.ES[0][2 * cg];
+#else
+        const double* ebase = &sm.ES[0][es_pos(8 * cg)];
+#endif
         while (rel) {
           const int p = __ffs(rel) - 1;
           rel &= rel - 1;
           const double2* wp = reinterpret_cast<const double2*>(wbase + p * W_STRIDE);
           const double* ep = ebase + p * ES_STRIDE;
           const double2 w01 = wp[0], w23 = wp[1];
+          double d[8];
+#if MTN_TILE_IL
           double2 e01[4];
           double e2[4];
 #pragma unroll
@@ -567,17 +575,36 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
             e01[h] = *reinterpret_cast<const double2*>(ep + 16 * h);
             e2[h] = ep[16 * h + 2];
           }
-          const double w[4] = {w01.x, w01.y, w23.x, w23.y};
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            const double d0 = e01[h].y - e01[h].x, d1 = e2[h] - e01[h].y;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              acc[k][2 * h] = fma(w[k], d0, acc[k][2 * h]);
-              acc[k][2 * h + 1] = fma(w[k], d1, acc[k][2 * h + 1]);
-              if (COUNT) n_upd += ((w[k] != 0.0) && (d0 != 0.0)) + ((w[k] != 0.0) && (d1 != 0.0));
-            }
+            d[2 * h] = e01[h].y - e01[h].x;
+            d[2 * h + 1] = e2[h] - e01[h].y;
           }
+#else
+          {
+            const double2* e2p = reinterpret_cast<const double2*>(ep);
+            const double2 ea = e2p[0], eb = e2p[1], ec = e2p[2], ed = e2p[3];
+            const double e8 = ep[10];  // = es_pos(8 cg + 8): first edge of the next group
+            d[0] = ea.y - ea.x; d[1] = eb.x - ea.y; d[2] = eb.y - eb.x; d[3] = ec.x - eb.y;
+            d[4] = ec.y - ec.x; d[5] = ed.x - ec.y; d[6] = ed.y - ed.x; d[7] = e8 - ed.y;
+          }
+#endif
+          const double w[4] = {w01.x, w01.y, w23.x, w23.y};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              acc[k][q] = fma(w[k], d[q], acc[k][q]);
+              if (COUNT) n_upd += (w[k] != 0.0) && (d[q] != 0.0);
+            }
+        }
+        // my sub-block's share of W back to zero (the invariant the mask above relies on): 32
+        // particles x 128 bytes, eight 16-byte stores per lane, after my own last read of it
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const int idx = m * 32 + lane;
+          *reinterpret_cast<double2*>(&sm.W[idx >> 3][sub * SUB_PIX + 2 * (idx & 7)]) = make_double2(0.0, 0.0);
         }
       }
       __syncthreads();  // W, ES, boxes and rec[buf] are free again
@@ -585,14 +612,20 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
     }
 
     // ---- one store per voxel: x 1 / dv of the channel (spectral_models.py:139), then
-    // out = (in + acc) / px_area; per pixel and h the eight channel groups of a warp write one
-    // contiguous 128-byte line ------------------------------------------------------------
+    // out = (in + acc) / px_area; accumulators (2h, 2h + 1) of a lane are the channel pair starting
+    // at pair_ch(h): per pixel and h the eight channel groups of a warp write one contiguous
+    // 128-byte line -----------------------------------------------------------------------
     {
       const int pr = lane >> 3, cg = lane & 7;
       const int tpx = (sub / SUBS_Y) * SUB_X + pr, tpy0 = (sub % SUBS_Y) * SUB_Y;
+#if MTN_TILE_IL
+      auto pair_ch = [&](int h) { return 2 * cg + 16 * h; };
+#else
+      auto pair_ch = [&](int h) { return 8 * cg + 2 * h; };
+#endif
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        const double2 i2 = *reinterpret_cast<const double2*>(&sm.inv_dv[2 * cg + 16 * h]);
+        const double2 i2 = *reinterpret_cast<const double2*>(&sm.inv_dv[pair_ch(h)]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           acc[k][2 * h] *= i2.x;
@@ -600,12 +633,12 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         }
       }
       if (it.slot >= 0) {
-        double* dst = a.partials + (size_t)it.slot * TILE_PIX * CB + 2 * cg;
+        double* dst = a.partials + (size_t)it.slot * TILE_PIX * CB;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
           for (int h = 0; h < 4; ++h)
-            *reinterpret_cast<double2*>(dst + (size_t)(tpx * TILE_Y + tpy0 + k) * CB + 16 * h) =
+            *reinterpret_cast<double2*>(dst + (size_t)(tpx * TILE_Y + tpy0 + k) * CB + pair_ch(h)) =
                 make_double2(acc[k][2 * h], acc[k][2 * h + 1]);
       } else {
         const int gx = x0 + tpx;
@@ -613,13 +646,13 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         for (int k = 0; k < 4; ++k) {
           const int gy = y0 + tpy0 + k;
           if (gx < g.x_hi && gy < g.ny) {
-            double* dst = a.slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0 + 2 * cg;
+            double* dst = a.slab + ((size_t)(gx - g.x_lo) * g.ny + gy) * g.C + c0;
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-              const int cl = 2 * cg + 16 * h;  // first channel of the pair within the brick
+              const int cl = pair_ch(h);  // first channel of the pair within the brick
               const int nvalid = cl < clo ? 0 : max(0, min(2, nch - cl));
               if (nvalid > 0)
-                store2(dst + 16 * h, acc[k][2 * h], acc[k][2 * h + 1], nvalid, a.px_area, !a.zeroed,
+                store2(dst + cl, acc[k][2 * h], acc[k][2 * h + 1], nvalid, a.px_area, !a.zeroed,
                        (g.C & 1) == 0);
             }
           }
