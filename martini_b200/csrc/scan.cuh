@@ -110,13 +110,23 @@ __global__ void __launch_bounds__(1024) scan3_sums_inplace(int64_t* __restrict__
                                                            int64_t* __restrict__ total_out) {
   __shared__ int64_t sm[33];
   int64_t* sums = blockIdx.x == 0 ? a : (blockIdx.x == 1 ? b : c);
+  constexpr int PER = 8;  // consecutive entries per thread and round (39 063 block sums at 1e7 particles)
   int64_t carry = 0;
-  for (int64_t base = 0; base < m; base += blockDim.x) {
-    const int64_t i = base + threadIdx.x;
-    const int64_t x = i < m ? sums[i] : 0;
+  for (int64_t base = 0; base < m; base += (int64_t)blockDim.x * PER) {
+    const int64_t i0 = base + (int64_t)threadIdx.x * PER;
+    int64_t v[PER], s = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      v[k] = i0 + k < m ? sums[i0 + k] : 0;
+      s += v[k];
+    }
     int64_t total;
-    const int64_t ex = block_excl_scan(x, sm, &total);
-    if (i < m) sums[i] = carry + ex;
+    int64_t run = carry + block_excl_scan(s, sm, &total);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      if (i0 + k < m) sums[i0 + k] = run;
+      run += v[k];
+    }
     carry += total;
   }
   if (threadIdx.x == 0) total_out[blockIdx.x] = carry;

@@ -7,7 +7,7 @@
 // 2 x 10).  Per pass: (1) one digit histogram per block tile of SORT_TILE pairs, (2) one
 // exclusive scan over the digit-major histogram matrix, (3) a scatter in which the block first
 // orders its tile by digit in shared memory -- every warp walks its contiguous share in order
-// and ranks equal digits with __match_any_sync, the warps' counts are prefix-summed per digit
+// and ranks equal digits with one ballot per digit bit, the warps' counts are prefix-summed per digit
 // -- and then writes each digit's run to its place in one piece: runs of SORT_TILE / 2^bits
 // pairs (64 to 512 bytes) instead of the single 8-byte stores of rounds 1-2, which cost four
 // times their bytes in 32-byte sectors (131 us against 32 us per pass of 9.3e6 pairs, the
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_count_kernel(
   for (int d = threadIdx.x; d < bins; d += SORT_THREADS) hist[(int64_t)d * n_tiles + blockIdx.x] = cnt[d];
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(
+__global__ void __launch_bounds__(SORT_THREADS, 2) radix_scatter_kernel(
     const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int64_t n, int shift, int bits,
     int64_t n_tiles, const uint32_t* __restrict__ offs) {
   MTN_DYN_SMEM(unsigned char, smem_raw);
@@ -88,7 +88,9 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(
   __syncthreads();
 
   // rank inside the warp's share: pairs of equal digit, in order
-  uint16_t rank[SORT_PER_THREAD];
+  uint32_t rank2[SORT_PER_THREAD / 2];  // two 16-bit ranks per register
+#pragma unroll
+  for (int s = 0; s < SORT_PER_THREAD / 2; ++s) rank2[s] = 0;
   uint32_t* wcnt = cnt + warp * bins;
   const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
@@ -96,14 +98,22 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(
     const bool valid = warp * SORT_IPW + s * 32 + lane < n_valid;
     // invalid lanes get private digits so they never match a real one
     const uint32_t d = valid ? ((uint32_t)(kv[s] >> shift) & mask) : (uint32_t)(bins + lane);
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    // lanes holding my digit, one ballot per digit bit (a fixed ~2 instructions per bit:
+    // __match_any_sync takes one pass per DISTINCT value in the warp, ~30 of them for a random
+    // 9-bit digit, and was most of this kernel)
+    uint32_t peers = __ballot_sync(0xffffffffu, valid);
+    for (int k = 0; k < bits; ++k) {
+      const uint32_t bk = __ballot_sync(0xffffffffu, (d >> k) & 1u);
+      peers &= ((d >> k) & 1u) ? bk : ~bk;
+    }
+    if (!valid) peers = 1u << lane;
     const uint32_t r = __popc(peers & lt);
     uint32_t before = 0;
     if (valid) before = wcnt[d];
     __syncwarp();
     if (valid && r == 0) wcnt[d] = before + __popc(peers);
     __syncwarp();
-    rank[s] = (uint16_t)(before + r);
+    rank2[s >> 1] |= (before + r) << (16 * (s & 1));
   }
   __syncthreads();
 
@@ -112,9 +122,10 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(
     const int per = (bins + SORT_THREADS - 1) / SORT_THREADS;  // consecutive digits per thread (<= 4)
     uint32_t tot[4] = {0, 0, 0, 0};
     uint32_t mine = 0;
-    for (int k = 0; k < per; ++k) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
       const int d = tid * per + k;
-      if (d < bins) {
+      if (k < per && d < bins) {
         uint32_t run = 0;
         for (int w = 0; w < SORT_WARPS; ++w) {
           const uint32_t c = cnt[w * bins + d];
@@ -127,9 +138,10 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(
     }
     uint32_t total;
     uint32_t start = block_excl_scan(mine, scan_sm, &total);
-    for (int k = 0; k < per; ++k) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
       const int d = tid * per + k;
-      if (d < bins) {
+      if (k < per && d < bins) {
         for (int w = 0; w < SORT_WARPS; ++w) cnt[w * bins + d] += start;
         delta[d] = offs[(int64_t)d * n_tiles + blockIdx.x] - start;  // (mod 2^32)
         start += tot[k];
@@ -142,7 +154,7 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(
   for (int s = 0; s < SORT_PER_THREAD; ++s) {
     if (warp * SORT_IPW + s * 32 + lane < n_valid) {
       const uint32_t d = (uint32_t)(kv[s] >> shift) & mask;
-      stage[wcnt[d] + rank[s]] = kv[s];
+      stage[wcnt[d] + ((rank2[s >> 1] >> (16 * (s & 1))) & 0xffffu)] = kv[s];
     }
   }
   __syncthreads();
