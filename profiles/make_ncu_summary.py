@@ -60,7 +60,7 @@ def summarise(rep, workload):
 
 
 def main():
-    path = os.path.join(HERE, "ncu_summaries.json")
+    path = os.environ.get("NCU_SUMMARY_OUT") or os.path.join(HERE, "ncu_summaries.json")  # (the GPU box writes under gpurun_out/)
     db = json.load(open(path)) if os.path.exists(path) else {"captures": []}
     args = sys.argv[1:]
     for rep, workload in zip(args[0::2], args[1::2]):
