@@ -109,25 +109,38 @@ __global__ void __launch_bounds__(1024) scan3_sums_inplace(int64_t* __restrict__
                                                            int64_t* __restrict__ c, int64_t m,
                                                            int64_t* __restrict__ total_out) {
   __shared__ int64_t sm[33];
+  constexpr int PER = 4;  // consecutive entries per thread and round, staged through shared memory
+  __shared__ int64_t stage[1024 * PER];  // so that the global loads and stores of a round are coalesced
   int64_t* sums = blockIdx.x == 0 ? a : (blockIdx.x == 1 ? b : c);
-  // consecutive entries per thread, sized so that ordinary inputs take ONE round (39 063 block
-  // sums at 1e7 particles: 39 per thread; every round costs a load latency and three barriers)
-  const int per = (int)max((int64_t)1, min((int64_t)64, (m + blockDim.x - 1) / blockDim.x));
   int64_t carry = 0;
-  for (int64_t base = 0; base < m; base += (int64_t)blockDim.x * per) {
-    const int64_t i0 = base + (int64_t)threadIdx.x * per;
-    int64_t s = 0;
-    for (int k = 0; k < per; ++k) s += i0 + k < m ? sums[i0 + k] : 0;
+  for (int64_t base = 0; base < m; base += (int64_t)blockDim.x * PER) {
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int64_t i = base + (int64_t)k * blockDim.x + threadIdx.x;
+      stage[k * blockDim.x + threadIdx.x] = i < m ? sums[i] : 0;
+    }
+    __syncthreads();
+    int64_t v[PER], s = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      v[k] = stage[threadIdx.x * PER + k];
+      s += v[k];
+    }
     int64_t total;
     int64_t run = carry + block_excl_scan(s, sm, &total);
-    for (int k = 0; k < per; ++k) {
-      if (i0 + k < m) {
-        const int64_t v = sums[i0 + k];
-        sums[i0 + k] = run;
-        run += v;
-      }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      stage[threadIdx.x * PER + k] = run;
+      run += v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int64_t i = base + (int64_t)k * blockDim.x + threadIdx.x;
+      if (i < m) sums[i] = stage[k * blockDim.x + threadIdx.x];
     }
     carry += total;
+    __syncthreads();
   }
   if (threadIdx.x == 0) total_out[blockIdx.x] = carry;
 }

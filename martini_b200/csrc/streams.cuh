@@ -67,16 +67,16 @@ __device__ __forceinline__ bool next_item(const StreamArgs& a, int lane, Item& i
 // ------------------------------------------------------------------------------- column
 __host__ __device__ inline int column_acc_stride(int C) { return C >= CSB ? CSB : (C + 63) / 64 * 64; }
 // what the column kernel needs of a particle, staged per warp for its batch of 32: 32 bytes,
-// read back as two broadcast 16-byte loads (seven shuffles per particle before)
+// read back as two 16-byte loads
 struct __align__(16) ColRec {
-  double v, sc;   // line centre, sgn / (sqrt(2) sigma)
+  double v, sc;    // line centre, sgn / (sqrt(2) sigma)
   double amp;
-  uint32_t cw;    // c_first | c_last << 16
-  uint32_t pad;
+  uint32_t cw;     // live channels of the superblock: cs | ce << 16  (channels [cs, ce), edges cs..ce)
+  uint32_t start;  // first item of the particle's edge run in the batch's enumeration
 };
 inline size_t column_smem_bytes(int C) {
   return ((size_t)STREAM_WARPS * column_acc_stride(C) + ERFC_DOUBLES) * sizeof(double) +
-         (size_t)STREAM_WARPS * 32 * sizeof(ColRec);
+         (size_t)STREAM_WARPS * 32 * sizeof(ColRec) + (size_t)STREAM_WARPS * 32;  // + owner lists
 }
 
 template <bool COUNT>
@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs
   double* acc = col_smem + warp * acc_stride;
   double* erf_table = col_smem + STREAM_WARPS * acc_stride;
   ColRec* crec = reinterpret_cast<ColRec*>(erf_table + ERFC_DOUBLES) + warp * 32;  // (16-byte aligned: even counts)
+  uint8_t* owner = reinterpret_cast<uint8_t*>(reinterpret_cast<ColRec*>(erf_table + ERFC_DOUBLES) + STREAM_WARPS * 32) + warp * 32;
   const double sgn = g.edges_increasing ? 1.0 : -1.0;
   for (int c = lane; c < acc_stride; c += 32) acc[c] = 0.0;
   for (int k = threadIdx.x; k < ERFC_DOUBLES; k += STREAM_THREADS) erf_table[k] = g_erf_table_compact[k];
@@ -104,78 +105,81 @@ __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs
     const double* edge = a.edges + cbase;
     const double* idv = a.inv_dv + cbase;
     int lo = CSB, hi = 0;  // touched range of the accumulator
+    // The edges of the batch's particles are enumerated as ONE run of items (particle 0's live
+    // edges, particle 1's, ...) and handed to the lanes 32 at a time, so every erf evaluation
+    // of a warp has 32 (31) live lanes whatever the windows' lengths: the ~42-edge windows of
+    // config 3 used to take two 32-lane chains each, the second a third full.  A step advances
+    // by 31 items: lane 31 only supplies the upper edge of lane 30's channel and comes back as
+    // lane 0 of the next step.  Lanes of different particles may hold the same channel; they
+    // add to the accumulator particle by particle, in index order (deterministic, the order of
+    // the reference's sum).
+    const uint32_t lt = (1u << lane) - 1u;
     for (uint32_t base = it.begin; base < it.end; base += 32) {
       const int nb = (int)min(32u, it.end - base);
       __syncwarp();  // (the previous batch's records are no longer read)
-      if (lane < nb) {
-        const Record* r = a.records + (uint32_t)a.pairs[base + lane];
+      uint32_t ne = 0, my_start;
+      {
+        int cs = 0, ce = 0;
         ColRec c;
-        c.v = r->v;
-        c.sc = sgn * r->inv_s;
-        c.amp = r->amp;
-        c.cw = (uint32_t)r->c_first | ((uint32_t)r->c_last << 16);
-        c.pad = 0;
+        c.v = c.sc = c.amp = 0.0;
+        if (lane < nb) {
+          const Record* r = a.records + (uint32_t)a.pairs[base + lane];
+          c.v = r->v;
+          c.sc = sgn * r->inv_s;
+          c.amp = r->amp;
+          // the particle's live window (plan.cuh: channel_window, exact predicates) cut to the
+          // superblock: channels [cs, ce)
+          cs = max((int)r->c_first - cbase, 0);
+          ce = min((int)r->c_last + 1 - cbase, nchs);
+          if (cs >= ce) cs = ce = 0;
+        }
+        ne = ce > cs ? (uint32_t)(ce - cs + 1) : 0u;
+        const uint32_t incl = warp_incl_scan_u32(ne, lane);
+        my_start = incl - ne;
+        c.cw = (uint32_t)cs | ((uint32_t)ce << 16);
+        c.start = my_start;
         crec[lane] = c;
+        const uint32_t nonempty = __ballot_sync(0xffffffffu, ne != 0);
+        if (ne != 0) {
+          owner[__popc(nonempty & lt)] = (uint8_t)lane;
+          lo = min(lo, cs);
+          hi = max(hi, ce);
+        }
+        if (COUNT) n_w += ne != 0;
       }
+      const uint32_t total = __shfl_sync(0xffffffffu, my_start + ne, 31);
+      lo = (int)__reduce_min_sync(0xffffffffu, (unsigned)lo);
+      hi = (int)__reduce_max_sync(0xffffffffu, (unsigned)hi);
       __syncwarp();
-      for (int k = 0; k < nb; ++k) {
-        const double2 vs = *reinterpret_cast<const double2*>(&crec[k].v);
-        const int4 aw = *reinterpret_cast<const int4*>(&crec[k].amp);
-        const double v = vs.x, sc = vs.y;
-        const double amp = __hiloint2double(aw.y, aw.x);
-        const uint32_t cwk = (uint32_t)aw.z;
-        // the particle's live window (plan.cuh: channel_window, exact predicates) cut to the
-        // superblock: channels [cs, ce)
-        const int cs = max((int)(cwk & 0xffffu) - cbase, 0), ce = min((int)(cwk >> 16) + 1 - cbase, nchs);
-        if (cs >= ce) continue;
-        lo = min(lo, cs);
-        hi = max(hi, ce);
-        if (COUNT) n_w += lane == 0;
-        // 64 channels per step: lane l evaluates the edges e0 + l and e0 + 32 + l (two
-        // independent erf chains), the 65th edge of a full step is evaluated by every lane
-        for (int e0 = cs; e0 < ce; e0 += 64) {
-          const int n_here = min(64, ce - e0);
-          const int c1 = e0 + lane, c2 = e0 + 32 + lane;
-          // g orientation (sign folded in): S[c] = E[c+1] - E[c] >= 0; saturated edges at the
-          // ends of the window come out as exactly -1 / +1
-          // (lanes beyond the window's edges skip the evaluation: their table reads would
-          // cost data-pipe wavefronts for nothing)
-          double E1 = 0.0, E2 = 0.0, E3 = 0.0;
-          if (lane <= n_here) {
-            const double t1 = (__ldg(edge + min(c1, nchs)) - v) * sc;
-            E1 = erf_tab_compact(erf_table, t1);
-            if (COUNT) n_erf += fabs(t1) < ERF_SAT;
+      const bool my_nonempty = ne != 0;
+      for (uint32_t q0 = 0; q0 + 1 < total; q0 += 31) {
+        const uint32_t q = q0 + lane;
+        const bool valid = q < total;
+        const int ord = owner_ordinal(q0, my_start, my_nonempty, lane);
+        const int p = owner[valid ? ord : 0];
+        const double2 vs = *reinterpret_cast<const double2*>(&crec[p].v);
+        const int4 aw = *reinterpret_cast<const int4*>(&crec[p].amp);
+        const int cs = aw.z & 0xffff, ce = (int)((uint32_t)aw.z >> 16);
+        const int e = valid ? cs + (int)(q - (uint32_t)aw.w) : 0;  // edge (= channel below it) in the superblock
+        // g orientation (sign folded in): S[c] = E[c+1] - E[c] >= 0; saturated edges at the ends
+        // of the window come out as exactly -1 / +1
+        const double t = (__ldg(edge + e) - vs.x) * vs.y;
+        const double E = erf_tab_compact(erf_table, t);
+        if (COUNT) n_erf += valid && (lane < 31 || q + 1 == total) && fabs(t) < ERF_SAT;
+        const double U = __shfl_down_sync(0xffffffffu, E, 1);  // upper edge of my channel: the next item
+        const bool active = valid && lane < 31 && e < ce;      // (e == ce: the particle's last edge, no channel)
+        const double sval = (U - E) * __hiloint2double(aw.y, aw.x);
+        // DiracDelta kernel: the weight of its one pixel is exactly 1
+        uint32_t todo = __ballot_sync(0xffffffffu, active);
+        while (todo) {
+          const int pl = __shfl_sync(0xffffffffu, p, __ffs(todo) - 1);
+          const bool mine = active && p == pl;
+          if (mine) {
+            acc[e] += sval;
+            if (COUNT) n_upd += sval != 0.0;
           }
-          if (n_here >= 32) {
-            if (lane + 32 <= n_here) {
-              const double t2 = (__ldg(edge + min(c2, nchs)) - v) * sc;
-              E2 = erf_tab_compact(erf_table, t2);
-              if (COUNT) n_erf += fabs(t2) < ERF_SAT;
-            }
-            if (n_here == 64) {
-              const double t3 = (__ldg(edge + e0 + 64) - v) * sc;
-              E3 = erf_tab_compact(erf_table, t3);
-              if (COUNT) n_erf += lane == 0 && fabs(t3) < ERF_SAT;
-            }
-          }
-          // upper edge of each channel: the next lane's value; lane 31 wraps into the next chain
-          double U1 = __shfl_down_sync(0xffffffffu, E1, 1);
-          double U2 = __shfl_down_sync(0xffffffffu, E2, 1);
-          const double E2_0 = __shfl_sync(0xffffffffu, E2, 0);
-          if (lane == 31) {
-            U1 = E2_0;
-            U2 = E3;
-          }
-          if (c1 < ce) {
-            const double s = (U1 - E1) * (amp * __ldg(idv + c1));
-            acc[c1] += s;  // DiracDelta kernel: the weight of its one pixel is exactly 1
-            if (COUNT) n_upd += s != 0.0;
-          }
-          if (c2 < ce) {
-            const double s = (U2 - E2) * (amp * __ldg(idv + c2));
-            acc[c2] += s;
-            if (COUNT) n_upd += s != 0.0;
-          }
+          todo &= ~__ballot_sync(0xffffffffu, mine);
+          __syncwarp();
         }
       }
     }
@@ -184,13 +188,13 @@ __global__ void __launch_bounds__(STREAM_THREADS) column_kernel(const StreamArgs
     if (it.slot >= 0) {
       double* dst = a.partials + (size_t)it.slot * CSB;
       for (int c = lane; c < nchs; c += 32) {
-        dst[c] = acc[c];
+        dst[c] = acc[c] * __ldg(idv + c);
         acc[c] = 0.0;
       }
     } else if (hi > lo) {
       double* dst = a.slab + (size_t)pixel * g.C + cbase;
       for (int c = (lo & ~31) + lane; c < hi; c += 32) {
-        if (c >= lo) dst[c] += acc[c] / a.px_area;
+        if (c >= lo) dst[c] += acc[c] * __ldg(idv + c) / a.px_area;  // 1 / dv of the channel (spectral_models.py:139)
         acc[c] = 0.0;
       }
     }

@@ -85,6 +85,22 @@ inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
     if ((present >> l) & 1u) r += (unsigned)o[l];
   return r;
 }
+inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
+  uint64_t o[32];
+  unsigned present, r = 0xffffffffu;
+  mtn_emu::warp_exchange(mask, v, o, &present);
+  for (int l = 0; l < 32; ++l)
+    if (((present >> l) & 1u) && (unsigned)o[l] < r) r = (unsigned)o[l];
+  return r;
+}
+inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+  uint64_t o[32];
+  unsigned present, r = 0;
+  mtn_emu::warp_exchange(mask, v, o, &present);
+  for (int l = 0; l < 32; ++l)
+    if (((present >> l) & 1u) && (unsigned)o[l] > r) r = (unsigned)o[l];
+  return r;
+}
 inline unsigned __match_any_sync(unsigned mask, unsigned v) {
   uint64_t o[32];
   unsigned present, r = 0;
