@@ -229,6 +229,7 @@ struct ProjSmem {
   SetupBuf sb[2];  // (two: batch b+1 is set up while batch b is evaluated)
   uint64_t bar[2];
   uint32_t item;
+  uint32_t ctr[2][2];  // [batch parity][kernel integrals / edge erfs]: next chunk of phase-A items
 };
 
 // tile pixel (x, y) of pixel j of sub-block s
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
     // pixels of the tile that exist in the slab / cube
     const int x_last = min(x0 + TILE_X, g.x_hi) - 1, y_last = min(y0 + TILE_Y, g.ny) - 1;
 
+    if (tid < 4) sm.ctr[tid >> 1][tid & 1] = 0u;
     for (int e = tid; e <= CB; e += PROJ_THREADS) sm.edge[e] = a.edges[min(max(c0 + e, 0), g.C)];
     for (int c = tid; c < CB; c += PROJ_THREADS)
       sm.inv_dv[c] = (c >= clo && c < nch) ? 1.0 / fabs(a.edges[c0 + c + 1] - a.edges[c0 + c]) : 0.0;
@@ -344,8 +346,19 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         int bx0 = 0, bnx = 0, by0 = 0, bny = 0, cs = 0, ce = 0;
         if (lane < nbb) {
           const Record& r = sm.rec[bb & 1u][lane];
-          const int xa = max(r.i0, x0), xb = min(r.i1, x_last);
-          const int ya = max(r.j0, y0), yb = min(r.j1, y_last);
+          int xa = max(r.i0, x0), xb = min(r.i1, x_last);
+          int ya = max(r.j0, y0), yb = min(r.j1, y_last);
+          // the candidate box is wider than the kernel's round support by up to a pixel on every
+          // side (sm_range = ceil(...)): columns / rows of it with |i - px| >= support hold exact
+          // zeros (R >= support there; the margin of plan.cuh: tile_reached), W stays zero where
+          // nothing is written, so they need not be enumerated
+          const double sup = r.h * g.support[r.kid] * (1.0 + 1.0e-9);
+          if (sup < 1.0e9) {
+            xa = max(xa, (int)ceil(r.px - sup));
+            xb = min(xb, (int)floor(r.px + sup));
+            ya = max(ya, (int)ceil(r.py - sup));
+            yb = min(yb, (int)floor(r.py + sup));
+          }
           if (xa <= xb && ya <= yb) {
             bx0 = xa - x0;
             bnx = xb - xa + 1;
@@ -420,7 +433,14 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         const uint32_t my_start = S.wprefix[lane];
         const bool my_nonempty = S.wprefix[lane + 1] > my_start;
         constexpr int NW = 2;  // independent evaluation chains per lane
-        for (uint32_t q0 = warp * 32 * NW; q0 < total; q0 += PROJ_WARPS * 32 * NW) {
+        // chunks of 32 NW items are handed out through a shared counter: warps 0 and 1 come late
+        // (they set up the next batch first) and chunks differ in cost, so a fixed striping left
+        // the other warps waiting at the barrier below
+        for (;;) {
+          uint32_t q0 = 0;
+          if (lane == 0) q0 = atomicAdd(&sm.ctr[buf][0], 1u) * (32u * NW);
+          q0 = __shfl_sync(0xffffffffu, q0, 0);
+          if (q0 >= total) break;
           int ord[NW];
 #pragma unroll
           for (int u = 0; u < NW; ++u) ord[u] = owner_ordinal(q0 + 32 * u, my_start, my_nonempty, lane);
@@ -471,7 +491,11 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
         const uint32_t total = S.eprefix[PBATCH];
         const uint32_t my_start = S.eprefix[lane];
         const bool my_nonempty = S.eprefix[lane + 1] > my_start;
-        for (uint32_t q0 = warp * 64; q0 < total; q0 += PROJ_WARPS * 64) {
+        for (;;) {
+          uint32_t q0 = 0;
+          if (lane == 0) q0 = atomicAdd(&sm.ctr[buf][1], 1u) * 64u;
+          q0 = __shfl_sync(0xffffffffu, q0, 0);
+          if (q0 >= total) break;
           const int ord[2] = {owner_ordinal(q0, my_start, my_nonempty, lane),
                               owner_ordinal(q0 + 32, my_start, my_nonempty, lane)};
           bool ok[2];
@@ -535,6 +559,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS_PER_SM) project_kernel
       }
       __syncthreads();
 
+      if (tid < 2) sm.ctr[buf ^ 1u][tid] = 0u;  // (last used by batch b - 1; batch b + 1 starts after the barrier below)
       // ---- warp-private list: which particles touch my sub-block.  Lane = particle: W is zero
       // wherever phase A did not write (outside the box) and where the kernel's support ends, so
       // "any of my sub-block's 16 weights non-zero" is the whole test.
